@@ -1,0 +1,336 @@
+"""Drop-in surface: the reference's own callables, same names / argument meaning / return contract, backed by
+the CUDA library through the C-ABI (include/cfnerf_b200.h).
+
+    render_rays   run_nerf_uncertainty_NF.py:457-553
+    run_network   run_nerf_uncertainty_NF.py:67-85
+    raw2outputs   run_nerf_uncertainty_NF.py:411-454
+    sample_pdf    extension (the reference kept only the comment run_nerf_helpers.py:9-11; upstream nerf-pytorch
+                  semantics, specified by oracle/cfnerf_oracle.py::sample_pdf)
+    install(mod)  rebinds `mod.render_rays` / `mod.raw2outputs` so the unmodified `render()` / `train()` use them.
+
+Extra keyword-only arguments (never required by the reference's callers) expose what the reference draws
+implicitly, so tests can inject it: `t_rand`, `eps_alpha`, `eps_rgb`, `u`, and `precision`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check
+from .engine import Engine, _f32c, _ptr, _stream, _unwrap, engine_for
+
+DEFAULT_PRECISION = "bf16"
+
+
+# ------------------------------------------------------------------------------------------------------
+# schedules and latents (host-side plumbing, mirrors the reference lines cited)
+# ------------------------------------------------------------------------------------------------------
+def reference_t_schedule(n_samples: int, device) -> torch.Tensor:
+    """main:510 — the hard-coded 96+32 schedule (the reference requires N_samples == 128, main:516).  For any other
+    N_samples (extension) the upstream linspace(0,1,N) schedule is used.  Computed on the CPU in fp32 like
+    the oracle, then moved: torch's CUDA linspace may differ in the last bit."""
+    if n_samples == 128:
+        t = torch.cat([torch.linspace(0., 0.5, steps=97)[:-1], torch.linspace(0.5, 1., steps=32)], 0)
+    else:
+        t = torch.linspace(0., 1., steps=n_samples)
+    return t.to(device)
+
+
+def test_latents(module, device):
+    """models.py:198-205 — constructor-time draws with the LAST sample's noise forced to zero."""
+    ea = module.sample_alpha.detach().clone().float()
+    er = module.sample_rgb.detach().clone().float()
+    ea[-1] = 0
+    er[-1] = 0
+    return ea.reshape(-1).to(device).contiguous(), er.to(device).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------
+# stand-alone kernels
+# ------------------------------------------------------------------------------------------------------
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False):
+    """main:411-454.  raw (B,N,K,4), z_vals (B,N), rays_d (B,3) -> rgb_map (B,3,K), disp_map (B,K),
+    weights (B,N,K), depth_map (B,K).  `raw_noise_std` only consumes RNG in the reference (the noise is never
+    added, main:432-442); it is accepted and ignored."""
+    lib = _lib.load()
+    if not raw.is_cuda:
+        raise RuntimeError("cfnerf_b200.raw2outputs needs CUDA tensors (no CPU fallback)")
+    dev = raw.device
+    raw, z_vals, rays_d = _f32c(raw, dev), _f32c(z_vals, dev), _f32c(rays_d, dev)
+    B, N, K, four = raw.shape
+    assert four == 4 and z_vals.shape == (B, N) and rays_d.shape == (B, 3)
+    f32 = dict(dtype=torch.float32, device=dev)
+    rgb, disp = torch.empty(B, 3, K, **f32), torch.empty(B, K, **f32)
+    w, depth = torch.empty(B, N, K, **f32), torch.empty(B, K, **f32)
+    with torch.cuda.device(dev):
+        check(lib.cfn_raw2outputs_f32(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, int(bool(white_bkgd)), _ptr(rgb),
+                                      _ptr(disp), _ptr(w), _ptr(depth), B, N, K, _stream()), "cfn_raw2outputs_f32")
+    return rgb, disp, w, depth
+
+
+def sample_pdf(bins, weights, N_samples, det=False, pytest=False, *, u=None, return_below=False):
+    """Upstream signature `sample_pdf(bins, weights, N_samples, det, pytest)`.  bins (B,M), weights (B,M-1) ->
+    samples (B,N_samples); `u` (B,N_samples) overrides the uniforms (det -> linspace(0,1,N), else torch.rand)."""
+    lib = _lib.load()
+    dev = bins.device
+    if dev.type != "cuda":
+        raise RuntimeError("cfnerf_b200.sample_pdf needs CUDA tensors (no CPU fallback)")
+    bins, weights = _f32c(bins, dev), _f32c(weights, dev)
+    B, M = bins.shape
+    assert weights.shape == (B, M - 1)
+    if u is None:
+        if det:
+            u = torch.linspace(0., 1., steps=N_samples).to(dev).expand(B, N_samples)
+        else:
+            u = torch.rand(B, N_samples, device=dev)
+    u = _f32c(u, dev)
+    out = torch.empty(B, N_samples, dtype=torch.float32, device=dev)
+    below = torch.empty(B, N_samples, dtype=torch.int32, device=dev) if return_below else None
+    with torch.cuda.device(dev):
+        check(lib.cfn_sample_pdf_f32(_ptr(bins), _ptr(weights), _ptr(u), _ptr(out), _ptr(below), B, M, N_samples,
+                                     _stream()), "cfn_sample_pdf_f32")
+    return (out, below) if return_below else out
+
+
+def merge_sorted(z_a, z_b):
+    """sort(cat[z_a, z_b], -1) per ray."""
+    lib = _lib.load()
+    dev = z_a.device
+    z_a, z_b = _f32c(z_a, dev), _f32c(z_b, dev)
+    B, Na = z_a.shape
+    Nb = z_b.shape[1]
+    out = torch.empty(B, Na + Nb, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cfn_merge_sorted_f32(_ptr(z_a), _ptr(z_b), _ptr(out), B, Na, Nb, _stream()), "cfn_merge_sorted_f32")
+    return out
+
+
+def mean_over_k(w):
+    lib = _lib.load()
+    dev = w.device
+    w = _f32c(w, dev)
+    rows, K = w.numel() // w.shape[-1], w.shape[-1]
+    out = torch.empty(w.shape[:-1], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cfn_mean_over_k_f32(_ptr(w), _ptr(out), rows, K, _stream()), "cfn_mean_over_k_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# training: one autograd node around network + flows + compositing
+# ------------------------------------------------------------------------------------------------------
+class _RenderTrainFn(torch.autograd.Function):
+    """forward: cfn_network_fwd(save) + cfn_flow_composite_fwd(train); backward: cfn_flow_composite_bwd +
+    cfn_network_bwd.  The parameters are inputs so that autograd writes into the reference module's own .grad."""
+
+    @staticmethod
+    def forward(ctx, eng: Engine, rays, z_vals, eps_a, eps_c, white_bkgd, want_weights, *params):
+        B, N = z_vals.shape
+        fp, ws = eng.network(B, N, rays=rays, z_vals=z_vals, save=True)
+        out = eng.flow_composite(fp, z_vals, rays[:, 3:6], 11, eps_a, eps_c, white_bkgd, want_raw=True,
+                                 want_weights=want_weights, train=True)
+        ctx.eng, ctx.white_bkgd = eng, white_bkgd
+        ctx.save_for_backward(rays, z_vals, eps_a, eps_c, fp, ws)
+        ld = out["logdet_sums"].sum(0)  # totals over rays: (2,)
+        w = out["weights"] if want_weights else torch.empty(0, device=rays.device)
+        ctx.mark_non_differentiable(out["disp_map"], out["raw"], w)
+        return out["rgb_map"], out["disp_map"], out["depth_map"], out["raw"], ld, w
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_disp, g_depth, g_raw, g_ld, g_w):
+        eng = ctx.eng
+        rays, z_vals, eps_a, eps_c, fp, ws = ctx.saved_tensors
+        B, N = z_vals.shape
+        dev = rays.device
+        g_rgb = _f32c(g_rgb, dev) if g_rgb is not None else torch.zeros(B, 3, eng.K, device=dev)
+        g_depth = _f32c(g_depth, dev) if g_depth is not None else None
+        gl = g_ld.detach().float().cpu().tolist() if g_ld is not None else [0.0, 0.0]
+        with torch.cuda.device(dev):
+            g_fp, g_glob = eng.flow_composite_bwd(fp, z_vals, rays[:, 3:6], 11, eps_a, eps_c, ctx.white_bkgd, g_rgb,
+                                                  g_depth, gl[0], gl[1])
+            grads = eng.network_bwd(g_fp, B, N, ws)
+        gg = g_glob.sum(0)
+        grads[0], grads[1] = gg[0:1], gg[1:2]
+        grads[2], grads[3] = gg[2:5], gg[5:8]
+        grads = [g.reshape(p.shape) for g, p in zip(grads, eng.params)]
+        return (None, None, None, None, None, None, None, *grads)
+
+
+def _entropy_base_terms(module, eps_a, eps_c):
+    """base log-densities of models.py:268/283 (no 2*pi term), written like the reference so autograd gives the same
+    gradient for the global std parameters."""
+    a_mean, a_std = module.alpha_mean, module.alpha_std
+    c_mean, c_std = module.rgb_mean, module.rgb_std
+    a0 = eps_a.reshape(-1, 1) * a_std[None, :] + a_mean[None, :]
+    c0 = eps_c * c_std[None, :] + c_mean[None, :]
+    base_a = -0.5 * (a_std.log() * 2 + (a0 - a_mean) * (a0 - a_mean) * (a_std ** 2).reciprocal())
+    base_c = -0.5 * (c_std.log() * 2 + (c0 - c_mean) * (c0 - c_mean) * (c_std ** 2).reciprocal())
+    return base_a.mean(), base_c.mean()
+
+
+# ------------------------------------------------------------------------------------------------------
+# run_network / render_rays
+# ------------------------------------------------------------------------------------------------------
+def run_network(inputs, viewdirs, fn, is_val, is_test, embed_fn=None, embeddirs_fn=None, netchunk=1024 * 64, *,
+                eps_alpha=None, eps_rgb=None, precision=None):
+    """main:67-85.  inputs (B,N,3), viewdirs (B,3) -> (outputs (B,N,K,4) [rgb|sigma raw], loss_entropy).
+    `embed_fn` / `embeddirs_fn` / `netchunk` are accepted for signature compatibility: the encoding is fused into the
+    network kernel and chunking "does not affect final results" (main:112-113).  Test mode returns zeros for
+    loss_entropy like the reference (models.py:223); train mode returns the entropy scalar broadcast to (B*N,K,1)
+    (models.py:291) — use render_rays for a differentiable training step."""
+    module = _unwrap(fn)
+    dev = inputs.device
+    eng = engine_for(fn, dev, precision or DEFAULT_PRECISION)
+    B, N = inputs.shape[0], inputs.shape[1]
+    pts = _f32c(inputs.reshape(-1, 3), dev)
+    if viewdirs is None:
+        raise ValueError("the reference model requires use_viewdirs (model/models.py:63-64)")
+    vd = _f32c(viewdirs.reshape(-1, 3), dev)
+    if vd.shape[0] != B:
+        raise ValueError("viewdirs must be (B,3): one direction per ray (main:74-76)")
+    train = not is_test
+    if eps_alpha is None:
+        if train:
+            eps_alpha = torch.empty([eng.K, 1], device=dev).normal_()      # models.py:234
+            eps_rgb = torch.empty([eng.K, 3], device=dev).normal_()        # models.py:246
+        else:
+            eps_alpha, eps_rgb = test_latents(module, dev)
+    eps_a, eps_c = _f32c(eps_alpha.reshape(-1), dev), _f32c(eps_rgb, dev)
+    with torch.cuda.device(dev), torch.no_grad():
+        fp = eng.network(B, N, pts=pts, viewdirs=vd)
+        # raw comes out of the flow stage; compositing outputs are discarded here (z/dirs are dummies)
+        z_dummy = torch.zeros(B, N, device=dev)
+        out = eng.flow_composite(fp, z_dummy, vd, 3, eps_a, eps_c, False, want_raw=True, train=train)
+    raw = out["raw"]
+    if not train:
+        return raw, torch.zeros_like(raw)
+    with torch.no_grad():
+        base_a, base_c = _entropy_base_terms(module, eps_a, eps_c)
+        ld = out["logdet_sums"].sum(0) / float(B * N * eng.K)
+        ent = base_a - ld[0] + base_c - ld[1]
+    return raw, ent.expand(B * N, eng.K, 1)
+
+
+def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=128, is_train=False, uniformsample=False,
+                retraw=False, lindisp=False, K_samples=0, perturb=0., N_importance=0, network_fine=None,
+                white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False, *, t_rand=None, eps_alpha=None,
+                eps_rgb=None, u=None, precision=None, want_weights=False, want_kstats=False):
+    """main:457-553, plus the coarse+fine extension when N_importance > 0 and network_fine is given.
+
+    Returns the reference dict: rgb_map (B,3,K), disp_map (B,K), depth_map (B,K); when is_train also raw
+    (B,N,K,4), loss_entropy (B*N,K,1) (the per-call scalar broadcast, models.py:291) and pts (B,N,3).
+    `network_query_fn` is accepted and ignored (encoding + chunking are fused)."""
+    module = _unwrap(network_fn)
+    dev = ray_batch.device
+    prec = precision or DEFAULT_PRECISION
+    if is_train:
+        prec = "fp32" if precision is None else precision  # round 1: the training path runs the fp32 GEMMs
+    eng = engine_for(network_fn, dev, prec)
+    if K_samples and K_samples != eng.K:
+        raise ValueError(f"K_samples={K_samples} but the network was built with K={eng.K}")
+    rays = _f32c(ray_batch, dev)
+    if rays.shape[-1] != 11:
+        raise ValueError("ray_batch must be (B,11) = [o d near far viewdir] (use_viewdirs, main:504-507)")
+    B = rays.shape[0]
+    hier = N_importance > 0 and network_fine is not None
+    with torch.cuda.device(dev):
+        t_vals = reference_t_schedule(N_samples, dev)
+        if perturb > 0. and t_rand is None:
+            t_rand = torch.rand(B, N_samples, device=dev)                                     # main:524
+            if pytest:
+                import numpy as np
+                t_rand = torch.Tensor(np.random.rand(B, N_samples)).to(dev)                  # main:527-530
+        if t_rand is not None:
+            t_rand = _f32c(t_rand, dev)
+        z_vals = eng.zvals(rays, t_vals, t_rand if perturb > 0. or t_rand is not None else None, lindisp)
+        if eps_alpha is None:
+            if is_train:
+                eps_alpha = torch.empty([eng.K, 1], device=dev).normal_()                     # models.py:234
+                eps_rgb = torch.empty([eng.K, 3], device=dev).normal_()                       # models.py:246
+            else:
+                eps_alpha, eps_rgb = test_latents(module, dev)
+        eps_a, eps_c = _f32c(eps_alpha.reshape(-1), dev), _f32c(eps_rgb, dev)
+        if is_train and raw_noise_std > 0.:
+            # the reference draws noise here and never adds it (main:432-442); same count keeps the RNG stream aligned
+            torch.randn(B, N_samples, eng.K, device=dev)
+
+        def one_pass(net, z, train, need_w):
+            e = engine_for(net, dev, prec)
+            N = z.shape[1]
+            if train:
+                rgb, disp, depth, raw, ld, w = _RenderTrainFn.apply(e, rays, z, eps_a, eps_c, bool(white_bkgd),
+                                                                    need_w, *e.params)
+                base_a, base_c = _entropy_base_terms(_unwrap(net), eps_a, eps_c)
+                cnt = float(B * N * e.K)
+                ent = base_a - ld[0] / cnt + base_c - ld[1] / cnt                             # models.py:286
+                return dict(rgb_map=rgb, disp_map=disp, depth_map=depth, raw=raw, weights=w if need_w else None,
+                            loss_entropy=ent)
+            with torch.no_grad():
+                fp = e.network(B, N, rays=rays, z_vals=z)
+                return e.flow_composite(fp, z, rays[:, 3:6], 11, eps_a, eps_c, bool(white_bkgd),
+                                        want_raw=False, want_weights=need_w, want_kstats=want_kstats)
+
+        if not hier:
+            o = one_pass(network_fn, z_vals, is_train, want_weights)
+            ret = {"rgb_map": o["rgb_map"], "disp_map": o["disp_map"], "depth_map": o["depth_map"]}
+            if want_weights:
+                ret["weights"] = o["weights"]
+            if want_kstats and o.get("kstats") is not None:
+                ret["kstats"] = o["kstats"]
+            N = N_samples
+        else:
+            oc = one_pass(network_fn, z_vals, is_train, True)
+            with torch.no_grad():
+                w_mean = mean_over_k(oc["weights"])                                            # (B,Nc): shared fine grid
+                z_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+                z_samples = sample_pdf(z_mid, w_mean[..., 1:-1], N_importance, det=(perturb == 0.), pytest=pytest,
+                                       u=u)
+                z_all = merge_sorted(z_vals, z_samples)
+            o = one_pass(network_fine, z_all, is_train, want_weights)
+            ret = {"rgb_map": o["rgb_map"], "disp_map": o["disp_map"], "depth_map": o["depth_map"],
+                   "rgb0": oc["rgb_map"], "disp0": oc["disp_map"], "depth0": oc["depth_map"],
+                   "z_samples": z_samples, "z_vals": z_all}
+            if want_weights:
+                ret["weights"] = o["weights"]
+            if want_kstats and o.get("kstats") is not None:
+                ret["kstats"] = o["kstats"]
+            if is_train:
+                ret["loss_entropy0"] = oc["loss_entropy"].expand(B * N_samples, eng.K, 1)
+            z_vals = z_all
+            N = z_all.shape[1]
+        if is_train:
+            ret["raw"] = o["raw"]
+            ret["loss_entropy"] = o["loss_entropy"].expand(B * N, eng.K, 1)                    # models.py:291
+            ret["pts"] = rays[:, None, 0:3] + rays[:, None, 3:6] * z_vals[..., :, None]       # main:534
+    return ret
+
+
+def install(ref_module, precision: str | None = None):
+    """Rebind the reference's module-global names: `batchify_rays` looks `render_rays` up by global
+    name (main:93) and `render_rays` looks `raw2outputs` up the same way (main:540)."""
+    global DEFAULT_PRECISION
+    if precision is not None:
+        DEFAULT_PRECISION = precision
+    ref_module.render_rays = render_rays
+    ref_module.raw2outputs = raw2outputs
+    return ref_module
+
+
+# ------------------------------------------------------------------------------------------------------
+# A11: the caller's K-reduction and KDE-NLL loss (main:1027-1050), kept in torch for round 1
+# ------------------------------------------------------------------------------------------------------
+def kde_nll_loss(rgb_map, target, loss_entropy, K, beta1=0.01):
+    eps = 1e-05
+    rgb_mean = rgb_map.mean(-1)
+    mse = torch.mean((rgb_mean - target) ** 2)
+    psnr = -10. * torch.log(mse) / math.log(10.)
+    rgb_std = torch.std(rgb_map, -1) * K / (K - 1)                                            # main:1034
+    h = (rgb_std.detach() * (0.8 / K) ** (-1. / 7.) + eps)[..., None]                         # main:1036
+    p1 = torch.exp(-((rgb_map - target[..., None]) ** 2) / (2 * h * h))
+    p2 = (2 * math.pi) ** (-1.5) / h
+    nll = -torch.log((p1 * p2).mean(-1) + eps).mean()
+    loss = nll + beta1 * loss_entropy.mean() if beta1 else nll
+    return {"loss": loss, "loss_nll": nll, "mse": mse, "psnr": psnr}

@@ -1,0 +1,289 @@
+// C-ABI entry points (include/cfnerf_b200.h): handle lifetime, parameter table, argument checking and
+// dispatch to the kernels.  No torch types, no hidden device allocation outside create/pack.
+#include <stdarg.h>
+#include <string.h>
+
+#include "handle.h"
+
+namespace cfn {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace cfn
+
+using namespace cfn;
+
+extern "C" const char* cfn_last_error(void) { return g_err; }
+extern "C" int cfn_version(void) { return 100; }
+
+static void add_slot(CfnHandle* h, const std::string& name, int rows, int cols) {
+  ParamSlot s;
+  s.name = name;
+  s.rows = rows;
+  s.cols = cols;
+  s.numel = (int64_t)rows * cols;
+  s.offset = h->n_floats;
+  h->n_floats += s.numel;
+  h->slots.push_back(s);
+}
+static int add_linear(CfnHandle* h, const std::string& name, int out_f, int in_f) {
+  int idx = (int)h->slots.size();
+  add_slot(h, name + ".weight", out_f, in_f);
+  add_slot(h, name + ".bias", out_f, 1);
+  return idx;
+}
+
+extern "C" int cfn_create(const CfnConfig* cfg, CfnHandle** out) {
+  CFN_CHECK_ARG(cfg && out, "cfn_create: null argument");
+  CFN_CHECK_ARG(cfg->D >= 3 && cfg->D <= 16, "netdepth %d unsupported (3..16)", cfg->D);
+  CFN_CHECK_ARG(cfg->W >= 16 && cfg->W % 2 == 0, "netwidth %d unsupported", cfg->W);
+  CFN_CHECK_ARG(cfg->L_pos >= 0 && cfg->L_pos <= 16 && cfg->L_dir >= 0 && cfg->L_dir <= 16, "multires unsupported");
+  CFN_CHECK_ARG(cfg->h_alpha >= 1 && cfg->h_rgb >= 1, "h sizes must be positive");
+  CFN_CHECK_ARG(cfg->F >= 1 && cfg->F <= 8, "n_flows %d unsupported (1..8)", cfg->F);
+  CFN_CHECK_ARG(cfg->K >= 1 && cfg->K <= 1024, "K_samples %d unsupported", cfg->K);
+  CFN_CHECK_ARG(cfg->precision >= CFN_PREC_FP32 && cfg->precision <= CFN_PREC_FP16, "unknown precision mode");
+  CfnHandle* h = new CfnHandle();
+  h->cfg = *cfg;
+  h->in_pos = 3 + 6 * cfg->L_pos;
+  h->in_dir = 3 + 6 * cfg->L_dir;
+  h->PP = 18 * cfg->F;
+  // skips=[netdepth/2] with true division (main:327): only an even depth produces an integer layer index
+  h->skip = (cfg->D % 2 == 0 && cfg->D / 2 <= cfg->D - 2) ? cfg->D / 2 : -1;
+  h->n_floats = 0;
+  h->packed = false;
+  h->tc = nullptr;
+  const int W = cfg->W, F = cfg->F;
+  add_slot(h, "alpha_mean", 1, 1);
+  add_slot(h, "alpha_std", 1, 1);
+  add_slot(h, "rgb_mean", 3, 1);
+  add_slot(h, "rgb_std", 3, 1);
+  for (int i = 0; i < cfg->D; ++i) {
+    int fin = (i == 0) ? h->in_pos : ((h->skip >= 0 && i == h->skip + 1) ? W + h->in_pos : W);
+    add_linear(h, "pts_linears." + std::to_string(i), W, fin);
+  }
+  h->s_views = add_linear(h, "views_linears.0", W / 2, W + h->in_dir);
+  h->s_feat = add_linear(h, "feature_linear", W, W);
+  h->s_halpha = add_linear(h, "h_alpha_linear", cfg->h_alpha, W);
+  h->s_hrgb = add_linear(h, "h_rgb_linear", cfg->h_rgb, W / 2);
+  h->s_frgb = add_linear(h, "flows_rgb.amor_d", F * 9, cfg->h_rgb);
+  add_linear(h, "flows_rgb.amor_diag1.0", F * 3, cfg->h_rgb);
+  add_linear(h, "flows_rgb.amor_diag2.0", F * 3, cfg->h_rgb);
+  add_linear(h, "flows_rgb.amor_b", F * 3, cfg->h_rgb);
+  h->s_falpha = add_linear(h, "flows_alpha.amor_d", F, cfg->h_alpha);
+  add_linear(h, "flows_alpha.amor_diag1.0", F, cfg->h_alpha);
+  add_linear(h, "flows_alpha.amor_diag2.0", F, cfg->h_alpha);
+  add_linear(h, "flows_alpha.amor_b", F, cfg->h_alpha);
+
+  // gather tables: packed record row -> (source linear, row, tanh?)   (models.py:366-385)
+  const int fa = h->s_falpha, fc = h->s_frgb;
+  for (int f = 0; f < F; ++f) h->gatherA.push_back({fa + 2, fa + 3, f, 1});   // d1[f] = tanh(amor_diag1)[0,f]
+  for (int f = 0; f < F; ++f) h->gatherA.push_back({fa + 4, fa + 5, f, 1});   // d2[f]
+  for (int f = 0; f < F; ++f) h->gatherA.push_back({fa + 6, fa + 7, f, 0});   // b[f]
+  for (int f = 0; f < F; ++f) {
+    auto D = [&](int i, int j) { return GatherRow{fc + 0, fc + 1, (i * 3 + j) * F + f, 0}; };
+    auto d1 = [&](int i) { return GatherRow{fc + 2, fc + 3, i * F + f, 1}; };
+    auto d2 = [&](int i) { return GatherRow{fc + 4, fc + 5, i * F + f, 1}; };
+    auto bb = [&](int i) { return GatherRow{fc + 6, fc + 7, i * F + f, 0}; };
+    // R1: upper triangle of D, tanh'ed diag1 on the diagonal
+    h->gatherC.push_back(d1(0)); h->gatherC.push_back(D(0, 1)); h->gatherC.push_back(D(0, 2));
+    h->gatherC.push_back(d1(1)); h->gatherC.push_back(D(1, 2)); h->gatherC.push_back(d1(2));
+    // R2: upper triangle of D^T, tanh'ed diag2 on the diagonal
+    h->gatherC.push_back(d2(0)); h->gatherC.push_back(D(1, 0)); h->gatherC.push_back(D(2, 0));
+    h->gatherC.push_back(d2(1)); h->gatherC.push_back(D(2, 1)); h->gatherC.push_back(d2(2));
+    h->gatherC.push_back(bb(0)); h->gatherC.push_back(bb(1)); h->gatherC.push_back(bb(2));
+  }
+
+  auto fail = [&](const char* what) {
+    set_error("cfn_create: %s", what);
+    cfn_destroy(h);
+    return CFN_ECUDA;
+  };
+  h->w32 = h->amA = h->amA_b = h->amC = h->amC_b = h->tanh_flags = nullptr;
+  h->gatherA_dev = h->gatherC_dev = nullptr;
+  h->grads_table_dev = nullptr;
+  if (cudaMalloc(&h->grads_table_dev, 64 * sizeof(float*)) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMalloc(&h->w32, h->n_floats * sizeof(float)) != cudaSuccess) return fail("cudaMalloc(w32)");
+  h->globals = h->w32;
+  if (cudaMalloc(&h->amA, (size_t)3 * F * cfg->h_alpha * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMalloc(&h->amA_b, (size_t)3 * F * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMalloc(&h->amC, (size_t)15 * F * cfg->h_rgb * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMalloc(&h->amC_b, (size_t)15 * F * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMalloc(&h->tanh_flags, (size_t)h->PP * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMalloc(&h->gatherA_dev, h->gatherA.size() * sizeof(GatherRow)) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMalloc(&h->gatherC_dev, h->gatherC.size() * sizeof(GatherRow)) != cudaSuccess) return fail("cudaMalloc");
+  std::vector<float> flags;
+  for (auto& g : h->gatherA) flags.push_back((float)g.tanh);
+  for (auto& g : h->gatherC) flags.push_back((float)g.tanh);
+  if (cudaMemcpy(h->tanh_flags, flags.data(), flags.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->gatherA_dev, h->gatherA.data(), h->gatherA.size() * sizeof(GatherRow), cudaMemcpyHostToDevice) !=
+          cudaSuccess ||
+      cudaMemcpy(h->gatherC_dev, h->gatherC.data(), h->gatherC.size() * sizeof(GatherRow), cudaMemcpyHostToDevice) !=
+          cudaSuccess)
+    return fail("cudaMemcpy(tables)");
+  if (cfg->precision != CFN_PREC_FP32) {
+    int rc = tc_create(h);
+    if (rc != CFN_OK) {
+      cfn_destroy(h);
+      return rc;
+    }
+  }
+  *out = h;
+  return CFN_OK;
+}
+
+extern "C" int cfn_destroy(CfnHandle* h) {
+  if (!h) return CFN_OK;
+  if (h->tc) tc_destroy(h);
+  cudaFree(h->w32);
+  cudaFree(h->amA);
+  cudaFree(h->amA_b);
+  cudaFree(h->amC);
+  cudaFree(h->amC_b);
+  cudaFree(h->tanh_flags);
+  cudaFree(h->gatherA_dev);
+  cudaFree(h->gatherC_dev);
+  cudaFree(h->grads_table_dev);
+  delete h;
+  return CFN_OK;
+}
+
+extern "C" int cfn_param_count(const CfnHandle* h) { return h ? (int)h->slots.size() : 0; }
+extern "C" const char* cfn_param_name(const CfnHandle* h, int i) {
+  if (!h || i < 0 || i >= (int)h->slots.size()) return nullptr;
+  return h->slots[i].name.c_str();
+}
+extern "C" int64_t cfn_param_numel(const CfnHandle* h, int i) {
+  if (!h || i < 0 || i >= (int)h->slots.size()) return -1;
+  return h->slots[i].numel;
+}
+extern "C" int cfn_flow_param_width(const CfnHandle* h) { return h ? h->PP : 0; }
+
+extern "C" int cfn_pack_weights(CfnHandle* h, const float* const* params, int n_params, void* stream) {
+  CFN_CHECK_ARG(h && params, "cfn_pack_weights: null argument");
+  CFN_CHECK_ARG(n_params == (int)h->slots.size(), "cfn_pack_weights: expected %d tensors, got %d",
+                (int)h->slots.size(), n_params);
+  for (int i = 0; i < n_params; ++i) CFN_CHECK_ARG(params[i] != nullptr, "cfn_pack_weights: tensor %d is null", i);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = pack_fp32(h, params, s);
+  if (rc != CFN_OK) return rc;
+  if (h->tc) {
+    rc = tc_pack(h, s);
+    if (rc != CFN_OK) return rc;
+  }
+  h->packed = true;
+  return CFN_OK;
+}
+
+extern "C" int cfn_workspace_bytes(const CfnHandle* h, int64_t n_points, int save_for_backward, size_t* out) {
+  CFN_CHECK_ARG(h && out && n_points >= 0, "cfn_workspace_bytes: bad argument");
+  if (h->tc && !save_for_backward) {
+    *out = tc_workspace_bytes(h, n_points);
+    return CFN_OK;
+  }
+  *out = fp32_workspace_floats(h, n_points, save_for_backward) * sizeof(float) + 256;
+  return CFN_OK;
+}
+
+extern "C" int cfn_zvals_f32(const float* rays, const float* t_vals, const float* t_rand, int lindisp, float* z_vals,
+                             int64_t B, int N, void* stream) {
+  CFN_CHECK_ARG(rays && t_vals && z_vals && B >= 0 && N >= 1, "cfn_zvals_f32: bad argument");
+  return launch_zvals(rays, t_vals, t_rand, lindisp, z_vals, B, N, (cudaStream_t)stream);
+}
+
+extern "C" int cfn_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts,
+                               const float* viewdirs, int64_t B, int N, float* flow_params, void* workspace,
+                               size_t workspace_bytes, int save_for_backward, void* stream) {
+  CFN_CHECK_ARG(h && flow_params && B >= 0 && N >= 1, "cfn_network_fwd: bad argument");
+  CFN_CHECK_ARG((pts && viewdirs) || (rays && z_vals), "cfn_network_fwd: need (pts, viewdirs) or (rays, z_vals)");
+  if (!h->packed) {
+    set_error("cfn_network_fwd: call cfn_pack_weights first");
+    return CFN_ESTATE;
+  }
+  if (B == 0) return CFN_OK;
+  size_t need = 0;
+  cfn_workspace_bytes(h, B * N, save_for_backward, &need);
+  if (workspace_bytes < need || (!workspace && need)) {
+    set_error("cfn_network_fwd: workspace %zu bytes < required %zu", workspace_bytes, need);
+    return CFN_ENOMEM;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->tc && !save_for_backward)
+    return tc_network_fwd(h, rays, z_vals, pts, viewdirs, B, N, flow_params, workspace, workspace_bytes, s);
+  return fp32_network_fwd(h, rays, z_vals, pts, viewdirs, B, N, flow_params, (float*)workspace, save_for_backward, s);
+}
+
+extern "C" int cfn_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, void* workspace,
+                               size_t workspace_bytes, float* const* grads, int n_params, void* stream) {
+  CFN_CHECK_ARG(h && g_flow_params && grads && workspace, "cfn_network_bwd: null argument");
+  CFN_CHECK_ARG(n_params == (int)h->slots.size(), "cfn_network_bwd: expected %d tensors", (int)h->slots.size());
+  size_t need = 0;
+  cfn_workspace_bytes(h, B * N, 1, &need);
+  if (workspace_bytes < need) {
+    set_error("cfn_network_bwd: workspace %zu bytes < required %zu", workspace_bytes, need);
+    return CFN_ENOMEM;
+  }
+  return fp32_network_bwd(h, g_flow_params, B, N, (float*)workspace, grads, (cudaStream_t)stream);
+}
+
+extern "C" int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, const float* z_vals,
+                                      const float* rays_d, int rays_d_stride, const float* eps_alpha,
+                                      const float* eps_rgb, int64_t B, int N, int white_bkgd, float* rgb_map,
+                                      float* disp_map, float* depth_map, float* raw, float* weights,
+                                      float* logdet_sums, float* kstats, void* stream) {
+  CFN_CHECK_ARG(h && flow_params && z_vals && rays_d && eps_alpha && eps_rgb && rgb_map && disp_map && depth_map,
+                "cfn_flow_composite_fwd: null argument");
+  if (!h->packed) {
+    set_error("cfn_flow_composite_fwd: call cfn_pack_weights first");
+    return CFN_ESTATE;
+  }
+  return launch_flow_composite_fwd(h->cfg.F, h->cfg.K, h->globals, flow_params, z_vals, rays_d, rays_d_stride,
+                                   eps_alpha, eps_rgb, B, N, white_bkgd, rgb_map, disp_map, depth_map, raw, weights,
+                                   logdet_sums, kstats, (cudaStream_t)stream);
+}
+
+extern "C" int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, const float* z_vals,
+                                      const float* rays_d, int rays_d_stride, const float* eps_alpha,
+                                      const float* eps_rgb, int64_t B, int N, int white_bkgd, const float* g_rgb_map,
+                                      const float* g_depth_map, float g_logdet_alpha, float g_logdet_rgb,
+                                      float* g_flow_params, float* g_globals_partial, void* stream) {
+  CFN_CHECK_ARG(h && flow_params && z_vals && rays_d && eps_alpha && eps_rgb && g_rgb_map && g_flow_params &&
+                    g_globals_partial,
+                "cfn_flow_composite_bwd: null argument");
+  if (!h->packed) {
+    set_error("cfn_flow_composite_bwd: call cfn_pack_weights first");
+    return CFN_ESTATE;
+  }
+  return launch_flow_composite_bwd(h->cfg.F, h->cfg.K, h->globals, flow_params, z_vals, rays_d, rays_d_stride,
+                                   eps_alpha, eps_rgb, B, N, white_bkgd, g_rgb_map, g_depth_map, g_logdet_alpha,
+                                   g_logdet_rgb, g_flow_params, g_globals_partial, (cudaStream_t)stream);
+}
+
+extern "C" int cfn_raw2outputs_f32(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
+                                   int white_bkgd, float* rgb_map, float* disp_map, float* weights,
+                                   float* depth_map, int64_t B, int N, int K, void* stream) {
+  CFN_CHECK_ARG(raw && z_vals && rays_d && rgb_map && disp_map && depth_map && B >= 0,
+                "cfn_raw2outputs_f32: null argument");
+  return launch_raw2outputs(raw, z_vals, rays_d, rays_d_stride, white_bkgd, rgb_map, disp_map, weights, depth_map, B,
+                            N, K, (cudaStream_t)stream);
+}
+
+extern "C" int cfn_sample_pdf_f32(const float* bins, const float* weights, const float* u, float* samples,
+                                  int32_t* below, int64_t B, int M, int Nf, void* stream) {
+  CFN_CHECK_ARG(bins && weights && u && samples && B >= 0, "cfn_sample_pdf_f32: null argument");
+  return launch_sample_pdf(bins, weights, u, samples, below, B, M, Nf, (cudaStream_t)stream);
+}
+
+extern "C" int cfn_merge_sorted_f32(const float* a, const float* b, float* out, int64_t B, int Na, int Nb,
+                                    void* stream) {
+  CFN_CHECK_ARG(a && b && out && B >= 0, "cfn_merge_sorted_f32: null argument");
+  return launch_merge_sorted(a, b, out, B, Na, Nb, (cudaStream_t)stream);
+}
+
+extern "C" int cfn_mean_over_k_f32(const float* w, float* out, int64_t rows, int K, void* stream) {
+  CFN_CHECK_ARG(w && out && rows >= 0 && K >= 1, "cfn_mean_over_k_f32: bad argument");
+  return launch_mean_over_k(w, out, rows, K, (cudaStream_t)stream);
+}

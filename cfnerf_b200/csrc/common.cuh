@@ -1,0 +1,78 @@
+// Shared declarations of the cfnerf_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cfnerf_b200.h"
+
+namespace cfn {
+
+void set_error(const char* fmt, ...);
+
+#define CFN_CHECK_ARG(cond, ...)          \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::cfn::set_error(__VA_ARGS__);      \
+      return CFN_EINVAL;                  \
+    }                                     \
+  } while (0)
+
+#define CFN_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::cfn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CFN_ECUDA;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+#define CFN_LAUNCH_CHECK() CFN_CUDA(cudaGetLastError())
+
+// ---- accurate fp32 math used by every non-GEMM kernel (no fast-math anywhere) -----------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// F.softplus(beta=1, threshold=20) (run_nerf_uncertainty_NF.py:424)
+__device__ __forceinline__ float softplusf_(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+
+// flow-parameter record per 3-D point: [alpha d1[F] | alpha d2[F] | alpha b[F] | rgb flow 0 (15) | ... ]
+// rgb flow f (15): R1_00 R1_01 R1_02 R1_11 R1_12 R1_22 | R2_00 R2_01 R2_02 R2_11 R2_12 R2_22 | b0 b1 b2
+constexpr int kRgbFlowRec = 15;
+__host__ __device__ inline int flow_param_width(int F) { return 18 * F; }
+
+// ---- kernels implemented across the .cu files ----------------------------------------------------
+int launch_zvals(const float* rays, const float* t_vals, const float* t_rand, int lindisp, float* z_vals, int64_t B,
+                 int N, cudaStream_t s);
+int launch_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride, int white_bkgd,
+                       float* rgb_map, float* disp_map, float* weights, float* depth_map, int64_t B, int N, int K,
+                       cudaStream_t s);
+int launch_sample_pdf(const float* bins, const float* weights, const float* u, float* samples, int32_t* below,
+                      int64_t B, int M, int Nf, cudaStream_t s);
+int launch_merge_sorted(const float* a, const float* b, float* out, int64_t B, int Na, int Nb, cudaStream_t s);
+int launch_mean_over_k(const float* w, float* out, int64_t rows, int K, cudaStream_t s);
+
+int launch_flow_composite_fwd(int F, int K, const float* globals, const float* flow_params, const float* z_vals,
+                              const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
+                              int64_t B, int N, int white_bkgd, float* rgb_map, float* disp_map, float* depth_map,
+                              float* raw, float* weights, float* logdet_sums, float* kstats, cudaStream_t s);
+int launch_flow_composite_bwd(int F, int K, const float* globals, const float* flow_params, const float* z_vals,
+                              const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
+                              int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
+                              float g_ld_alpha, float g_ld_rgb, float* g_flow_params, float* g_globals,
+                              cudaStream_t s);
+
+// C[m,n] = epi( sum_k A(m,k) * B(k,n) + bias[n] ) with arbitrary element strides (fp32 CUDA-core GEMM).
+enum Epilogue { EPI_NONE = 0, EPI_RELU = 1, EPI_TANH_MASK = 2, EPI_RELU_MASK_MUL = 3 };
+struct GemmArgs {
+  const float* A; int64_t a_rs, a_cs;   // A(m,k) = A[m*a_rs + k*a_cs]
+  const float* B; int64_t b_rs, b_cs;   // B(k,n) = B[k*b_rs + n*b_cs]
+  float* C; int64_t c_rs;               // C(m,n) = C[m*c_rs + n]
+  const float* bias;                    // (N) or nullptr
+  const float* aux; int64_t aux_rs;     // EPI_TANH_MASK: aux = per-column flag (N); EPI_RELU_MASK_MUL: aux(m,n) activation, C *= (aux>0)
+  int64_t M; int N; int64_t K;
+  int epilogue;
+  int accumulate;                       // C += result (applied before the epilogue)
+  int split_k;                          // >1: atomicAdd partial sums into a pre-zeroed C (no bias/epilogue)
+};
+int launch_sgemm(const GemmArgs& g, cudaStream_t s);
+
+}  // namespace cfn

@@ -1,0 +1,507 @@
+// K2 / K4: conditional triangular-Sylvester flow stacks over K latent samples + alpha compositing of all K
+// fields, forward and backward.  One warp per ray, lane = latent sample k (groups of 32 when K > 32); the warp
+// walks the N samples front to back, carrying transmittance and the running sums in registers, so there is no
+// scan primitive and no (B,N,K,...) intermediate in HBM.  The 18F conditioning scalars of each point are staged
+// through shared memory in 16-point chunks (coalesced 128-bit loads, register double-buffering) and read back
+// as warp-wide broadcasts.
+//
+// Reference semantics: model/models.py:188-291 (NeRF_Flows.forward), model/models.py:387-416 +
+// model/flow/flows.py:189-268 (flow step, log-det), run_nerf_uncertainty_NF.py:411-454 (raw2outputs);
+// backward = SURVEY.md Appendix A.1/A.2 (verified there against autograd).
+#include "common.cuh"
+
+namespace cfn {
+
+constexpr int kChunk = 16;   // points staged per shared-memory chunk
+constexpr int kMaxF = 8;     // flows per stack supported by the backward kernel's register arrays
+
+// Stage one chunk of flow parameters: global (coalesced) -> registers.
+template <int MAXV>
+__device__ __forceinline__ void chunk_load(const float* __restrict__ src, int n_floats, int lane, float4 (&v)[MAXV]) {
+  const int nvec = n_floats >> 2;  // chunk base is 16-byte aligned (16*PP floats per chunk)
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int idx = lane + 32 * i;
+    if (idx < nvec) v[i] = __ldg(reinterpret_cast<const float4*>(src) + idx);
+  }
+}
+template <int MAXV>
+__device__ __forceinline__ void chunk_store(float* dst, int n_floats, int lane, const float4 (&v)[MAXV]) {
+  const int nvec = n_floats >> 2;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int idx = lane + 32 * i;
+    if (idx < nvec) reinterpret_cast<float4*>(dst)[idx] = v[i];
+  }
+}
+
+// MAXV float4 per lane must cover kChunk*PP/4 float4 per chunk: PP = 18F -> 72F float4 / 32 lanes.
+// F <= 8 -> at most 18 float4 per lane.  We instantiate for F<=4 (MAXV=9) and F<=8 (MAXV=18).
+
+template <int MAXV, bool TRAIN>
+__global__ void __launch_bounds__(128)
+flow_composite_fwd_kernel(int F, int K, const float* __restrict__ globals, const float* __restrict__ flow_params,
+                          const float* __restrict__ z_vals, const float* __restrict__ rays_d, int rays_d_stride,
+                          const float* __restrict__ eps_alpha, const float* __restrict__ eps_rgb, int64_t B, int N,
+                          int white_bkgd, float* __restrict__ rgb_map, float* __restrict__ disp_map,
+                          float* __restrict__ depth_map, float* __restrict__ raw, float* __restrict__ weights,
+                          float* __restrict__ logdet_sums, float* __restrict__ kstats) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int PP = 18 * F;
+  const int per_warp = (kChunk * PP + 2 * N + 3) & ~3;   // keeps every warp's chunk buffer 16-byte aligned
+  float* sp = smem + warp * per_warp;  // chunk of parameters
+  float* sz = sp + kChunk * PP;        // z_vals of the ray
+  float* sd = sz + N;                  // dists * |d|
+  const int64_t b = (int64_t)blockIdx.x * 4 + warp;
+  if (b >= B) return;
+
+  for (int n = lane; n < N; n += 32) sz[n] = z_vals[b * N + n];
+  const float* d = rays_d + b * rays_d_stride;
+  const float dx = d[0], dy = d[1], dz = d[2];
+  const float norm = sqrtf(dx * dx + dy * dy + dz * dz);
+  __syncwarp();
+  for (int n = lane; n < N; n += 32) sd[n] = ((n < N - 1) ? (sz[n + 1] - sz[n]) : 10.0f) * norm;
+
+  const float a_mean = globals[0], a_std = globals[1];
+  const float c_mean0 = globals[2], c_mean1 = globals[3], c_mean2 = globals[4];
+  const float c_std0 = globals[5], c_std1 = globals[6], c_std2 = globals[7];
+
+  const float* prow = flow_params + (b * N) * PP;
+  const int n_chunks = (N + kChunk - 1) / kChunk;
+  const int KG = (K + 31) / 32;
+  // 128-bit staging needs a 16-byte aligned row (always true for even N*F); otherwise everything goes scalar
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(prow) & 15) == 0;
+
+  float ld_a_sum = 0.f, ld_c_sum = 0.f;                      // TRAIN: per-lane sums of the log-det terms
+  float st_sum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};               // kstats: sums over k of r,g,b,depth,disp
+  float st_sq[3] = {0.f, 0.f, 0.f};
+
+  // two passes over the K groups when kstats needs a centred variance: we keep it single pass and use the
+  // shifted two-accumulator form below only for K <= 32 groups; variance is finalised after the loop.
+  for (int kg = 0; kg < KG; ++kg) {
+    const int k = kg * 32 + lane;
+    const bool active = k < K;
+    const float ea = active ? eps_alpha[k] : 0.f;
+    const float e0 = active ? eps_rgb[k * 3 + 0] : 0.f, e1 = active ? eps_rgb[k * 3 + 1] : 0.f,
+                e2 = active ? eps_rgb[k * 3 + 2] : 0.f;
+    // z0 = eps * std + mean  (models.py:200/206, 239/251)
+    const float za0 = ea * a_std + a_mean;
+    const float zc00 = e0 * c_std0 + c_mean0, zc01 = e1 * c_std1 + c_mean1, zc02 = e2 * c_std2 + c_mean2;
+
+    float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, depth = 0.f, acc = 0.f;
+
+    float4 stage[MAXV];
+    {
+      const int npts = min(kChunk, N);
+      const int nvf = vec_ok ? ((npts * PP) & ~3) : 0;
+      chunk_load<MAXV>(prow, nvf, lane, stage);
+      __syncwarp();
+      chunk_store<MAXV>(sp, nvf, lane, stage);
+      for (int i = nvf + lane; i < npts * PP; i += 32) sp[i] = prow[i];   // scalar tail / unaligned rows
+      __syncwarp();
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+      const int n0 = c * kChunk;
+      const int npts = min(kChunk, N - n0);
+      const bool has_next = (c + 1) < n_chunks;
+      const int next_pts = has_next ? min(kChunk, N - n0 - kChunk) : 0;
+      const int next_vf = vec_ok ? ((next_pts * PP) & ~3) : 0;
+      if (has_next) chunk_load<MAXV>(prow + (int64_t)(n0 + kChunk) * PP, next_vf, lane, stage);
+
+      for (int i = 0; i < npts; ++i) {
+        const int n = n0 + i;
+        const float* P = sp + i * PP;
+        // ---- alpha stack (z_size 1; the flip is the identity) ----
+        float za = za0, lda = 0.f;
+        for (int f = 0; f < F; ++f) {
+          const float d1 = P[f], d2 = P[F + f], bb = P[2 * F + f];
+          const float t = tanhf(d2 * za + bb);
+          za += d1 * t;
+          if (TRAIN) lda += logf(fabsf((1.0f - t * t) * (d1 * d2) + 1.0f) + 1e-8f);
+        }
+        // ---- rgb stack (z_size 3; components reversed on odd flows, models.py:404-408) ----
+        float z0 = zc00, z1 = zc01, z2 = zc02, ldc = 0.f;
+        for (int f = 0; f < F; ++f) {
+          const float* Q = P + 3 * F + kRgbFlowRec * f;
+          const bool odd = f & 1;
+          const float p0 = odd ? z2 : z0, p1 = z1, p2 = odd ? z0 : z2;
+          const float t0 = tanhf(Q[6] * p0 + Q[7] * p1 + Q[8] * p2 + Q[12]);
+          const float t1 = tanhf(Q[9] * p1 + Q[10] * p2 + Q[13]);
+          const float t2 = tanhf(Q[11] * p2 + Q[14]);
+          const float s0 = Q[0] * t0 + Q[1] * t1 + Q[2] * t2;
+          const float s1 = Q[3] * t1 + Q[4] * t2;
+          const float s2 = Q[5] * t2;
+          z0 += odd ? s2 : s0;
+          z1 += s1;
+          z2 += odd ? s0 : s2;
+          if (TRAIN) {
+            ldc += logf(fabsf((1.0f - t0 * t0) * (Q[0] * Q[6]) + 1.0f) + 1e-8f) +
+                   logf(fabsf((1.0f - t1 * t1) * (Q[3] * Q[9]) + 1.0f) + 1e-8f) +
+                   logf(fabsf((1.0f - t2 * t2) * (Q[5] * Q[11]) + 1.0f) + 1e-8f);
+          }
+        }
+        if (TRAIN && active) {
+          ld_a_sum += lda + (za - softplusf_(za));                                           // models.py:263
+          ld_c_sum += ldc + ((z0 + z1 + z2) - 2.0f * (softplusf_(z0) + softplusf_(z1) + softplusf_(z2)));  // :278
+        }
+        // ---- compositing (raw2outputs) ----
+        const float alpha = 1.0f - expf(-softplusf_(za) * sd[n]);
+        const float w = alpha * T;
+        T = T * ((1.0f - alpha) + 1e-10f);
+        cr += w * sigmoidf_(z0);
+        cg += w * sigmoidf_(z1);
+        cb += w * sigmoidf_(z2);
+        depth += w * sz[n];
+        acc += w;
+        if (active) {
+          if (raw) reinterpret_cast<float4*>(raw)[(b * N + n) * K + k] = make_float4(z0, z1, z2, za);
+          if (weights) weights[(b * N + n) * K + k] = w;
+        }
+      }
+      __syncwarp();
+      if (has_next) {
+        chunk_store<MAXV>(sp, next_vf, lane, stage);
+        const float* src = prow + (int64_t)(n0 + kChunk) * PP;
+        for (int i = next_vf + lane; i < next_pts * PP; i += 32) sp[i] = src[i];
+      }
+      __syncwarp();
+    }
+    const float disp = 1.0f / fmaxf(2e-10f, depth / (acc + 1e-10f) + 1e-10f);
+    if (white_bkgd) {
+      const float bg = 1.0f - acc;
+      cr += bg; cg += bg; cb += bg;
+    }
+    if (active) {
+      rgb_map[(b * 3 + 0) * K + k] = cr;
+      rgb_map[(b * 3 + 1) * K + k] = cg;
+      rgb_map[(b * 3 + 2) * K + k] = cb;
+      disp_map[b * K + k] = disp;
+      depth_map[b * K + k] = depth;
+      st_sum[0] += cr; st_sum[1] += cg; st_sum[2] += cb; st_sum[3] += depth; st_sum[4] += disp;
+    }
+  }
+
+  if (TRAIN && logdet_sums) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ld_a_sum += __shfl_xor_sync(0xffffffffu, ld_a_sum, o);
+      ld_c_sum += __shfl_xor_sync(0xffffffffu, ld_c_sum, o);
+    }
+    if (lane == 0) {
+      logdet_sums[b * 2 + 0] = ld_a_sum;
+      logdet_sums[b * 2 + 1] = ld_c_sum;
+    }
+  }
+  if (kstats) {
+    // mean over K, then the centred second moment from the values just written (L1/L2 hits)
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) st_sum[j] += __shfl_xor_sync(0xffffffffu, st_sum[j], o);
+    const float invK = 1.0f / (float)K;
+    const float m0 = st_sum[0] * invK, m1 = st_sum[1] * invK, m2 = st_sum[2] * invK;
+    __syncwarp();
+    for (int k = lane; k < K; k += 32) {
+      const float a0 = rgb_map[(b * 3 + 0) * K + k] - m0, a1 = rgb_map[(b * 3 + 1) * K + k] - m1,
+                  a2 = rgb_map[(b * 3 + 2) * K + k] - m2;
+      st_sq[0] += a0 * a0; st_sq[1] += a1 * a1; st_sq[2] += a2 * a2;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) st_sq[j] += __shfl_xor_sync(0xffffffffu, st_sq[j], o);
+    if (lane == 0) {
+      const float bess = (K > 1) ? (float)K / (float)(K - 1) : 0.f;       // the second K/(K-1) factor (main:1034)
+      const float inv = (K > 1) ? 1.0f / (float)(K - 1) : 0.f;
+      float* o = kstats + b * 8;
+      o[0] = m0; o[1] = m1; o[2] = m2;
+      o[3] = sqrtf(st_sq[0] * inv) * bess;
+      o[4] = sqrtf(st_sq[1] * inv) * bess;
+      o[5] = sqrtf(st_sq[2] * inv) * bess;
+      o[6] = st_sum[3] * invK;
+      o[7] = st_sum[4] * invK;
+    }
+  }
+}
+
+static size_t fwd_smem_bytes(int F, int N) { return (size_t)4 * ((kChunk * 18 * F + 2 * N + 3) & ~3) * sizeof(float); }
+
+int launch_flow_composite_fwd(int F, int K, const float* globals, const float* flow_params, const float* z_vals,
+                              const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
+                              int64_t B, int N, int white_bkgd, float* rgb_map, float* disp_map, float* depth_map,
+                              float* raw, float* weights, float* logdet_sums, float* kstats, cudaStream_t s) {
+  if (B == 0) return CFN_OK;
+  CFN_CHECK_ARG(F >= 1 && F <= kMaxF, "flow_composite: n_flows=%d unsupported (1..%d)", F, kMaxF);
+  CFN_CHECK_ARG(N >= 1 && N <= 2048 && K >= 1, "flow_composite: unsupported N=%d K=%d", N, K);
+  size_t smem = fwd_smem_bytes(F, N);
+  unsigned grid = (unsigned)((B + 3) / 4);
+  const bool train = logdet_sums != nullptr;
+#define CFN_FWD_LAUNCH(MAXV, TR)                                                                                  \
+  do {                                                                                                            \
+    auto kern = flow_composite_fwd_kernel<MAXV, TR>;                                                              \
+    if (smem > 48 * 1024) CFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, 128, smem, s>>>(F, K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N, \
+                                 white_bkgd, rgb_map, disp_map, depth_map, raw, weights, logdet_sums, kstats);    \
+  } while (0)
+  if (F <= 4) {
+    if (train) CFN_FWD_LAUNCH(9, true); else CFN_FWD_LAUNCH(9, false);
+  } else {
+    if (train) CFN_FWD_LAUNCH(18, true); else CFN_FWD_LAUNCH(18, false);
+  }
+#undef CFN_FWD_LAUNCH
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+// =====================================================================================================
+// Backward (K4).  Per ray-warp and K group:
+//   pass 1 (front to back): alpha stack only -> T_n kept in shared memory (N x 32 floats per warp);
+//   pass 2 (back to front): recompute both stacks with their intermediates in registers, compositing
+//   adjoint with the suffix sum S (Appendix A.2), flow adjoint step by step in reverse (Appendix A.1), and a
+//   shared-memory transpose-reduction of the 18F per-point parameter gradients over the 32 latent lanes.
+// Gradients w.r.t. the global latent parameters through z0 = eps*std + mean are summed per ray into
+// g_globals_partial (B,8) (deterministic; the host sums over rays).
+// =====================================================================================================
+template <int FT>
+__global__ void __launch_bounds__(128)
+flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float* __restrict__ flow_params,
+                          const float* __restrict__ z_vals, const float* __restrict__ rays_d, int rays_d_stride,
+                          const float* __restrict__ eps_alpha, const float* __restrict__ eps_rgb, int64_t B, int N,
+                          int white_bkgd, const float* __restrict__ g_rgb_map, const float* __restrict__ g_depth_map,
+                          float gl_a, float gl_c, float* __restrict__ g_flow_params,
+                          float* __restrict__ g_globals_partial) {
+  constexpr int F = FT;
+  constexpr int PP = 18 * F;
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp = 2 * N + N * 32 + PP * 33 + PP;
+  float* sz = smem + warp * per_warp;   // z
+  float* sd = sz + N;                   // dists
+  float* sT = sd + N;                   // T_n per lane      [N][32]
+  float* sG = sT + N * 32;              // gradient transpose scratch [PP][33]
+  float* sP = sG + PP * 33;             // parameters of the current point [PP]
+  const int64_t b = (int64_t)blockIdx.x * 4 + warp;
+  if (b >= B) return;
+
+  for (int n = lane; n < N; n += 32) sz[n] = z_vals[b * N + n];
+  const float* d = rays_d + b * rays_d_stride;
+  const float dx = d[0], dy = d[1], dz = d[2];
+  const float norm = sqrtf(dx * dx + dy * dy + dz * dz);
+  __syncwarp();
+  for (int n = lane; n < N; n += 32) sd[n] = ((n < N - 1) ? (sz[n + 1] - sz[n]) : 10.0f) * norm;
+  __syncwarp();
+
+  const float a_mean = globals[0], a_std = globals[1];
+  const float c_mean[3] = {globals[2], globals[3], globals[4]};
+  const float c_std[3] = {globals[5], globals[6], globals[7]};
+  const float* prow = flow_params + (b * N) * PP;
+  float* grow = g_flow_params + (b * N) * PP;
+  const int KG = (K + 31) / 32;
+  float gg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d/d[a_mean, a_std, c_mean(3), c_std(3)]
+
+  for (int kg = 0; kg < KG; ++kg) {
+    const int k = kg * 32 + lane;
+    const bool active = k < K;
+    const float ea = active ? eps_alpha[k] : 0.f;
+    float ec[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ec[c] = active ? eps_rgb[k * 3 + c] : 0.f;
+    const float za0 = ea * a_std + a_mean;
+    float zc0[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) zc0[c] = ec[c] * c_std[c] + c_mean[c];
+    // upstream gradients of this latent sample
+    float gC[3] = {0.f, 0.f, 0.f}, gD = 0.f;
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gC[c] = g_rgb_map[(b * 3 + c) * K + k];
+      if (g_depth_map) gD = g_depth_map[b * K + k];
+    }
+    const float gA = white_bkgd ? -(gC[0] + gC[1] + gC[2]) : 0.f;
+
+    // ---- pass 1: alpha stack, transmittance ----
+    {
+      float T = 1.0f;
+      for (int n = 0; n < N; ++n) {
+        const float* P = prow + (int64_t)n * PP;   // warp-uniform address: one broadcast transaction
+        float za = za0;
+#pragma unroll
+        for (int f = 0; f < F; ++f) za += __ldg(P + f) * tanhf(__ldg(P + F + f) * za + __ldg(P + 2 * F + f));
+        const float alpha = 1.0f - expf(-softplusf_(za) * sd[n]);
+        sT[n * 32 + lane] = T;
+        T = T * ((1.0f - alpha) + 1e-10f);
+      }
+    }
+    __syncwarp();
+
+    // ---- pass 2: back to front ----
+    float S = 0.f;
+    for (int n = N - 1; n >= 0; --n) {
+      // stage the point's parameters (PP floats) into shared memory
+      for (int i = lane; i < PP; i += 32) sP[i] = __ldg(prow + (int64_t)n * PP + i);
+      __syncwarp();
+      // recompute alpha stack with intermediates
+      float za_in[F], ta[F];
+      float za = za0;
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        za_in[f] = za;
+        ta[f] = tanhf(sP[F + f] * za + sP[2 * F + f]);
+        za += sP[f] * ta[f];
+      }
+      // recompute rgb stack with intermediates
+      float zp[F][3], tc[F][3];
+      float z[3] = {zc0[0], zc0[1], zc0[2]};
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const float* Q = sP + 3 * F + kRgbFlowRec * f;
+        const bool odd = f & 1;
+        zp[f][0] = odd ? z[2] : z[0]; zp[f][1] = z[1]; zp[f][2] = odd ? z[0] : z[2];
+        tc[f][0] = tanhf(Q[6] * zp[f][0] + Q[7] * zp[f][1] + Q[8] * zp[f][2] + Q[12]);
+        tc[f][1] = tanhf(Q[9] * zp[f][1] + Q[10] * zp[f][2] + Q[13]);
+        tc[f][2] = tanhf(Q[11] * zp[f][2] + Q[14]);
+        const float s0 = Q[0] * tc[f][0] + Q[1] * tc[f][1] + Q[2] * tc[f][2];
+        const float s1 = Q[3] * tc[f][1] + Q[4] * tc[f][2];
+        const float s2 = Q[5] * tc[f][2];
+        z[0] += odd ? s2 : s0; z[1] += s1; z[2] += odd ? s0 : s2;
+      }
+      // ---- compositing adjoint (Appendix A.2) ----
+      const float T = sT[n * 32 + lane];
+      const float alpha = 1.0f - expf(-softplusf_(za) * sd[n]);
+      const float w = alpha * T;
+      const float q = (1.0f - alpha) + 1e-10f;
+      float col[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) col[c] = sigmoidf_(z[c]);
+      const float v = gC[0] * col[0] + gC[1] * col[1] + gC[2] * col[2] + gD * sz[n] + gA;
+      const float g_alpha = v * T - S / q;
+      S += v * w;
+      // d alpha / d raw_sigma = (1-alpha) * delta * sigmoid(raw_sigma);  entropy activation term (models.py:263)
+      float g_za = g_alpha * (1.0f - alpha) * sd[n] * sigmoidf_(za) + gl_a * (1.0f - sigmoidf_(za));
+      float gz[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        gz[c] = w * gC[c] * col[c] * (1.0f - col[c]) + gl_c * (1.0f - 2.0f * col[c]);  // models.py:278
+      if (!active) { g_za = 0.f; gz[0] = gz[1] = gz[2] = 0.f; }
+      const float gla = active ? gl_a : 0.f, glc = active ? gl_c : 0.f;
+
+      // ---- alpha stack adjoint (Appendix A.1 with z_size 1) ----
+#pragma unroll
+      for (int f = F - 1; f >= 0; --f) {
+        const float d1 = sP[f], d2 = sP[F + f];
+        const float t = ta[f], omt2 = 1.0f - t * t;
+        const float u = omt2 * (d1 * d2) + 1.0f;
+        const float sgn = (u > 0.f) ? 1.f : ((u < 0.f) ? -1.f : 0.f);
+        const float sl = gla * sgn / (fabsf(u) + 1e-8f);
+        const float g_d1 = g_za * t + sl * omt2 * d2;
+        const float gt = d1 * g_za + sl * (-2.0f * t * d1 * d2);
+        const float gpre = gt * omt2;
+        const float g_d2 = gpre * za_in[f] + sl * omt2 * d1;
+        g_za = g_za + d2 * gpre;
+        sG[(f)*33 + lane] = g_d1;
+        sG[(F + f) * 33 + lane] = g_d2;
+        sG[(2 * F + f) * 33 + lane] = gpre;
+      }
+      // ---- rgb stack adjoint ----
+#pragma unroll
+      for (int f = F - 1; f >= 0; --f) {
+        const float* Q = sP + 3 * F + kRgbFlowRec * f;
+        float* G = sG + (3 * F + kRgbFlowRec * f) * 33 + lane;
+        const bool odd = f & 1;
+        // gy = P g'
+        const float gy0 = odd ? gz[2] : gz[0], gy1 = gz[1], gy2 = odd ? gz[0] : gz[2];
+        const float t0 = tc[f][0], t1 = tc[f][1], t2 = tc[f][2];
+        const float o0 = 1.0f - t0 * t0, o1 = 1.0f - t1 * t1, o2 = 1.0f - t2 * t2;
+        const float dd0 = Q[0] * Q[6], dd1 = Q[3] * Q[9], dd2 = Q[5] * Q[11];
+        const float u0 = o0 * dd0 + 1.0f, u1 = o1 * dd1 + 1.0f, u2 = o2 * dd2 + 1.0f;
+        const float sl0 = glc * ((u0 > 0.f) ? 1.f : ((u0 < 0.f) ? -1.f : 0.f)) / (fabsf(u0) + 1e-8f);
+        const float sl1 = glc * ((u1 > 0.f) ? 1.f : ((u1 < 0.f) ? -1.f : 0.f)) / (fabsf(u1) + 1e-8f);
+        const float sl2 = glc * ((u2 > 0.f) ? 1.f : ((u2 < 0.f) ? -1.f : 0.f)) / (fabsf(u2) + 1e-8f);
+        // gR1 = gy t^T (upper), diagonal gets the log-det term
+        G[0 * 33] = gy0 * t0 + sl0 * o0 * Q[6];
+        G[1 * 33] = gy0 * t1;
+        G[2 * 33] = gy0 * t2;
+        G[3 * 33] = gy1 * t1 + sl1 * o1 * Q[9];
+        G[4 * 33] = gy1 * t2;
+        G[5 * 33] = gy2 * t2 + sl2 * o2 * Q[11];
+        // gt = R1^T gy + log-det term
+        const float gt0 = Q[0] * gy0 + sl0 * (-2.0f * t0 * dd0);
+        const float gt1 = Q[1] * gy0 + Q[3] * gy1 + sl1 * (-2.0f * t1 * dd1);
+        const float gt2 = Q[2] * gy0 + Q[4] * gy1 + Q[5] * gy2 + sl2 * (-2.0f * t2 * dd2);
+        const float gp0 = gt0 * o0, gp1 = gt1 * o1, gp2 = gt2 * o2;
+        // gR2 = gpre zp^T (upper), diagonal gets the log-det term
+        G[6 * 33] = gp0 * zp[f][0] + sl0 * o0 * Q[0];
+        G[7 * 33] = gp0 * zp[f][1];
+        G[8 * 33] = gp0 * zp[f][2];
+        G[9 * 33] = gp1 * zp[f][1] + sl1 * o1 * Q[3];
+        G[10 * 33] = gp1 * zp[f][2];
+        G[11 * 33] = gp2 * zp[f][2] + sl2 * o2 * Q[5];
+        G[12 * 33] = gp0;
+        G[13 * 33] = gp1;
+        G[14 * 33] = gp2;
+        // gz = g' + P (R2^T gpre)
+        const float r0 = Q[6] * gp0;
+        const float r1 = Q[7] * gp0 + Q[9] * gp1;
+        const float r2 = Q[8] * gp0 + Q[10] * gp1 + Q[11] * gp2;
+        gz[0] += odd ? r2 : r0;
+        gz[1] += r1;
+        gz[2] += odd ? r0 : r2;
+      }
+      // gradients of the base samples z0 = eps*std + mean
+      gg[0] += g_za; gg[1] += ea * g_za;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { gg[2 + c] += gz[c]; gg[5 + c] += ec[c] * gz[c]; }
+
+      // ---- reduce the PP per-point parameter gradients over the 32 latent lanes ----
+      __syncwarp();
+      for (int j = lane; j < PP; j += 32) {
+        const float* row = sG + j * 33;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += row[i];
+        float* dst = grow + (int64_t)n * PP + j;
+        if (kg == 0) *dst = acc; else *dst += acc;
+      }
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gg[j] += __shfl_xor_sync(0xffffffffu, gg[j], o);
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g_globals_partial[b * 8 + j] = gg[j];
+  }
+}
+
+int launch_flow_composite_bwd(int F, int K, const float* globals, const float* flow_params, const float* z_vals,
+                              const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
+                              int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
+                              float g_ld_alpha, float g_ld_rgb, float* g_flow_params, float* g_globals_partial,
+                              cudaStream_t s) {
+  if (B == 0) return CFN_OK;
+  CFN_CHECK_ARG(F >= 1 && F <= kMaxF, "flow_composite_bwd: n_flows=%d unsupported (1..%d)", F, kMaxF);
+  CFN_CHECK_ARG(N >= 1 && N <= 320 && K >= 1, "flow_composite_bwd: unsupported N=%d (<=320) K=%d", N, K);
+  const int PP = 18 * F;
+  size_t smem = (size_t)4 * (2 * N + N * 32 + PP * 33 + PP) * sizeof(float);
+  unsigned grid = (unsigned)((B + 3) / 4);
+#define CFN_BWD_CASE(FF)                                                                                             \
+  case FF: {                                                                                                         \
+    auto kern = flow_composite_bwd_kernel<FF>;                                                                       \
+    CFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+    kern<<<grid, 128, smem, s>>>(K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N,   \
+                                 white_bkgd, g_rgb_map, g_depth_map, g_ld_alpha, g_ld_rgb, g_flow_params,            \
+                                 g_globals_partial);                                                                 \
+  } break;
+  switch (F) {
+    CFN_BWD_CASE(1) CFN_BWD_CASE(2) CFN_BWD_CASE(3) CFN_BWD_CASE(4) CFN_BWD_CASE(5) CFN_BWD_CASE(6) CFN_BWD_CASE(7)
+    CFN_BWD_CASE(8)
+  }
+#undef CFN_BWD_CASE
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+}  // namespace cfn

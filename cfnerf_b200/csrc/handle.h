@@ -1,0 +1,67 @@
+// Handle layout shared by the C-ABI translation units.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+struct GatherRow {
+  int slot_w;   // parameter slot of the source weight matrix
+  int slot_b;   // parameter slot of the source bias
+  int row;      // row of the source nn.Linear
+  int tanh;     // 1: the reference applies tanh to this output (amor_diag1/2, models.py:367-368)
+};
+
+struct ParamSlot {
+  std::string name;
+  int64_t numel;
+  int rows, cols;     // nn.Linear weight (rows=out, cols=in); bias/globals: rows=numel, cols=1
+  int64_t offset;     // float offset inside w32
+};
+
+struct TcPlan;  // tensor-core weight stream + launch plan (mlp_tc.cu)
+
+struct CfnHandle {
+  CfnConfig cfg;
+  int in_pos, in_dir, PP, skip;   // skip = index of the layer whose output is concatenated with gamma(p); -1 = none
+  std::vector<ParamSlot> slots;
+  int64_t n_floats;               // total master floats
+  bool packed;
+
+  // slot indices
+  int s_pts(int i, int bias) const { return 4 + 2 * i + bias; }
+  int s_views, s_feat, s_halpha, s_hrgb, s_frgb, s_falpha;   // base index of each (weight; +1 = bias)
+
+  // device buffers (handle-owned)
+  float* w32;        // fp32 copy of every parameter, slot order
+  float* globals;    // -> w32 + 0 : alpha_mean, alpha_std, rgb_mean(3), rgb_std(3)
+  float* amA;        // (3F, h_alpha) gathered alpha conditioning matrix
+  float* amA_b;      // (3F)
+  float* amC;        // (15F, h_rgb) gathered rgb conditioning matrix
+  float* amC_b;      // (15F)
+  float* tanh_flags; // (18F) 1.0 where the output is a tanh'ed diagonal
+  int* gatherA_dev;  // (3F,4) GatherRow
+  int* gatherC_dev;  // (15F,4)
+  std::vector<GatherRow> gatherA, gatherC;
+  float** grads_table_dev;  // (n slots) scratch pointer table for cfn_network_bwd
+
+  TcPlan* tc;        // nullptr in fp32 mode
+};
+
+namespace cfn {
+// fp32 path (mlp_fp32.cu)
+size_t fp32_workspace_floats(const CfnHandle* h, int64_t n_points, int save);
+int fp32_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts, const float* viewdirs,
+                     int64_t B, int N, float* flow_params, float* ws, int save, cudaStream_t s);
+int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, float* ws, float* const* grads,
+                     cudaStream_t s);
+int pack_fp32(CfnHandle* h, const float* const* params, cudaStream_t s);
+
+// tensor-core path (mlp_tc.cu)
+int tc_create(CfnHandle* h);
+void tc_destroy(CfnHandle* h);
+int tc_pack(CfnHandle* h, cudaStream_t s);
+size_t tc_workspace_bytes(const CfnHandle* h, int64_t n_points);
+int tc_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts, const float* viewdirs,
+                   int64_t B, int N, float* flow_params, void* ws, size_t ws_bytes, cudaStream_t s);
+}  // namespace cfn

@@ -1,0 +1,384 @@
+// CFN_PREC_FP32 network stage: positional encoding (run_nerf_helpers.py:21-69), the 8x512 trunk with skip-concat,
+// the conditioning heads (model/models.py:165-186) and the amortised flow parameters (models.py:358-385, done ONCE
+// per point instead of K times), forward with optional saved activations and the full backward (dgrad chain +
+// split-K wgrad).  All contractions are fp32 CUDA-core FMAs (sgemm.cu): this is the 1e-5 "check" mode of the
+// render path and the round-1 training path.
+#include "handle.h"
+
+namespace cfn {
+
+// ---------------------------------------------------------------------------------------------------
+// workspace layout (floats; M = number of points)
+// ---------------------------------------------------------------------------------------------------
+struct Fp32Layout {
+  int ld5, ldv, ldg;
+  int64_t X5, V, H, v, ha, hr;            // forward
+  int64_t P, GP, G1, G2, gv, gh, dAm;      // saved outputs / backward scratch
+  int nH;
+  int64_t total;
+};
+
+static Fp32Layout make_layout(const CfnHandle* h, int64_t M, int save) {
+  Fp32Layout L;
+  const int W = h->cfg.W;
+  L.ld5 = h->in_pos + W;
+  L.ldv = W + h->in_dir;
+  L.ldg = L.ld5 > L.ldv ? L.ld5 : L.ldv;
+  L.nH = save ? h->cfg.D : 2;
+  int64_t o = 0;
+  auto take = [&](int64_t n) { int64_t r = o; o += (n + 3) & ~(int64_t)3; return r; };
+  L.X5 = take(M * L.ld5);
+  L.V = take(M * L.ldv);
+  L.H = take((int64_t)L.nH * M * W);
+  L.v = take(M * (W / 2));
+  L.ha = take(M * h->cfg.h_alpha);
+  L.hr = take(M * h->cfg.h_rgb);
+  L.P = L.GP = L.G1 = L.G2 = L.gv = L.gh = L.dAm = 0;
+  if (save) {
+    L.P = take(M * h->PP);
+    L.GP = take(M * h->PP);
+    L.G1 = take(M * L.ldg);
+    L.G2 = take(M * L.ldg);
+    L.gv = take(M * (W / 2));
+    int hm = h->cfg.h_alpha > h->cfg.h_rgb ? h->cfg.h_alpha : h->cfg.h_rgb;
+    L.gh = take(M * hm);
+    L.dAm = take((int64_t)h->PP * (hm + 1));
+  }
+  L.total = o;
+  return L;
+}
+
+size_t fp32_workspace_floats(const CfnHandle* h, int64_t M, int save) {
+  return (size_t)make_layout(h, M, save).total;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// positional encoding: gamma(p) -> X5[:, 0:in_pos], gamma(d) -> V[:, W:W+in_dir]
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void embed3(float x, float y, float z, int L, float* out) {
+  out[0] = x; out[1] = y; out[2] = z;
+  float f = 1.0f;
+  for (int l = 0; l < L; ++l) {
+    float* o = out + 3 + 6 * l;
+    const float xf = x * f, yf = y * f, zf = z * f;   // exact: f is a power of two (helpers:38)
+    o[0] = sinf(xf); o[1] = sinf(yf); o[2] = sinf(zf);
+    o[3] = cosf(xf); o[4] = cosf(yf); o[5] = cosf(zf);
+    f *= 2.0f;
+  }
+}
+
+__global__ void encode_kernel(const float* __restrict__ rays, const float* __restrict__ z_vals,
+                              const float* __restrict__ pts, const float* __restrict__ viewdirs, int64_t M, int N,
+                              int L_pos, int L_dir, float* __restrict__ X5, int ld5, float* __restrict__ Vd, int ldv) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int64_t b = m / N;
+  float px, py, pz;
+  if (pts) {
+    px = pts[m * 3 + 0]; py = pts[m * 3 + 1]; pz = pts[m * 3 + 2];
+  } else {
+    const float* r = rays + b * 11;
+    const float z = z_vals[m];
+    // pts = rays_o + rays_d * z (main:534): separate multiply and add, as torch evaluates it
+    px = __fadd_rn(r[0], __fmul_rn(r[3], z));
+    py = __fadd_rn(r[1], __fmul_rn(r[4], z));
+    pz = __fadd_rn(r[2], __fmul_rn(r[5], z));
+  }
+  embed3(px, py, pz, L_pos, X5 + m * ld5);
+  const float* vd = viewdirs ? (viewdirs + b * 3) : (rays + b * 11 + 8);
+  embed3(vd[0], vd[1], vd[2], L_dir, Vd + m * ldv);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// parameter packing (fp32): flat copy + gathered conditioning matrices
+// ---------------------------------------------------------------------------------------------------
+struct SlotTable {
+  int64_t offset[64];
+  int cols[64];
+};
+
+__global__ void gather_rows_kernel(const float* __restrict__ w32, SlotTable t, const int* __restrict__ gather, int rows,
+                                   int cols, float* __restrict__ out_w, float* __restrict__ out_b) {
+  int r = blockIdx.x;
+  if (r >= rows) return;
+  const int slot_w = gather[r * 4 + 0], slot_b = gather[r * 4 + 1], row = gather[r * 4 + 2];
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) out_w[r * cols + c] = w32[t.offset[slot_w] + (int64_t)row * cols + c];
+  if (threadIdx.x == 0) out_b[r] = w32[t.offset[slot_b] + row];
+}
+
+static SlotTable slot_table(const CfnHandle* h) {
+  SlotTable t;
+  for (size_t i = 0; i < h->slots.size() && i < 64; ++i) {
+    t.offset[i] = h->slots[i].offset;
+    t.cols[i] = h->slots[i].cols;
+  }
+  return t;
+}
+
+int pack_fp32(CfnHandle* h, const float* const* params, cudaStream_t s) {
+  CFN_CHECK_ARG(h->slots.size() <= 64, "too many parameter tensors");
+  for (size_t i = 0; i < h->slots.size(); ++i)
+    CFN_CUDA(cudaMemcpyAsync(h->w32 + h->slots[i].offset, params[i], h->slots[i].numel * sizeof(float),
+                             cudaMemcpyDeviceToDevice, s));
+  SlotTable t = slot_table(h);
+  gather_rows_kernel<<<3 * h->cfg.F, 64, 0, s>>>(h->w32, t, h->gatherA_dev, 3 * h->cfg.F, h->cfg.h_alpha, h->amA,
+                                                 h->amA_b);
+  gather_rows_kernel<<<15 * h->cfg.F, 64, 0, s>>>(h->w32, t, h->gatherC_dev, 15 * h->cfg.F, h->cfg.h_rgb, h->amC,
+                                                  h->amC_b);
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------
+static inline const float* Wp(const CfnHandle* h, int slot) { return h->w32 + h->slots[slot].offset; }
+
+// Y(M x out) = epi(X(M x in) W^T + b) for an nn.Linear stored (out, in) row-major
+static int linear_fwd(const CfnHandle* h, int slot, const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t M,
+                      int epi, const float* aux, cudaStream_t s) {
+  const ParamSlot& w = h->slots[slot];
+  GemmArgs g{};
+  g.A = X; g.a_rs = ldx; g.a_cs = 1;
+  g.B = Wp(h, slot); g.b_rs = 1; g.b_cs = w.cols;      // B(k,n) = W[n*in + k]
+  g.C = Y; g.c_rs = ldy;
+  g.bias = Wp(h, slot + 1);
+  g.aux = aux; g.aux_rs = 0;
+  g.M = M; g.N = w.rows; g.K = w.cols;
+  g.epilogue = epi; g.accumulate = 0; g.split_k = 1;
+  return launch_sgemm(g, s);
+}
+
+struct LayerIO {
+  const float* in; int64_t ld_in;
+  float* out; int64_t ld_out;
+};
+
+static LayerIO trunk_io(const CfnHandle* h, const Fp32Layout& L, float* ws, int64_t M, int i, int save) {
+  const int W = h->cfg.W;
+  auto Hbuf = [&](int j) { return ws + L.H + (int64_t)(save ? j : (j & 1)) * M * W; };
+  LayerIO io;
+  if (i == 0) { io.in = ws + L.X5; io.ld_in = L.ld5; }
+  else if (h->skip >= 0 && i == h->skip + 1) { io.in = ws + L.X5; io.ld_in = L.ld5; }
+  else { io.in = Hbuf(i - 1); io.ld_in = W; }
+  if (h->skip >= 0 && i == h->skip) { io.out = ws + L.X5 + h->in_pos; io.ld_out = L.ld5; }
+  else { io.out = Hbuf(i); io.ld_out = W; }
+  return io;
+}
+
+int fp32_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts, const float* viewdirs,
+                     int64_t B, int N, float* flow_params, float* ws, int save, cudaStream_t s) {
+  const int64_t M = B * N;
+  const int W = h->cfg.W, D = h->cfg.D, F = h->cfg.F;
+  Fp32Layout L = make_layout(h, M, save);
+  encode_kernel<<<(unsigned)((M + 127) / 128), 128, 0, s>>>(rays, z_vals, pts, viewdirs, M, N, h->cfg.L_pos,
+                                                            h->cfg.L_dir, ws + L.X5, L.ld5, ws + L.V + W, L.ldv);
+  CFN_LAUNCH_CHECK();
+  int rc;
+  LayerIO last{};
+  for (int i = 0; i < D; ++i) {
+    LayerIO io = trunk_io(h, L, ws, M, i, save);
+    if ((rc = linear_fwd(h, h->s_pts(i, 0), io.in, io.ld_in, io.out, io.ld_out, M, EPI_RELU, nullptr, s))) return rc;
+    last = io;
+  }
+  const float* h7 = last.out;
+  const int64_t ld7 = last.ld_out;
+  // heads (models.py:175-182)
+  if ((rc = linear_fwd(h, h->s_halpha, h7, ld7, ws + L.ha, h->cfg.h_alpha, M, EPI_NONE, nullptr, s))) return rc;
+  if ((rc = linear_fwd(h, h->s_feat, h7, ld7, ws + L.V, L.ldv, M, EPI_NONE, nullptr, s))) return rc;
+  if ((rc = linear_fwd(h, h->s_views, ws + L.V, L.ldv, ws + L.v, W / 2, M, EPI_RELU, nullptr, s))) return rc;
+  if ((rc = linear_fwd(h, h->s_hrgb, ws + L.v, W / 2, ws + L.hr, h->cfg.h_rgb, M, EPI_NONE, nullptr, s))) return rc;
+  // amortised flow parameters, once per point (models.py:358-385)
+  {
+    GemmArgs g{};
+    g.A = ws + L.ha; g.a_rs = h->cfg.h_alpha; g.a_cs = 1;
+    g.B = h->amA; g.b_rs = 1; g.b_cs = h->cfg.h_alpha;
+    g.C = flow_params; g.c_rs = h->PP;
+    g.bias = h->amA_b; g.aux = h->tanh_flags; g.aux_rs = 0;
+    g.M = M; g.N = 3 * F; g.K = h->cfg.h_alpha; g.epilogue = EPI_TANH_MASK; g.split_k = 1;
+    if ((rc = launch_sgemm(g, s))) return rc;
+    g.A = ws + L.hr; g.a_rs = h->cfg.h_rgb;
+    g.B = h->amC; g.b_cs = h->cfg.h_rgb;
+    g.C = flow_params + 3 * F;
+    g.bias = h->amC_b; g.aux = h->tanh_flags + 3 * F;
+    g.N = 15 * F; g.K = h->cfg.h_rgb;
+    if ((rc = launch_sgemm(g, s))) return rc;
+  }
+  if (save) CFN_CUDA(cudaMemcpyAsync(ws + L.P, flow_params, (size_t)M * h->PP * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return CFN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------
+__global__ void tanh_bwd_kernel(const float* __restrict__ g, const float* __restrict__ p, const float* __restrict__ flags,
+                                float* __restrict__ out, int64_t total, int PP) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float pv = p[i];
+  out[i] = flags[i % PP] != 0.f ? g[i] * (1.0f - pv * pv) : g[i];
+}
+
+// out[n] += sum over a slab of rows of g[m*ld + n]   (out pre-zeroed)
+__global__ void colsum_kernel(const float* __restrict__ g, int64_t ld, int64_t M, int N, float* __restrict__ out,
+                              int rows_per_block) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(M, r0 + rows_per_block);
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float s = 0.f;
+    for (int64_t m = r0; m < r1; ++m) s += g[m * ld + n];
+    atomicAdd(out + n, s);
+  }
+}
+
+static int colsum(const float* g, int64_t ld, int64_t M, int N, float* out, cudaStream_t s) {
+  CFN_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), s));
+  const int rows = 256;
+  colsum_kernel<<<(unsigned)((M + rows - 1) / rows), N < 256 ? ((N + 31) / 32) * 32 : 256, 0, s>>>(g, ld, M, N, out, rows);
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+// dW(out x in) = G(M x out)^T X(M x in), split over the point dimension, atomically accumulated into zeroed dW
+static int wgrad(const float* G, int64_t ldg, int out_f, const float* X, int64_t ldx, int in_f, int64_t M, float* dW,
+                 cudaStream_t s) {
+  CFN_CUDA(cudaMemsetAsync(dW, 0, (size_t)out_f * in_f * sizeof(float), s));
+  GemmArgs g{};
+  g.A = G; g.a_rs = 1; g.a_cs = ldg;        // A(m=o, k=pt) = G[pt*ldg + o]
+  g.B = X; g.b_rs = ldx; g.b_cs = 1;        // B(k=pt, n=i) = X[pt*ldx + i]
+  g.C = dW; g.c_rs = in_f;
+  g.M = out_f; g.N = in_f; g.K = M;
+  int tiles = ((out_f + 127) / 128) * ((in_f + 127) / 128);
+  int64_t split = (M + 1023) / 1024;
+  int64_t cap = (148 * 8 + tiles - 1) / tiles;
+  if (split > cap) split = cap;
+  if (split < 2) split = 2;                 // split_k > 1 selects the atomic accumulate path
+  g.split_k = (int)split;
+  return launch_sgemm(g, s);
+}
+
+// Gin(M x n_cols) = [accumulate +] Gout(M x out) W[:, col0:col0+n_cols], optional ReLU mask
+static int dgrad(const CfnHandle* h, int slot, const float* Gout, int64_t ldgo, int col0, int n_cols, float* Gin,
+                 int64_t ldgi, int64_t M, const float* mask, int64_t ld_mask, int accumulate, cudaStream_t s) {
+  const ParamSlot& w = h->slots[slot];
+  GemmArgs g{};
+  g.A = Gout; g.a_rs = ldgo; g.a_cs = 1;
+  g.B = Wp(h, slot) + col0; g.b_rs = w.cols; g.b_cs = 1;   // B(k=o, n=i) = W[o*in + col0 + i]
+  g.C = Gin; g.c_rs = ldgi;
+  g.aux = mask; g.aux_rs = ld_mask;
+  g.M = M; g.N = n_cols; g.K = w.rows;
+  g.epilogue = mask ? EPI_RELU_MASK_MUL : EPI_NONE;
+  g.accumulate = accumulate; g.split_k = 1;
+  return launch_sgemm(g, s);
+}
+
+__global__ void scatter_rows_kernel(const float* __restrict__ dAm, const float* __restrict__ dAb, int cols,
+                                    const int* __restrict__ gather, int rows, float* const* __restrict__ grads) {
+  int r = blockIdx.x;
+  if (r >= rows) return;
+  const int slot_w = gather[r * 4 + 0], slot_b = gather[r * 4 + 1], row = gather[r * 4 + 2];
+  float* gw = grads[slot_w];
+  float* gb = grads[slot_b];
+  if (gw) for (int c = threadIdx.x; c < cols; c += blockDim.x) gw[(int64_t)row * cols + c] = dAm[r * cols + c];
+  if (gb && threadIdx.x == 0) gb[row] = dAb[r];
+}
+
+int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, float* ws, float* const* grads,
+                     cudaStream_t s) {
+  const int64_t M = B * N;
+  const int W = h->cfg.W, D = h->cfg.D, F = h->cfg.F, PP = h->PP;
+  const int ha_n = h->cfg.h_alpha, hr_n = h->cfg.h_rgb;
+  Fp32Layout L = make_layout(h, M, 1);
+  int rc;
+  for (int i = 4; i < (int)h->slots.size(); ++i)
+    CFN_CHECK_ARG(grads[i] != nullptr, "cfn_network_bwd: grads[%d] (%s) is null", i, h->slots[i].name.c_str());
+  float* dAm = ws + L.dAm;                       // (rows, cols) gathered weight grads
+  float* dAb = dAm + (int64_t)PP * (ha_n > hr_n ? ha_n : hr_n);   // (rows) gathered bias grads
+
+  // 1. through the tanh on the diagonals
+  {
+    int64_t total = M * PP;
+    tanh_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g_flow_params, ws + L.P, h->tanh_flags, ws + L.GP,
+                                                                    total, PP);
+    CFN_LAUNCH_CHECK();
+  }
+  const float* GP = ws + L.GP;
+  LayerIO last = trunk_io(h, L, ws, M, D - 1, 1);
+  const float* h7 = last.out;
+  const int64_t ld7 = last.ld_out;
+  float* G1 = ws + L.G1;
+  float* G2 = ws + L.G2;
+  float* gh = ws + L.gh;
+  float* gv = ws + L.gv;
+
+  // zero every flow-conditioning gradient: rows the path never reads keep an exact 0
+  for (int base : {h->s_frgb, h->s_falpha})
+    for (int j = 0; j < 8; ++j)
+      CFN_CUDA(cudaMemsetAsync(grads[base + j], 0, h->slots[base + j].numel * sizeof(float), s));
+
+  // pointer table on the device (handle-owned; the pageable copy is staged before the call returns)
+  float** table = h->grads_table_dev;
+  CFN_CUDA(cudaMemcpyAsync(table, grads, h->slots.size() * sizeof(float*), cudaMemcpyHostToDevice, s));
+
+  // 2. alpha conditioning branch
+  {
+    // gathered dAmA = GP[:, :3F]^T ha ; bias = colsum
+    if ((rc = wgrad(GP, PP, 3 * F, ws + L.ha, ha_n, ha_n, M, dAm, s))) return rc;
+    if ((rc = colsum(GP, PP, M, 3 * F, dAb, s))) return rc;
+    scatter_rows_kernel<<<3 * F, 64, 0, s>>>(dAm, dAb, ha_n, h->gatherA_dev, 3 * F, table);
+    CFN_LAUNCH_CHECK();
+    // g_ha = GP[:, :3F] amA
+    GemmArgs g{};
+    g.A = GP; g.a_rs = PP; g.a_cs = 1;
+    g.B = h->amA; g.b_rs = ha_n; g.b_cs = 1;
+    g.C = gh; g.c_rs = ha_n; g.M = M; g.N = ha_n; g.K = 3 * F; g.split_k = 1;
+    if ((rc = launch_sgemm(g, s))) return rc;
+    if ((rc = wgrad(gh, ha_n, ha_n, h7, ld7, W, M, grads[h->s_halpha], s))) return rc;
+    if ((rc = colsum(gh, ha_n, M, ha_n, grads[h->s_halpha + 1], s))) return rc;
+    // g_h7 (unmasked, first contribution) = g_ha W_halpha
+    if ((rc = dgrad(h, h->s_halpha, gh, ha_n, 0, W, G1, W, M, nullptr, 0, 0, s))) return rc;
+  }
+  // 3. rgb conditioning branch
+  {
+    if ((rc = wgrad(GP + 3 * F, PP, 15 * F, ws + L.hr, hr_n, hr_n, M, dAm, s))) return rc;
+    if ((rc = colsum(GP + 3 * F, PP, M, 15 * F, dAb, s))) return rc;
+    scatter_rows_kernel<<<15 * F, 64, 0, s>>>(dAm, dAb, hr_n, h->gatherC_dev, 15 * F, table);
+    CFN_LAUNCH_CHECK();
+    GemmArgs g{};
+    g.A = GP + 3 * F; g.a_rs = PP; g.a_cs = 1;
+    g.B = h->amC; g.b_rs = hr_n; g.b_cs = 1;
+    g.C = gh; g.c_rs = hr_n; g.M = M; g.N = hr_n; g.K = 15 * F; g.split_k = 1;
+    if ((rc = launch_sgemm(g, s))) return rc;
+    if ((rc = wgrad(gh, hr_n, hr_n, ws + L.v, W / 2, W / 2, M, grads[h->s_hrgb], s))) return rc;
+    if ((rc = colsum(gh, hr_n, M, hr_n, grads[h->s_hrgb + 1], s))) return rc;
+    // g_v = (g_hr W_hrgb) * relu'(v)
+    if ((rc = dgrad(h, h->s_hrgb, gh, hr_n, 0, W / 2, gv, W / 2, M, ws + L.v, W / 2, 0, s))) return rc;
+    if ((rc = wgrad(gv, W / 2, W / 2, ws + L.V, L.ldv, L.ldv, M, grads[h->s_views], s))) return rc;
+    if ((rc = colsum(gv, W / 2, M, W / 2, grads[h->s_views + 1], s))) return rc;
+    // g_feat = g_v W_view[:, :W]   (gamma(d) columns need no gradient)
+    if ((rc = dgrad(h, h->s_views, gv, W / 2, 0, W, G2, W, M, nullptr, 0, 0, s))) return rc;
+    if ((rc = wgrad(G2, W, W, h7, ld7, W, M, grads[h->s_feat], s))) return rc;
+    if ((rc = colsum(G2, W, M, W, grads[h->s_feat + 1], s))) return rc;
+    // g_h7 = (g_h7 + g_feat W_feat) * relu'(h7)
+    if ((rc = dgrad(h, h->s_feat, G2, W, 0, W, G1, W, M, h7, ld7, 1, s))) return rc;
+  }
+  // 4. trunk, last layer to first
+  float* gout = G1;
+  float* gin = G2;
+  for (int i = D - 1; i >= 0; --i) {
+    LayerIO io = trunk_io(h, L, ws, M, i, 1);
+    const int slot = h->s_pts(i, 0);
+    const int fin = h->slots[slot].cols;
+    if ((rc = wgrad(gout, W, W, io.in, io.ld_in, fin, M, grads[slot], s))) return rc;
+    if ((rc = colsum(gout, W, M, W, grads[slot + 1], s))) return rc;
+    if (i == 0) break;
+    // gradient w.r.t. the previous layer's (post-ReLU) output, masked by its ReLU
+    LayerIO prev = trunk_io(h, L, ws, M, i - 1, 1);
+    const int col0 = (h->skip >= 0 && i == h->skip + 1) ? h->in_pos : 0;   // skip input is cat[gamma(p), h]
+    if ((rc = dgrad(h, slot, gout, W, col0, W, gin, W, M, prev.out, prev.ld_out, 0, s))) return rc;
+    float* t = gout; gout = gin; gin = t;
+  }
+  return CFN_OK;
+}
+
+}  // namespace cfn

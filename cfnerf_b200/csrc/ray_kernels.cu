@@ -1,0 +1,240 @@
+// Per-ray streaming kernels: sample schedule (A1), stand-alone raw2outputs (A8, "K2'"), sample_pdf and
+// sorted merge (A9, "K3"), K-mean of weights.  All fp32, HBM-bound, one warp per ray (lane = latent sample k
+// or lane = sample along the ray), coalesced 128-bit loads.
+#include "common.cuh"
+
+namespace cfn {
+
+// ------------------------------------------------------------------------------------------------
+// A1: z_vals = near*(1-t) + far*t  (or the lindisp form), optional stratified jitter.
+// Reference: run_nerf_uncertainty_NF.py:510-532.  Operation order is reproduced with explicit
+// round-to-nearest intrinsics so that no FMA contraction changes the last bit.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float z_of_t(float near, float far, float t, int lindisp) {
+  float omt = __fsub_rn(1.0f, t);
+  if (!lindisp) return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));
+  float a = __fmul_rn(__fdiv_rn(1.0f, near), omt);
+  float b = __fmul_rn(__fdiv_rn(1.0f, far), t);
+  return __fdiv_rn(1.0f, __fadd_rn(a, b));
+}
+
+__global__ void zvals_kernel(const float* __restrict__ rays, const float* __restrict__ t_vals,
+                             const float* __restrict__ t_rand, int lindisp, float* __restrict__ z_vals, int64_t B,
+                             int N) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * N) return;
+  int64_t b = idx / N;
+  int n = (int)(idx - b * N);
+  float near = rays[b * 11 + 6], far = rays[b * 11 + 7];
+  float z = z_of_t(near, far, t_vals[n], lindisp);
+  if (t_rand != nullptr) {
+    float upper = z, lower = z;
+    if (n < N - 1) upper = __fmul_rn(0.5f, __fadd_rn(z_of_t(near, far, t_vals[n + 1], lindisp), z));
+    if (n > 0) lower = __fmul_rn(0.5f, __fadd_rn(z, z_of_t(near, far, t_vals[n - 1], lindisp)));
+    z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand[idx]));
+  }
+  z_vals[idx] = z;
+}
+
+int launch_zvals(const float* rays, const float* t_vals, const float* t_rand, int lindisp, float* z_vals, int64_t B,
+                 int N, cudaStream_t s) {
+  if (B == 0) return CFN_OK;
+  int64_t total = B * N;
+  zvals_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(rays, t_vals, t_rand, lindisp, z_vals, B, N);
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A8: raw2outputs (run_nerf_uncertainty_NF.py:411-454).  raw (B,N,K,4) is streamed exactly once:
+// one warp owns (ray, group of 32 latent samples); lane k walks the N samples front to back carrying the
+// transmittance in a register (no scan primitive needed), 512 contiguous bytes per warp per sample.
+// Algorithmic traffic: 16NK + 4N + 12 (+4NK with weights) read/written per ray.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+template <bool WRITE_W>
+__global__ void __launch_bounds__(128) raw2outputs_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
+                                                          const float* __restrict__ rays_d, int rays_d_stride,
+                                                          int white_bkgd, float* __restrict__ rgb_map,
+                                                          float* __restrict__ disp_map, float* __restrict__ weights,
+                                                          float* __restrict__ depth_map, int64_t B, int N, int K,
+                                                          int KG) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sz = smem + warp * 2 * N;
+  float* sd = sz + N;
+  int64_t wg = (int64_t)blockIdx.x * 4 + warp;
+  if (wg >= B * KG) return;
+  int64_t b = wg / KG;
+  int k = (int)(wg - b * KG) * 32 + lane;
+  bool active = k < K;
+  for (int n = lane; n < N; n += 32) sz[n] = z_vals[b * N + n];
+  const float* d = rays_d + b * rays_d_stride;
+  float dx = d[0], dy = d[1], dz = d[2];
+  float norm = sqrtf(dx * dx + dy * dy + dz * dz);
+  __syncwarp();
+  for (int n = lane; n < N; n += 32) sd[n] = ((n < N - 1) ? (sz[n + 1] - sz[n]) : 10.0f) * norm;
+  __syncwarp();
+  if (!active) return;
+  const float4* rp = reinterpret_cast<const float4*>(raw) + (b * N) * K + k;
+  float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, depth = 0.f, acc = 0.f;
+  float* wp = WRITE_W ? (weights + (b * N) * K + k) : nullptr;
+#pragma unroll 8
+  for (int n = 0; n < N; ++n) {
+    float4 r = ldg_stream(rp + (int64_t)n * K);
+    float alpha = 1.0f - expf(-softplusf_(r.w) * sd[n]);
+    float w = alpha * T;
+    T = T * ((1.0f - alpha) + 1e-10f);
+    cr += w * sigmoidf_(r.x);
+    cg += w * sigmoidf_(r.y);
+    cb += w * sigmoidf_(r.z);
+    depth += w * sz[n];
+    acc += w;
+    if (WRITE_W) wp[(int64_t)n * K] = w;
+  }
+  float disp = 1.0f / fmaxf(2e-10f, depth / (acc + 1e-10f) + 1e-10f);
+  if (white_bkgd) {
+    float bg = 1.0f - acc;
+    cr += bg; cg += bg; cb += bg;
+  }
+  rgb_map[(b * 3 + 0) * K + k] = cr;
+  rgb_map[(b * 3 + 1) * K + k] = cg;
+  rgb_map[(b * 3 + 2) * K + k] = cb;
+  disp_map[b * K + k] = disp;
+  depth_map[b * K + k] = depth;
+}
+
+int launch_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride, int white_bkgd,
+                       float* rgb_map, float* disp_map, float* weights, float* depth_map, int64_t B, int N, int K,
+                       cudaStream_t s) {
+  if (B == 0) return CFN_OK;
+  CFN_CHECK_ARG(N >= 1 && N <= 4096 && K >= 1, "raw2outputs: unsupported N=%d K=%d", N, K);
+  int KG = (K + 31) / 32;
+  int64_t warps = B * KG;
+  unsigned grid = (unsigned)((warps + 3) / 4);
+  size_t smem = (size_t)4 * 2 * N * sizeof(float);
+  if (weights)
+    raw2outputs_kernel<true><<<grid, 128, smem, s>>>(raw, z_vals, rays_d, rays_d_stride, white_bkgd, rgb_map, disp_map,
+                                                     weights, depth_map, B, N, K, KG);
+  else
+    raw2outputs_kernel<false><<<grid, 128, smem, s>>>(raw, z_vals, rays_d, rays_d_stride, white_bkgd, rgb_map,
+                                                      disp_map, weights, depth_map, B, N, K, KG);
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A9: sample_pdf — bit-exact with oracle/cfnerf_oracle.py::sample_pdf (sequential fp32 sums, IEEE
+// division, no FMA contraction).  One warp per ray: lane 0 runs the two sequential scans (the order IS the
+// specification), all lanes then invert the CDF for their share of the Nf uniforms by binary search.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
+                                                         const float* __restrict__ u, float* __restrict__ samples,
+                                                         int32_t* __restrict__ below_out, int64_t B, int M, int Nf) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* cdf = smem + warp * 2 * M;
+  float* sb = cdf + M;
+  int64_t b = (int64_t)blockIdx.x * 4 + warp;
+  if (b >= B) return;
+  const float* wrow = weights + b * (M - 1);
+  // stage w + 1e-5 into cdf[1..M-1] and the bins
+  for (int j = lane; j < M - 1; j += 32) cdf[j + 1] = __fadd_rn(wrow[j], 1e-5f);
+  for (int j = lane; j < M; j += 32) sb[j] = bins[b * M + j];
+  __syncwarp();
+  if (lane == 0) {
+    float total = 0.0f;
+    for (int j = 1; j < M; ++j) total = __fadd_rn(total, cdf[j]);
+    float c = 0.0f;
+    cdf[0] = 0.0f;
+    for (int j = 1; j < M; ++j) {
+      c = __fadd_rn(c, __fdiv_rn(cdf[j], total));
+      cdf[j] = c;
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < Nf; i += 32) {
+    float uu = u[b * Nf + i];
+    // inds = #{j : cdf[j] <= u}  (searchsorted right=True); cdf is non-decreasing
+    int lo = 0, hi = M;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+    }
+    int below = max(lo - 1, 0), above = min(lo, M - 1);
+    float cb = cdf[below], ca = cdf[above];
+    float denom = __fsub_rn(ca, cb);
+    if (denom < 1e-5f) denom = 1.0f;
+    float t = __fdiv_rn(__fsub_rn(uu, cb), denom);
+    float bb = sb[below], ba = sb[above];
+    samples[b * Nf + i] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+    if (below_out) below_out[b * Nf + i] = below;
+  }
+}
+
+int launch_sample_pdf(const float* bins, const float* weights, const float* u, float* samples, int32_t* below,
+                      int64_t B, int M, int Nf, cudaStream_t s) {
+  if (B == 0 || Nf == 0) return CFN_OK;
+  CFN_CHECK_ARG(M >= 2 && M <= 2048, "sample_pdf: unsupported M=%d", M);
+  unsigned grid = (unsigned)((B + 3) / 4);
+  sample_pdf_kernel<<<grid, 128, (size_t)4 * 2 * M * sizeof(float), s>>>(bins, weights, u, samples, below, B, M, Nf);
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+// sort(cat[a,b]) per ray by ranking: element i goes to position #{j : v_j < v_i or (v_j == v_i and j < i)}.
+__global__ void merge_sorted_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                    int Na, int Nb) {
+  extern __shared__ float v[];
+  int64_t ray = blockIdx.x;
+  int T = Na + Nb;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) v[i] = (i < Na) ? a[ray * Na + i] : b[ray * Nb + (i - Na)];
+  __syncthreads();
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    float x = v[i];
+    int rank = 0;
+    for (int j = 0; j < T; ++j) {
+      float y = v[j];
+      rank += (y < x) || (y == x && j < i);
+    }
+    out[ray * T + rank] = x;
+  }
+}
+
+int launch_merge_sorted(const float* a, const float* b, float* out, int64_t B, int Na, int Nb, cudaStream_t s) {
+  if (B == 0) return CFN_OK;
+  int T = Na + Nb;
+  CFN_CHECK_ARG(T >= 1 && T <= 8192, "merge_sorted: unsupported size %d", T);
+  int threads = T < 256 ? ((T + 31) / 32) * 32 : 256;
+  merge_sorted_kernel<<<(unsigned)B, threads, (size_t)T * sizeof(float), s>>>(a, b, out, Na, Nb);
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+__global__ void mean_over_k_kernel(const float* __restrict__ w, float* __restrict__ out, int64_t rows, int K) {
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s += w[row * K + k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = s / (float)K;
+}
+
+int launch_mean_over_k(const float* w, float* out, int64_t rows, int K, cudaStream_t s) {
+  if (rows == 0) return CFN_OK;
+  int64_t threads = rows * 32;
+  mean_over_k_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(w, out, rows, K);
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+}  // namespace cfn

@@ -1,0 +1,144 @@
+/* cfnerf_b200 — C-ABI of the B200-native CF-NeRF render/train hot path.
+ *
+ * This header is the drop-in boundary.  The reference (poetrywanderer/CF-NeRF) is pure
+ * Python and has no FFI layer of its own; the callables a maintainer rebinds are
+ *   run_nerf_uncertainty_NF.py:457-553  render_rays      -> cfn_zvals_f32 + cfn_network_fwd + cfn_flow_composite_fwd
+ *   run_nerf_uncertainty_NF.py:67-85    run_network      -> cfn_network_fwd (+ cfn_flow_composite_fwd for raw)
+ *   run_nerf_uncertainty_NF.py:411-454  raw2outputs      -> cfn_raw2outputs_f32
+ *   run_nerf_helpers.py:9-11 (comment)  sample_pdf       -> cfn_sample_pdf_f32, cfn_merge_sorted_f32
+ *   model/models.py:188-291             NeRF_Flows.forward / autograd backward -> *_fwd / *_bwd below
+ * (cfnerf_b200/api.py holds the ctypes binding and the Python functions with the reference signatures;
+ *  INTEGRATION.md shows the stub a maintainer adds to the reference.)
+ *
+ * Conventions: every function returns 0 on success and a negative CFN_E* code on failure, with a
+ * thread-local message available from cfn_last_error().  All data pointers are DEVICE pointers owned by
+ * the caller (fp32, row-major, contiguous unless a stride is passed); `stream` is a cudaStream_t passed as
+ * void*; no function allocates device memory except cfn_create / cfn_pack_weights (handle-owned packed
+ * weights).  Calls on one handle must be serialised by the caller; different handles are independent.
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef CFNERF_B200_H
+#define CFNERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFN_OK 0
+#define CFN_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define CFN_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define CFN_ESTATE (-3)   /* call order violated (e.g. weights not packed) */
+#define CFN_ENOMEM (-4)   /* workspace too small */
+
+/* precision modes of the MLP chain (the only dense contraction on the path) */
+#define CFN_PREC_FP32 0 /* CUDA-core fp32 FMA GEMMs: the 1e-5 "check" mode and the round-1 training path   */
+#define CFN_PREC_BF16 1 /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulation in TMEM                  */
+#define CFN_PREC_FP16 2 /* tcgen05.mma kind::f16, fp16 operands (11-bit significand, TF32-class), fp32 acc  */
+
+/* Architecture of one NeRF_Flows network (model/models.py:20-36; run_nerf_uncertainty_NF.py:317-336). */
+typedef struct CfnConfig {
+  int32_t D;        /* --netdepth          (8)   */
+  int32_t W;        /* --netwidth          (512) */
+  int32_t L_pos;    /* --multires          (10)  -> 3+6L = 63 input channels */
+  int32_t L_dir;    /* --multires_views    (4)   -> 27 view channels         */
+  int32_t h_alpha;  /* --h_alpha_size      (64)  */
+  int32_t h_rgb;    /* --h_rgb_size        (64)  */
+  int32_t F;        /* --n_flows           (4)   */
+  int32_t K;        /* --K_samples         (32)  */
+  int32_t precision; /* CFN_PREC_* */
+} CfnConfig;
+
+typedef struct CfnHandle CfnHandle;
+
+const char* cfn_last_error(void);
+int cfn_version(void);
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+int cfn_create(const CfnConfig* cfg, CfnHandle** out);
+int cfn_destroy(CfnHandle* h);
+
+/* The parameter tensors the path reads, in the order cfn_pack_weights / cfn_network_bwd expect them.
+ * Names are the keys of NeRF_Flows.state_dict() (model/models.py:38-67, 339-350); the two dead heads
+ * alpha_linear / alpha_std_linear (models.py:59-60) are not part of the list. */
+int cfn_param_count(const CfnHandle* h);
+const char* cfn_param_name(const CfnHandle* h, int i);
+int64_t cfn_param_numel(const CfnHandle* h, int i);
+
+/* Copy/convert the fp32 master parameters into the handle's packed device layouts (fp32 gathered flow
+ * conditioning matrices; for the tensor-core modes also the bf16/fp16 pre-swizzled UMMA weight stream).
+ * Call after every optimizer step.  params[i] is a device pointer to tensor i (fp32, contiguous). */
+int cfn_pack_weights(CfnHandle* h, const float* const* params, int n_params, void* stream);
+
+/* floats per 3-D point produced by the network stage: 18*F (alpha: d1,d2,b per flow; rgb: R1 (6), R2 (6), b (3) per flow) */
+int cfn_flow_param_width(const CfnHandle* h);
+
+/* ---- A1: sample schedule along each ray (run_nerf_uncertainty_NF.py:510-532) ------------------- */
+/* rays (B,11) [o d near far viewdir]; t_vals (N) the [0,1] schedule; t_rand (B,N) stratified uniforms or
+ * NULL (perturb == 0); writes z_vals (B,N) with the reference's fp32 operation order. */
+int cfn_zvals_f32(const float* rays, const float* t_vals, const float* t_rand, int lindisp, float* z_vals,
+                  int64_t B, int N, void* stream);
+
+/* ---- A2-A5: positional encoding + MLP trunk/heads + flow conditioning ------------------------ */
+/* Bytes of caller-provided workspace cfn_network_fwd needs for n_points points.
+ * save_for_backward != 0 sizes it for the training path (activations kept for cfn_network_bwd). */
+int cfn_workspace_bytes(const CfnHandle* h, int64_t n_points, int save_for_backward, size_t* out);
+
+/* Points are either given explicitly (pts (B*N,3), run_network semantics, run_nerf_uncertainty_NF.py:67-85)
+ * or, when pts == NULL, generated as o + d*z from rays (B,11) and z_vals (B,N) (main:534).
+ * viewdirs (B,3) may be NULL when rays is given (columns 8..10 are used).
+ * flow_params (B*N, 18F) receives the per-point conditional flow parameters (diagonals already tanh'ed). */
+int cfn_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts, const float* viewdirs,
+                    int64_t B, int N, float* flow_params, void* workspace, size_t workspace_bytes,
+                    int save_for_backward, void* stream);
+
+/* Backward of cfn_network_fwd (training path).  g_flow_params (B*N,18F) is d loss / d flow_params;
+ * workspace must be the one a save_for_backward forward of the same points filled.  grads[i] (device,
+ * fp32, same shapes/order as the parameters; entries may be NULL to skip) are OVERWRITTEN for i >= 4
+ * (the four global latent parameters 0..3 get their gradient from cfn_flow_composite_bwd). */
+int cfn_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, void* workspace,
+                    size_t workspace_bytes, float* const* grads, int n_params, void* stream);
+
+/* ---- A6-A8 (+A11 partials): K-sample flows + alpha compositing --------------------------------- */
+/* eps_alpha (K), eps_rgb (K,3): base latent draws (models.py:198-206 / 233-251), shared by all points.
+ * rays_d: pointer to the first direction, rays_d_stride floats between rays (11 when it points into a ray batch).
+ * Outputs: rgb_map (B,3,K), disp_map (B,K), depth_map (B,K); optional raw (B,N,K,4) [rgb|sigma],
+ * weights (B,N,K); optional logdet_sums (B,2): per-ray sums over (n,k) of the alpha / rgb log-det terms
+ * (models.py:263,278) for the entropy loss; optional kstats (B,8): mean_k rgb (3), "uncertainty" std
+ * (unbiased std * K/(K-1), main:1034/1130) (3), mean_k depth, mean_k disp.  Any optional pointer may be NULL. */
+int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, const float* z_vals, const float* rays_d,
+                           int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t B, int N,
+                           int white_bkgd, float* rgb_map, float* disp_map, float* depth_map, float* raw,
+                           float* weights, float* logdet_sums, float* kstats, void* stream);
+
+/* Backward.  g_rgb_map (B,3,K) and g_depth_map (B,K) (NULL = zero) are upstream
+ * gradients; g_logdet_alpha / g_logdet_rgb are d loss / d(sum of log-dets) (scalars, e.g. -beta1/(B*N*K)).
+ * Writes g_flow_params (B*N,18F) and g_globals_partial (B,8): per-ray
+ * partial sums of d/d[alpha_mean, alpha_std, rgb_mean(3), rgb_std(3)] through z0 = eps*std+mean only (the caller sums
+ * over rays; kept per ray so the result is deterministic). */
+int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, const float* z_vals, const float* rays_d,
+                           int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t B, int N,
+                           int white_bkgd, const float* g_rgb_map, const float* g_depth_map, float g_logdet_alpha,
+                           float g_logdet_rgb, float* g_flow_params, float* g_globals_partial, void* stream);
+
+/* ---- A8 stand-alone: raw2outputs (run_nerf_uncertainty_NF.py:411-454) ------------------------ */
+int cfn_raw2outputs_f32(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
+                        int white_bkgd, float* rgb_map, float* disp_map, float* weights, float* depth_map,
+                        int64_t B, int N, int K, void* stream);
+
+/* ---- A9: hierarchical resampling (extension; oracle/cfnerf_oracle.py sample_pdf) ------------ */
+/* bins (B,M), weights (B,M-1), u (B,Nf) -> samples (B,Nf), optional below (B,Nf) int32.  Bit-exact with
+ * the sequential-fp32 oracle. */
+int cfn_sample_pdf_f32(const float* bins, const float* weights, const float* u, float* samples, int32_t* below,
+                       int64_t B, int M, int Nf, void* stream);
+/* out (B,Na+Nb) = sort(cat[a (B,Na), b (B,Nb)]) per row (values only). */
+int cfn_merge_sorted_f32(const float* a, const float* b, float* out, int64_t B, int Na, int Nb, void* stream);
+/* mean over K of weights (B,N,K) -> (B,N)  (the shared fine grid decision) */
+int cfn_mean_over_k_f32(const float* w, float* out, int64_t rows, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFNERF_B200_H */
