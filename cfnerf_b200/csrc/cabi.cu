@@ -234,7 +234,7 @@ extern "C" int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, co
                                       const float* eps_rgb, int64_t B, int N, int white_bkgd, float* rgb_map,
                                       float* disp_map, float* depth_map, float* raw, float* weights,
                                       float* logdet_sums, float* kstats, void* stream) {
-  CFN_CHECK_ARG(h && flow_params && z_vals && rays_d && eps_alpha && eps_rgb && rgb_map && disp_map && depth_map,
+  CFN_CHECK_ARG(h && B >= 0 && (B == 0 || (flow_params && z_vals && rays_d && eps_alpha && eps_rgb && rgb_map && disp_map && depth_map)),
                 "cfn_flow_composite_fwd: null argument");
   if (!h->packed) {
     set_error("cfn_flow_composite_fwd: call cfn_pack_weights first");
@@ -265,7 +265,8 @@ extern "C" int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, co
 extern "C" int cfn_raw2outputs_f32(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
                                    int white_bkgd, float* rgb_map, float* disp_map, float* weights,
                                    float* depth_map, int64_t B, int N, int K, void* stream) {
-  CFN_CHECK_ARG(raw && z_vals && rays_d && rgb_map && disp_map && depth_map && B >= 0,
+  CFN_CHECK_ARG(B >= 0, "cfn_raw2outputs_f32: negative batch");
+  CFN_CHECK_ARG(B == 0 || (raw && z_vals && rays_d && rgb_map && disp_map && depth_map),
                 "cfn_raw2outputs_f32: null argument");
   return launch_raw2outputs(raw, z_vals, rays_d, rays_d_stride, white_bkgd, rgb_map, disp_map, weights, depth_map, B,
                             N, K, (cudaStream_t)stream);
@@ -273,13 +274,14 @@ extern "C" int cfn_raw2outputs_f32(const float* raw, const float* z_vals, const 
 
 extern "C" int cfn_sample_pdf_f32(const float* bins, const float* weights, const float* u, float* samples,
                                   int32_t* below, int64_t B, int M, int Nf, void* stream) {
-  CFN_CHECK_ARG(bins && weights && u && samples && B >= 0, "cfn_sample_pdf_f32: null argument");
+  CFN_CHECK_ARG(B >= 0 && (B == 0 || Nf == 0 || (bins && weights && u && samples)), "cfn_sample_pdf_f32: null argument");
   return launch_sample_pdf(bins, weights, u, samples, below, B, M, Nf, (cudaStream_t)stream);
 }
 
 extern "C" int cfn_merge_sorted_f32(const float* a, const float* b, float* out, int64_t B, int Na, int Nb,
                                     void* stream) {
-  CFN_CHECK_ARG(a && b && out && B >= 0, "cfn_merge_sorted_f32: null argument");
+  CFN_CHECK_ARG(B >= 0 && Na >= 0 && Nb >= 0, "cfn_merge_sorted_f32: negative size");
+  CFN_CHECK_ARG(B == 0 || ((a || Na == 0) && (b || Nb == 0) && (out || Na + Nb == 0)), "cfn_merge_sorted_f32: null argument");
   return launch_merge_sorted(a, b, out, B, Na, Nb, (cudaStream_t)stream);
 }
 

@@ -233,7 +233,7 @@ int launch_flow_composite_fwd(int F, int K, const float* globals, const float* f
                               float* raw, float* weights, float* logdet_sums, float* kstats, cudaStream_t s) {
   if (B == 0) return CFN_OK;
   CFN_CHECK_ARG(F >= 1 && F <= kMaxF, "flow_composite: n_flows=%d unsupported (1..%d)", F, kMaxF);
-  CFN_CHECK_ARG(N >= 1 && N <= 2048 && K >= 1, "flow_composite: unsupported N=%d K=%d", N, K);
+  CFN_CHECK_ARG(N >= 1 && N <= 2048 && K >= 1, "flow_composite: unsupported N=%d K=%d (need 1 <= N <= 2048)", N, K);
   size_t smem = fwd_smem_bytes(F, N);
   unsigned grid = (unsigned)((B + 3) / 4);
   const bool train = logdet_sums != nullptr;
@@ -483,7 +483,7 @@ int launch_flow_composite_bwd(int F, int K, const float* globals, const float* f
                               cudaStream_t s) {
   if (B == 0) return CFN_OK;
   CFN_CHECK_ARG(F >= 1 && F <= kMaxF, "flow_composite_bwd: n_flows=%d unsupported (1..%d)", F, kMaxF);
-  CFN_CHECK_ARG(N >= 1 && N <= 320 && K >= 1, "flow_composite_bwd: unsupported N=%d (<=320) K=%d", N, K);
+  CFN_CHECK_ARG(N >= 2 && N <= 320 && K >= 1, "flow_composite_bwd: unsupported N=%d (<=320) K=%d", N, K);
   const int PP = 18 * F;
   size_t smem = (size_t)4 * (2 * N + N * 32 + PP * 33 + PP) * sizeof(float);
   unsigned grid = (unsigned)((B + 3) / 4);

@@ -19,7 +19,7 @@ struct ParamSlot {
   int64_t offset;     // float offset inside w32
 };
 
-struct TcPlan;  // tensor-core weight stream + launch plan (mlp_tc.cu)
+namespace cfn { struct TcPlan; }  // tensor-core weight stream + launch plan (mlp_tc.cu)
 
 struct CfnHandle {
   CfnConfig cfg;
@@ -45,7 +45,7 @@ struct CfnHandle {
   std::vector<GatherRow> gatherA, gatherC;
   float** grads_table_dev;  // (n slots) scratch pointer table for cfn_network_bwd
 
-  TcPlan* tc;        // nullptr in fp32 mode
+  cfn::TcPlan* tc;   // nullptr in fp32 mode
 };
 
 namespace cfn {

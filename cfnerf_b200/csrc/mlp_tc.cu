@@ -1,9 +1,771 @@
-// placeholder until the tcgen05 kernel lands (replaced in the next commit)
+// K1 — the network stage on the 5th-generation tensor cores (CFN_PREC_BF16 / CFN_PREC_FP16).
+//
+// One persistent CTA pair per two SMs (cta_group::2, M = 256 points per pair, 128 TMEM lanes per CTA) walks tiles
+// of 128 points per CTA through the WHOLE chain — positional encoding, 8x512 trunk with skip-concat, feature /
+// view layers and the (pre-composed) conditioning heads — without the activations ever leaving the SM:
+//   * gamma(p), gamma(d) are computed in registers and written straight into the swizzled shared-memory A tiles;
+//   * every layer is a tcgen05.mma (kind::f16, fp32 accumulation in TMEM, N = 256 halves) over the 128x512 A tile
+//     that stays resident in shared memory (128B-swizzled K-major chunks of 64 columns);
+//   * the weights are ONE linear, pre-tiled bf16/fp16 stream in HBM/L2 that the TMA (cp.async.bulk.tensor,
+//     SWIZZLE_128B) streams through a ring of shared-memory stages; with cta_group::2 each CTA loads half of every
+//     weight tile, so the pair reads each weight byte once;
+//   * the epilogue warps drain TMEM (tcgen05.ld), add the fp32 bias, apply ReLU, convert and store the next
+//     layer's A chunk in place; per-chunk mbarriers let the next layer's MMAs start while the drain is running;
+//   * the last two GEMMs emit the 18F conditional-flow parameters per point (tanh on the diagonals) to HBM.
+// Because h_alpha_linear / h_rgb_linear feed the amortisation Linears with no nonlinearity in between
+// (models.py:175,182 -> 366-368,380) they are composed into one matrix each at pack time.
+//
+// Reference semantics: run_nerf_helpers.py:21-69 (embedding), model/models.py:165-186 (encode),
+// model/models.py:358-385 (amortised parameters).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "handle.h"
+
 namespace cfn {
-int tc_create(CfnHandle*) { set_error("tensor-core path not built"); return CFN_EINVAL; }
-void tc_destroy(CfnHandle*) {}
-int tc_pack(CfnHandle*, cudaStream_t) { return CFN_EINVAL; }
-size_t tc_workspace_bytes(const CfnHandle*, int64_t) { return 0; }
-int tc_network_fwd(CfnHandle*, const float*, const float*, const float*, const float*, int64_t, int, float*, void*, size_t, cudaStream_t) { return CFN_EINVAL; }
+
+constexpr int TC_MAX_STEPS = 24;
+constexpr int TC_MAX_KCH = 10;
+constexpr int TC_CHUNK_BYTES = 128 * 128;   // 128 rows x 64 columns x 2 bytes
+constexpr int TC_SRC_GP = 8, TC_SRC_GD = 9;
+constexpr int TC_THREADS = 384;             // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int TC_MAX_STAGES = 8;
+
+struct TcStep {
+  int kind;       // 0: bias+ReLU -> A tile, 1: bias -> A tile, 2: bias (+tanh where flagged) -> flow_params in HBM
+  int n_total;    // padded output width (multiple of 16, <= 512)
+  int n_part;     // N of one tcgen05.mma (<= 256)
+  int n_parts;
+  int order_rev;  // issue the parts in reverse order (lets a pending drain of TMEM columns 0..63 finish)
+  int n_k;        // K chunks
+  int ksrc[TC_MAX_KCH];    // 0..7: activation chunk, 8: gamma(p), 9: gamma(d)
+  int ksteps[TC_MAX_KCH];  // K=16 instructions issued on that chunk (1..4)
+  int bias_off;   // floats into the table: bias[n_total] (then flags[n_total] for kind 2)
+  int out_col;    // kind 2: first column in the flow-parameter record
+  int n_valid;    // kind 2: valid output columns
+  int row0;       // first row of this step's blocks in the weight stream (rows of 64 elements)
+};
+
+struct TcPlanDev {
+  int n_steps;
+  int act_chunks;
+  TcStep steps[TC_MAX_STEPS];
+};
+
+struct TcArgs {
+  const float* rays; const float* z_vals; const float* pts; const float* viewdirs;
+  int64_t M; int N; int L_pos; int L_dir;
+  const float* table;   // biases / tanh flags
+  float* flow_params; int PP;
+  int64_t n_units;      // tiles of 128*CG points
+  int stages; int stage_bytes;
+};
+
+struct TcPlan {
+  TcPlanDev dev;
+  int cg;                       // cta_group (1 or 2)
+  void* stream_dev;             // packed weight stream (2-byte elements)
+  int64_t stream_rows;
+  float* table_dev;             // biases + flags
+  std::vector<float> table_host_flags;   // unused placeholder for symmetry
+  float* compA; float* compA_b; // composed alpha conditioning (3F x W), (3F)
+  float* compC; float* compC_b; // composed rgb conditioning (15F x W/2), (15F)
+  CUtensorMap tm_big, tm_small;
+  int stages, stage_bytes;
+  size_t smem_bytes;
+  int num_sms;
+  // pack recipe: one entry per 64-column block of the stream
+  struct Block { int src; int row0, rows_valid, col0, cols_valid, rows_padded; int64_t stream_row; };
+  std::vector<Block> blocks;
+  int* blocks_dev;
+  // bias recipe
+  struct BiasSeg { int src; int n_valid; int n_padded; int off; int with_flags; int flag_off; };
+  std::vector<BiasSeg> bias_segs;
+  int table_floats;
+};
+
+// ======================================================================================================
+// PTX wrappers
+// ======================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+// arrive on a barrier addressed in the shared::cluster window (own CTA or the pair's leader)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  if (CG == 1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+  } else {
+    // executed by both CTAs of the pair; the peer bit of the barrier address is cleared so the transaction bytes land
+    // on the leader CTA's barrier
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu) : "memory");
+  }
+}
+
+template <int CG>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// tcgen05.commit: the barrier receives one arrival when every MMA issued so far by this thread has completed.
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// two fp32 -> packed 16-bit pair (lo = element c, hi = element c+1), optional fused ReLU
+template <bool FP16, bool RELU>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t d;
+  if (FP16) {
+    if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  } else {
+    if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  }
+  return d;
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, A/B = bf16 (1) or fp16 (0), both K-major
+__device__ __forceinline__ uint32_t make_idesc(bool fp16, int M, int N) {
+  const uint32_t fmt = fp16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of the 16-byte unit u (0..7) of row r inside a 128B-swizzled 128x64 chunk
+__device__ __forceinline__ uint32_t swz(int r, int u) { return (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4)); }
+
+// ======================================================================================================
+// the kernel
+// ======================================================================================================
+struct TcBarriers {
+  uint64_t full[TC_MAX_STAGES];
+  uint64_t empty[TC_MAX_STAGES];
+  uint64_t act_ready[8];
+  uint64_t acc_full;
+  uint64_t out_done;
+  uint64_t in_ready;
+  uint32_t tmem_ptr;
+  uint32_t pad;
+};
+
+template <bool FP16>
+__device__ __forceinline__ void encode_row(float x, float y, float z, int L, uint32_t chunk_base, int r) {
+  // [x, sin(2^l x), cos(2^l x)]_l in blocks of 3 (run_nerf_helpers.py:29-51), zero padded to 64 columns
+  float e[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) e[i] = 0.f;
+  e[0] = x; e[1] = y; e[2] = z;
+  float f = 1.0f;
+#pragma unroll
+  for (int l = 0; l < 10; ++l) {
+    if (l < L) {
+      float s, c;
+      sincosf(x * f, &s, &c); e[3 + 6 * l + 0] = s; e[3 + 6 * l + 3] = c;
+      sincosf(y * f, &s, &c); e[3 + 6 * l + 1] = s; e[3 + 6 * l + 4] = c;
+      sincosf(z * f, &s, &c); e[3 + 6 * l + 2] = s; e[3 + 6 * l + 5] = c;
+    }
+    f *= 2.0f;
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    uint32_t p0 = pack2<FP16, false>(e[8 * u + 0], e[8 * u + 1]);
+    uint32_t p1 = pack2<FP16, false>(e[8 * u + 2], e[8 * u + 3]);
+    uint32_t p2 = pack2<FP16, false>(e[8 * u + 4], e[8 * u + 5]);
+    uint32_t p3 = pack2<FP16, false>(e[8 * u + 6], e[8 * u + 7]);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(chunk_base + swz(r, u)), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+  }
+}
+
+template <int CG, bool FP16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant__ CUtensorMap tm_small,
+              const __grid_constant__ TcPlanDev plan, const TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by SWIZZLE_128B; the dynamic segment is the only shared allocation
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int act_chunks = plan.act_chunks;
+  const uint32_t act_base = smem_base;
+  const uint32_t gp_base = act_base + act_chunks * TC_CHUNK_BYTES;
+  const uint32_t gd_base = gp_base + TC_CHUNK_BYTES;
+  const uint32_t stage_base = gd_base + TC_CHUNK_BYTES;
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_gen + (stage_base - smem_base) + (size_t)a.stages * a.stage_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int64_t unit0 = blockIdx.x / CG, n_grid_units = gridDim.x / CG;
+
+  // barrier addresses: local (shared::cta) and as seen on the pair's leader (shared::cluster)
+  auto bar_local = [&](const uint64_t* b) { return smem_u32(b); };
+  auto bar_leader = [&](const uint64_t* b) { return (CG == 2) ? mapa_rank(smem_u32(b), 0) : smem_u32(b); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(bar_local(&bars->full[s]), CG); mbar_init(bar_local(&bars->empty[s]), 1); }
+    for (int j = 0; j < 8; ++j) mbar_init(bar_local(&bars->act_ready[j]), 4 * CG);
+    mbar_init(bar_local(&bars->acc_full), 1);
+    mbar_init(bar_local(&bars->out_done), 4 * CG);
+    mbar_init(bar_local(&bars->in_ready), 8 * CG);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&bars->tmem_ptr)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&bars->tmem_ptr)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_ptr);
+
+  if (warp == 0) {
+    // ================================= TMA producer (one lane, both CTAs) =================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
+        for (int g = 0; g < plan.n_steps; ++g) {
+          const TcStep& st = plan.steps[g];
+          const int rows = st.n_part / CG;           // rows of each weight block this CTA stages
+          int blk = 0;
+          for (int pp = 0; pp < st.n_parts; ++pp) {
+            for (int kc = 0; kc < st.n_k; ++kc, ++blk) {
+              mbar_wait(bar_local(&bars->empty[stage]), phase ^ 1u);
+              const uint32_t full_leader = bar_local(&bars->full[stage]);   // peer bit cleared inside tma_load_2d
+              if (rank == 0) mbar_expect_tx(bar_local(&bars->full[stage]), (uint32_t)(rows * 128 * CG));
+              else mbar_arrive_cluster(bar_leader(&bars->full[stage]));
+              const int row_g = st.row0 + blk * st.n_part + (int)rank * rows;
+              const uint32_t dst = stage_base + (uint32_t)stage * a.stage_bytes;
+              int r = 0;
+              for (; rows - r >= 128; r += 128) tma_load_2d<CG>(dst + r * 128, &tm_big, 0, row_g + r, full_leader);
+              for (; r < rows; r += 16) tma_load_2d<CG>(dst + r * 128, &tm_small, 0, row_g + r, full_leader);
+              if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================= MMA issuer (one lane of the leader CTA) =================================
+    if (rank == 0 && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t act_gen = 0, in_cnt = 0, out_cnt = 0;
+      bool pending_out = false;
+      uint32_t waited[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) waited[j] = 0;
+      // wait until activation chunk j of generation `gen` is written (and its TMEM columns drained); barriers are
+      // always consumed one phase at a time so a parity can never alias an older phase
+      auto wait_act = [&](int j, uint32_t gen) {
+        while (waited[j] < gen) { mbar_wait(bar_local(&bars->act_ready[j]), waited[j] & 1u); ++waited[j]; }
+      };
+      for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
+        mbar_wait(bar_local(&bars->in_ready), in_cnt & 1u); ++in_cnt;
+        for (int g = 0; g < plan.n_steps; ++g) {
+          const TcStep& st = plan.steps[g];
+          const uint32_t idesc = make_idesc(FP16, 128 * CG, st.n_part);
+          for (int pi = 0; pi < st.n_parts; ++pi) {
+            const int pp = st.order_rev ? (st.n_parts - 1 - pi) : pi;
+            const int c0 = pp * st.n_part;
+            if (pending_out && c0 < 64) { mbar_wait(bar_local(&bars->out_done), (out_cnt - 1u) & 1u); pending_out = false; }
+            for (int j = c0 / 64; j <= (c0 + st.n_part - 1) / 64 && j < act_chunks; ++j) wait_act(j, act_gen);
+            for (int kc = 0; kc < st.n_k; ++kc) {
+              const int src = st.ksrc[kc];
+              if (src < 8) wait_act(src, act_gen);
+              mbar_wait(bar_local(&bars->full[stage]), phase);
+              tc_fence_after();
+              const uint32_t a_addr = (src < 8) ? (act_base + src * TC_CHUNK_BYTES) : (src == TC_SRC_GP ? gp_base : gd_base);
+              const uint64_t adesc = make_sdesc(a_addr);
+              const uint64_t bdesc = make_sdesc(stage_base + (uint32_t)stage * a.stage_bytes);
+              for (int ks = 0; ks < st.ksteps[kc]; ++ks)
+                umma<CG>(tmem_base + (uint32_t)c0, adesc + 2 * ks, bdesc + 2 * ks, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+              umma_commit<CG>(bar_local(&bars->empty[stage]));
+              if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+          umma_commit<CG>(bar_local(&bars->acc_full));
+          if (st.kind == 2) { pending_out = true; ++out_cnt; } else { ++act_gen; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================= encode + epilogue warps =================================
+    const int e = warp - 4, q = warp & 3, hh = e >> 2;
+    const int row = q * 32 + lane;                         // TMEM lane == row of the tile owned by this thread
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t acc_cnt = 0;
+    for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
+      const int64_t m = (unit * CG + rank) * 128 + row;    // global point index of this row
+      const bool valid = m < a.M;
+      // ---- positional encoding straight into the swizzled A tiles ----
+      {
+        const int64_t b = valid ? (m / a.N) : 0;
+        if (hh == 0) {
+          float px = 0.f, py = 0.f, pz = 0.f;
+          if (valid) {
+            if (a.pts) { px = a.pts[m * 3 + 0]; py = a.pts[m * 3 + 1]; pz = a.pts[m * 3 + 2]; }
+            else {
+              const float* r = a.rays + b * 11; const float z = a.z_vals[m];
+              px = __fadd_rn(r[0], __fmul_rn(r[3], z)); py = __fadd_rn(r[1], __fmul_rn(r[4], z)); pz = __fadd_rn(r[2], __fmul_rn(r[5], z));
+            }
+          }
+          encode_row<FP16>(px, py, pz, a.L_pos, gp_base, row);
+        } else {
+          float dx = 0.f, dy = 0.f, dz = 0.f;
+          if (valid) {
+            const float* vd = a.viewdirs ? (a.viewdirs + b * 3) : (a.rays + b * 11 + 8);
+            dx = vd[0]; dy = vd[1]; dz = vd[2];
+          }
+          encode_row<FP16>(dx, dy, dz, a.L_dir, gd_base, row);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->in_ready));
+      }
+      for (int g = 0; g < plan.n_steps; ++g) {
+        const TcStep& st = plan.steps[g];
+        mbar_wait(bar_local(&bars->acc_full), acc_cnt & 1u); ++acc_cnt;
+        tc_fence_after();
+        const float* bias = a.table + st.bias_off;
+        if (st.kind == 2) {
+          if (hh == 0) {
+            float* out = a.flow_params + m * a.PP + st.out_col;
+            const float* flags = bias + st.n_total;
+            for (int c0 = 0; c0 < st.n_total; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld16(tmem_row + (uint32_t)c0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                if (c0 + i < st.n_valid) {
+                  const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+                  const float4 ff = __ldg(reinterpret_cast<const float4*>(flags + c0 + i));
+                  float o[4];
+                  o[0] = __uint_as_float(v[i + 0]) + bb.x; o[1] = __uint_as_float(v[i + 1]) + bb.y;
+                  o[2] = __uint_as_float(v[i + 2]) + bb.z; o[3] = __uint_as_float(v[i + 3]) + bb.w;
+                  if (ff.x != 0.f) o[0] = tanhf(o[0]);
+                  if (ff.y != 0.f) o[1] = tanhf(o[1]);
+                  if (ff.z != 0.f) o[2] = tanhf(o[2]);
+                  if (ff.w != 0.f) o[3] = tanhf(o[3]);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (valid && c0 + i + k < st.n_valid) out[c0 + i + k] = o[k];   // record rows are only 8-byte aligned for odd F
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->out_done));
+          }
+        } else {
+          const int n_out_chunks = st.n_total / 64;
+          for (int j = hh; j < act_chunks; j += 2) {
+            if (j < n_out_chunks) {
+              const uint32_t chunk = act_base + j * TC_CHUNK_BYTES;
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                uint32_t v[32];
+                tmem_ld32(tmem_row + (uint32_t)(j * 64 + half * 32), v);
+                tmem_ld_wait();
+                const float4* bp = reinterpret_cast<const float4*>(bias + j * 64 + half * 32);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float4 b0 = __ldg(bp + 2 * u), b1 = __ldg(bp + 2 * u + 1);
+                  const float x0 = __uint_as_float(v[8 * u + 0]) + b0.x, x1 = __uint_as_float(v[8 * u + 1]) + b0.y;
+                  const float x2 = __uint_as_float(v[8 * u + 2]) + b0.z, x3 = __uint_as_float(v[8 * u + 3]) + b0.w;
+                  const float x4 = __uint_as_float(v[8 * u + 4]) + b1.x, x5 = __uint_as_float(v[8 * u + 5]) + b1.y;
+                  const float x6 = __uint_as_float(v[8 * u + 6]) + b1.z, x7 = __uint_as_float(v[8 * u + 7]) + b1.w;
+                  uint32_t p0, p1, p2, p3;
+                  if (st.kind == 0) {
+                    p0 = pack2<FP16, true>(x0, x1); p1 = pack2<FP16, true>(x2, x3);
+                    p2 = pack2<FP16, true>(x4, x5); p3 = pack2<FP16, true>(x6, x7);
+                  } else {
+                    p0 = pack2<FP16, false>(x0, x1); p1 = pack2<FP16, false>(x2, x3);
+                    p2 = pack2<FP16, false>(x4, x5); p3 = pack2<FP16, false>(x6, x7);
+                  }
+                  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};"
+                               :: "r"(chunk + swz(row, half * 4 + u)), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+                }
+              }
+              fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+              tc_fence_before();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->act_ready[j]));
+          }
+        }
+      }
+    }
+  }
+
+  // teardown: everything issued has been consumed (the epilogue waited for the last commit)
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ======================================================================================================
+// weight stream packing
+// ======================================================================================================
+struct PackSrc { const float* ptr; int ld; };
+struct PackSrcTable { PackSrc s[40]; };
+
+// one CUDA block per stream block: [rows_padded][64] 2-byte elements, zero padded
+template <bool FP16>
+__global__ void pack_stream_kernel(PackSrcTable srcs, const int* __restrict__ blocks, uint16_t* __restrict__ stream) {
+  const int* b = blocks + blockIdx.x * 8;
+  const int src = b[0], row0 = b[1], rows_valid = b[2], col0 = b[3], cols_valid = b[4], rows_padded = b[5];
+  const int64_t stream_row = ((int64_t)(uint32_t)b[7] << 31) | (uint32_t)b[6];
+  const PackSrc S = srcs.s[src];
+  for (int i = threadIdx.x; i < rows_padded * 64; i += blockDim.x) {
+    const int r = i >> 6, c = i & 63;
+    float v = 0.f;
+    if (r < rows_valid && c < cols_valid) v = S.ptr[(int64_t)(row0 + r) * S.ld + col0 + c];
+    uint16_t o;
+    if (FP16) o = __half_as_ushort(__float2half_rn(v));
+    else o = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    stream[(stream_row + r) * 64 + c] = o;
+  }
+}
+
+// bias table: table[off + i] = (i < n_valid) ? src[i] : 0
+__global__ void pack_bias_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_valid, int n_padded) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_padded) dst[i] = (i < n_valid) ? src[i] : 0.f;
+}
+
+// composed bias: out[r] = sum_k am[r,k] * hb[k] + ab[r]
+__global__ void compose_bias_kernel(const float* __restrict__ am, const float* __restrict__ hb, const float* __restrict__ ab,
+                                    float* __restrict__ out, int rows, int k) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int i = 0; i < k; ++i) s = fmaf(am[r * k + i], hb[i], s);
+  out[r] = s + ab[r];
+}
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_tensor_map(CUtensorMap* map, void* base, int64_t rows, int box_rows, bool fp16) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CFN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available from the driver"); return CFN_ECUDA; }
+    fn = (EncodeTiledFn)p;
+  }
+  cuuint64_t gdim[2] = {64, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CFN_ECUDA; }
+  return CFN_OK;
+}
+
+// source ids for the pack recipe
+enum { SRC_COMP_A = 30, SRC_COMP_C = 31 };   // 0..29: parameter slot / 2 for weights (slot index itself is used)
+
+int tc_create(CfnHandle* h) {
+  const CfnConfig& c = h->cfg;
+  const int W = c.W, F = c.F, D = c.D;
+  CFN_CHECK_ARG(W % 64 == 0 && W >= 128 && W <= 512, "tensor-core path: netwidth %d unsupported (multiple of 64 in 128..512)", W);
+  CFN_CHECK_ARG(h->in_pos <= 64 && h->in_dir <= 32, "tensor-core path: multires %d / multires_views %d unsupported (<=10 / <=4)", c.L_pos, c.L_dir);
+  CFN_CHECK_ARG(15 * F <= 256, "tensor-core path: n_flows %d unsupported", F);
+  CFN_CHECK_ARG(D + 4 <= TC_MAX_STEPS, "tensor-core path: netdepth %d unsupported", D);
+  CFN_CHECK_ARG(h->slots.size() <= 30, "too many parameter tensors");
+  TcPlan* p = new TcPlan();
+  h->tc = p;
+  p->cg = 2;
+  if (const char* e = getenv("CFN_TC_CTA_GROUP")) p->cg = (atoi(e) == 1) ? 1 : 2;
+  const int CG = p->cg;
+  p->stream_dev = nullptr; p->table_dev = nullptr; p->compA = p->compA_b = p->compC = p->compC_b = nullptr; p->blocks_dev = nullptr;
+  TcPlanDev& dev = p->dev;
+  memset(&dev, 0, sizeof(dev));
+  dev.act_chunks = W / 64;
+  const int AC = dev.act_chunks;
+  int64_t stream_row = 0;
+  int table_off = 0;
+
+  auto add_step = [&](int kind, int n_valid, int n_part_max, bool rev, std::vector<std::pair<int, int>> kch,
+                      // per K chunk: (source matrix id, first column) ; rows come from the part
+                      int src_mat, std::vector<int> kcol0, std::vector<int> kcols_valid, int bias_src, int out_col) {
+    TcStep& st = dev.steps[dev.n_steps++];
+    st.kind = kind;
+    const int gran = 16 * CG;                       // UMMA N granularity (16 per CTA)
+    int n_total = ((n_valid + gran - 1) / gran) * gran;
+    if (kind != 2) n_total = ((n_valid + 63) / 64) * 64;
+    st.n_total = n_total;
+    st.n_part = n_total < n_part_max ? n_total : n_part_max;
+    st.n_parts = (n_total + st.n_part - 1) / st.n_part;
+    st.order_rev = rev ? 1 : 0;
+    st.n_k = (int)kch.size();
+    for (int i = 0; i < st.n_k; ++i) { st.ksrc[i] = kch[i].first; st.ksteps[i] = kch[i].second; }
+    st.bias_off = table_off;
+    st.out_col = out_col;
+    st.n_valid = n_valid;
+    st.row0 = (int)stream_row;
+    // stream blocks in the order the producer consumes them: issue-order parts, then K chunks
+    for (int pi = 0; pi < st.n_parts; ++pi) {
+      const int pp = st.order_rev ? (st.n_parts - 1 - pi) : pi;
+      for (int i = 0; i < st.n_k; ++i) {
+        TcPlan::Block b;
+        b.src = src_mat;
+        b.row0 = pp * st.n_part;
+        b.rows_valid = std::max(0, std::min(st.n_part, n_valid - b.row0));
+        b.col0 = kcol0[i];
+        b.cols_valid = kcols_valid[i];
+        b.rows_padded = st.n_part;
+        b.stream_row = stream_row;
+        p->blocks.push_back(b);
+        stream_row += st.n_part;
+      }
+    }
+    TcPlan::BiasSeg bs{bias_src, n_valid, n_total, table_off, kind == 2 ? 1 : 0, out_col};
+    p->bias_segs.push_back(bs);
+    table_off += n_total * (kind == 2 ? 2 : 1);
+  };
+
+  // trunk
+  for (int i = 0; i < D; ++i) {
+    std::vector<std::pair<int, int>> kch; std::vector<int> col0, cv;
+    const int slot = h->s_pts(i, 0);
+    if (i == 0) { kch.push_back({TC_SRC_GP, 4}); col0.push_back(0); cv.push_back(h->in_pos); }
+    else if (h->skip >= 0 && i == h->skip + 1) {
+      kch.push_back({TC_SRC_GP, 4}); col0.push_back(0); cv.push_back(h->in_pos);           // cat[gamma(p), h] (models.py:171-172)
+      for (int j = 0; j < AC; ++j) { kch.push_back({j, 4}); col0.push_back(h->in_pos + 64 * j); cv.push_back(64); }
+    } else {
+      for (int j = 0; j < AC; ++j) { kch.push_back({j, 4}); col0.push_back(64 * j); cv.push_back(64); }
+    }
+    add_step(0, W, 256, false, kch, slot, col0, cv, slot + 1, 0);
+  }
+  // composed alpha conditioning from h7 (N = 3F), then the feature layer (parts reversed so that the drain of
+  // TMEM columns 0..63 by the alpha epilogue overlaps the first feature MMAs)
+  {
+    std::vector<std::pair<int, int>> kch; std::vector<int> col0, cv;
+    for (int j = 0; j < AC; ++j) { kch.push_back({j, 4}); col0.push_back(64 * j); cv.push_back(64); }
+    add_step(2, 3 * F, 256, false, kch, SRC_COMP_A, col0, cv, SRC_COMP_A, 0);
+    add_step(1, W, 256, true, kch, h->s_feat, col0, cv, h->s_feat + 1, 0);
+    // view layer on cat[feature, gamma(d)] (models.py:177-181)
+    kch.push_back({TC_SRC_GD, 2}); col0.push_back(W); cv.push_back(h->in_dir);
+    add_step(0, W / 2, 256, false, kch, h->s_views, col0, cv, h->s_views + 1, 0);
+  }
+  // composed rgb conditioning from the view features (N = 15F)
+  {
+    std::vector<std::pair<int, int>> kch; std::vector<int> col0, cv;
+    for (int j = 0; j < (W / 2 + 63) / 64; ++j) { kch.push_back({j, (W / 2 - 64 * j) >= 64 ? 4 : (W / 2 - 64 * j) / 16}); col0.push_back(64 * j); cv.push_back(std::min(64, W / 2 - 64 * j)); }
+    add_step(2, 15 * F, 256, false, kch, SRC_COMP_C, col0, cv, SRC_COMP_C, 3 * F);
+  }
+  p->stream_rows = stream_row;
+  p->table_floats = table_off;
+
+  cudaDeviceProp prop;
+  int devid = 0;
+  auto fail = [&](const char* what) { set_error("tc_create: %s", what); return CFN_ECUDA; };
+  if (cudaGetDevice(&devid) != cudaSuccess || cudaGetDeviceProperties(&prop, devid) != cudaSuccess) return fail("device query");
+  if (prop.major != 10) { set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor); return CFN_EINVAL; }
+  p->num_sms = prop.multiProcessorCount;
+  p->stage_bytes = (256 / CG) * 128;
+  const size_t fixed = (size_t)(AC + 2) * TC_CHUNK_BYTES + sizeof(TcBarriers) + 1024;
+  const size_t smem_max = (size_t)prop.sharedMemPerBlockOptin;
+  int stages = (int)((smem_max - fixed) / p->stage_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages < 2) return fail("not enough shared memory for two weight stages");
+  p->stages = stages;
+  p->smem_bytes = fixed + (size_t)stages * p->stage_bytes;
+
+  if (cudaMalloc(&p->stream_dev, (size_t)p->stream_rows * 128) != cudaSuccess) return fail("cudaMalloc(stream)");
+  if (cudaMalloc(&p->table_dev, (size_t)p->table_floats * sizeof(float)) != cudaSuccess) return fail("cudaMalloc(table)");
+  if (cudaMalloc(&p->compA, (size_t)3 * F * W * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMalloc(&p->compA_b, (size_t)3 * F * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMalloc(&p->compC, (size_t)15 * F * (W / 2) * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMalloc(&p->compC_b, (size_t)15 * F * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
+  std::vector<int> flat;
+  for (auto& b : p->blocks) {
+    flat.push_back(b.src); flat.push_back(b.row0); flat.push_back(b.rows_valid); flat.push_back(b.col0);
+    flat.push_back(b.cols_valid); flat.push_back(b.rows_padded);
+    flat.push_back((int)(b.stream_row & 0x7FFFFFFF)); flat.push_back((int)(b.stream_row >> 31));
+  }
+  if (cudaMalloc(&p->blocks_dev, flat.size() * sizeof(int)) != cudaSuccess) return fail("cudaMalloc(blocks)");
+  if (cudaMemcpy(p->blocks_dev, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return fail("cudaMemcpy(blocks)");
+  if (cudaMemset(p->table_dev, 0, (size_t)p->table_floats * sizeof(float)) != cudaSuccess) return fail("cudaMemset");
+  // tanh flags of the two output steps never change
+  for (auto& bs : p->bias_segs) {
+    if (!bs.with_flags) continue;
+    if (cudaMemcpy(p->table_dev + bs.off + bs.n_padded, h->tanh_flags + bs.flag_off, (size_t)bs.n_valid * sizeof(float),
+                   cudaMemcpyDeviceToDevice) != cudaSuccess) return fail("cudaMemcpy(flags)");
+  }
+  const bool fp16 = c.precision == CFN_PREC_FP16;
+  int rc;
+  if ((rc = make_tensor_map(&p->tm_big, p->stream_dev, p->stream_rows, 128, fp16))) return rc;
+  if ((rc = make_tensor_map(&p->tm_small, p->stream_dev, p->stream_rows, 16, fp16))) return rc;
+  auto set_attr = [&](const void* fnp) {
+    return cudaFuncSetAttribute(fnp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) == cudaSuccess;
+  };
+  bool ok = true;
+  if (CG == 1) ok = fp16 ? set_attr((const void*)mlp_tc_kernel<1, true>) : set_attr((const void*)mlp_tc_kernel<1, false>);
+  else ok = fp16 ? set_attr((const void*)mlp_tc_kernel<2, true>) : set_attr((const void*)mlp_tc_kernel<2, false>);
+  if (!ok) return fail("cudaFuncSetAttribute(max dynamic shared memory)");
+  return CFN_OK;
+}
+
+void tc_destroy(CfnHandle* h) {
+  TcPlan* p = h->tc;
+  if (!p) return;
+  cudaFree(p->stream_dev); cudaFree(p->table_dev); cudaFree(p->compA); cudaFree(p->compA_b); cudaFree(p->compC);
+  cudaFree(p->compC_b); cudaFree(p->blocks_dev);
+  delete p;
+  h->tc = nullptr;
+}
+
+int tc_pack(CfnHandle* h, cudaStream_t s) {
+  TcPlan* p = h->tc;
+  const CfnConfig& c = h->cfg;
+  const int W = c.W, F = c.F;
+  int rc;
+  // compose: compA (3F x W) = amA (3F x h_alpha) . W_halpha (h_alpha x W);  bias = amA . b_halpha + amA_b
+  {
+    GemmArgs g{};
+    g.A = h->amA; g.a_rs = c.h_alpha; g.a_cs = 1;
+    g.B = h->w32 + h->slots[h->s_halpha].offset; g.b_rs = W; g.b_cs = 1;
+    g.C = p->compA; g.c_rs = W; g.M = 3 * F; g.N = W; g.K = c.h_alpha; g.split_k = 1;
+    if ((rc = launch_sgemm(g, s))) return rc;
+    compose_bias_kernel<<<1, 128, 0, s>>>(h->amA, h->w32 + h->slots[h->s_halpha + 1].offset, h->amA_b, p->compA_b, 3 * F, c.h_alpha);
+    g.A = h->amC; g.a_rs = c.h_rgb;
+    g.B = h->w32 + h->slots[h->s_hrgb].offset; g.b_rs = W / 2;
+    g.C = p->compC; g.c_rs = W / 2; g.M = 15 * F; g.N = W / 2; g.K = c.h_rgb;
+    if ((rc = launch_sgemm(g, s))) return rc;
+    compose_bias_kernel<<<1, 128, 0, s>>>(h->amC, h->w32 + h->slots[h->s_hrgb + 1].offset, h->amC_b, p->compC_b, 15 * F, c.h_rgb);
+    CFN_LAUNCH_CHECK();
+  }
+  PackSrcTable t;
+  memset(&t, 0, sizeof(t));
+  for (size_t i = 0; i < h->slots.size(); ++i) { t.s[i].ptr = h->w32 + h->slots[i].offset; t.s[i].ld = h->slots[i].cols; }
+  t.s[SRC_COMP_A] = {p->compA, W};
+  t.s[SRC_COMP_C] = {p->compC, W / 2};
+  const bool fp16 = c.precision == CFN_PREC_FP16;
+  if (fp16) pack_stream_kernel<true><<<(unsigned)p->blocks.size(), 256, 0, s>>>(t, p->blocks_dev, (uint16_t*)p->stream_dev);
+  else pack_stream_kernel<false><<<(unsigned)p->blocks.size(), 256, 0, s>>>(t, p->blocks_dev, (uint16_t*)p->stream_dev);
+  CFN_LAUNCH_CHECK();
+  for (auto& bs : p->bias_segs) {
+    const float* src = bs.src == SRC_COMP_A ? p->compA_b : (bs.src == SRC_COMP_C ? p->compC_b : h->w32 + h->slots[bs.src].offset);
+    pack_bias_kernel<<<(bs.n_padded + 127) / 128, 128, 0, s>>>(src, p->table_dev + bs.off, bs.n_valid, bs.n_padded);
+  }
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+size_t tc_workspace_bytes(const CfnHandle*, int64_t) { return 256; }
+
+int tc_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts, const float* viewdirs,
+                   int64_t B, int N, float* flow_params, void*, size_t, cudaStream_t s) {
+  TcPlan* p = h->tc;
+  const int CG = p->cg;
+  TcArgs a;
+  a.rays = rays; a.z_vals = z_vals; a.pts = pts; a.viewdirs = viewdirs;
+  a.M = B * N; a.N = N; a.L_pos = h->cfg.L_pos; a.L_dir = h->cfg.L_dir;
+  a.table = p->table_dev; a.flow_params = flow_params; a.PP = h->PP;
+  a.n_units = (a.M + 128 * CG - 1) / (128 * CG);
+  a.stages = p->stages; a.stage_bytes = p->stage_bytes;
+  int64_t units_grid = p->num_sms / CG;
+  if (units_grid > a.n_units) units_grid = a.n_units;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(units_grid * CG));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = p->smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const bool fp16 = h->cfg.precision == CFN_PREC_FP16;
+  cudaError_t e;
+  if (CG == 1) e = fp16 ? cudaLaunchKernelEx(&cfg, mlp_tc_kernel<1, true>, p->tm_big, p->tm_small, p->dev, a)
+                        : cudaLaunchKernelEx(&cfg, mlp_tc_kernel<1, false>, p->tm_big, p->tm_small, p->dev, a);
+  else e = fp16 ? cudaLaunchKernelEx(&cfg, mlp_tc_kernel<2, true>, p->tm_big, p->tm_small, p->dev, a)
+                : cudaLaunchKernelEx(&cfg, mlp_tc_kernel<2, false>, p->tm_big, p->tm_small, p->dev, a);
+  if (e != cudaSuccess) { set_error("mlp_tc_kernel launch failed: %s", cudaGetErrorString(e)); return CFN_ECUDA; }
+  return CFN_OK;
+}
+
+}  // namespace cfn

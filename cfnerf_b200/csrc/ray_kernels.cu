@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(128) raw2outputs_kernel(const float* __restric
 int launch_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride, int white_bkgd,
                        float* rgb_map, float* disp_map, float* weights, float* depth_map, int64_t B, int N, int K,
                        cudaStream_t s) {
+  CFN_CHECK_ARG(N >= 2 && N <= 4096 && K >= 1, "raw2outputs: unsupported N=%d K=%d (need 2 <= N <= 4096)", N, K);
   if (B == 0) return CFN_OK;
-  CFN_CHECK_ARG(N >= 1 && N <= 4096 && K >= 1, "raw2outputs: unsupported N=%d K=%d", N, K);
   int KG = (K + 31) / 32;
   int64_t warps = B * KG;
   unsigned grid = (unsigned)((warps + 3) / 4);
@@ -209,8 +209,8 @@ __global__ void merge_sorted_kernel(const float* __restrict__ a, const float* __
 }
 
 int launch_merge_sorted(const float* a, const float* b, float* out, int64_t B, int Na, int Nb, cudaStream_t s) {
-  if (B == 0) return CFN_OK;
   int T = Na + Nb;
+  if (B == 0 || T == 0) return CFN_OK;
   CFN_CHECK_ARG(T >= 1 && T <= 8192, "merge_sorted: unsupported size %d", T);
   int threads = T < 256 ? ((T + 31) / 32) * 32 : 256;
   merge_sorted_kernel<<<(unsigned)B, threads, (size_t)T * sizeof(float), s>>>(a, b, out, Na, Nb);
