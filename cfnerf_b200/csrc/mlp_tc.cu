@@ -480,7 +480,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
 // weight stream packing
 // ======================================================================================================
 struct PackSrc { const float* ptr; int ld; };
-struct PackSrcTable { PackSrc s[40]; };
+struct PackSrcTable { PackSrc s[64]; };
 
 // one CUDA block per stream block: [rows_padded][64] 2-byte elements, zero padded
 template <bool FP16>
@@ -544,7 +544,7 @@ static int make_tensor_map(CUtensorMap* map, void* base, int64_t rows, int box_r
 }
 
 // source ids for the pack recipe
-enum { SRC_COMP_A = 30, SRC_COMP_C = 31 };   // 0..29: parameter slot / 2 for weights (slot index itself is used)
+enum { SRC_COMP_A = 62, SRC_COMP_C = 63 };   // 0..61: parameter slot index of the source weight matrix
 
 int tc_create(CfnHandle* h) {
   const CfnConfig& c = h->cfg;
@@ -553,7 +553,7 @@ int tc_create(CfnHandle* h) {
   CFN_CHECK_ARG(h->in_pos <= 64 && h->in_dir <= 32, "tensor-core path: multires %d / multires_views %d unsupported (<=10 / <=4)", c.L_pos, c.L_dir);
   CFN_CHECK_ARG(15 * F <= 256, "tensor-core path: n_flows %d unsupported", F);
   CFN_CHECK_ARG(D + 4 <= TC_MAX_STEPS, "tensor-core path: netdepth %d unsupported", D);
-  CFN_CHECK_ARG(h->slots.size() <= 30, "too many parameter tensors");
+  CFN_CHECK_ARG(h->slots.size() <= 62, "too many parameter tensors");
   TcPlan* p = new TcPlan();
   h->tc = p;
   p->cg = 2;
