@@ -36,6 +36,7 @@ SYMBOLS = {
     "cfn_sample_pdf_f32": (_i32, [_f32p, _f32p, _f32p, _f32p, _vp, _i64, _i32, _i32, _vp]),
     "cfn_merge_sorted_f32": (_i32, [_f32p, _f32p, _f32p, _i64, _i32, _i32, _vp]),
     "cfn_mean_over_k_f32": (_i32, [_f32p, _f32p, _i64, _i32, _vp]),
+    "cfn_debug_profile": (_i32, [_vp, _vp, _i32]),
 }
 
 PREC = {"fp32": 0, "bf16": 1, "fp16": 2}

@@ -289,3 +289,8 @@ extern "C" int cfn_mean_over_k_f32(const float* w, float* out, int64_t rows, int
   CFN_CHECK_ARG(w && out && rows >= 0 && K >= 1, "cfn_mean_over_k_f32: bad argument");
   return launch_mean_over_k(w, out, rows, K, (cudaStream_t)stream);
 }
+
+extern "C" int cfn_debug_profile(CfnHandle* h, uint64_t* out_host, int n) {
+  CFN_CHECK_ARG(h && out_host && n > 0, "cfn_debug_profile: bad argument");
+  return tc_debug_profile(h, (unsigned long long*)out_host, n);
+}

@@ -62,6 +62,7 @@ int tc_create(CfnHandle* h);
 void tc_destroy(CfnHandle* h);
 int tc_pack(CfnHandle* h, cudaStream_t s);
 size_t tc_workspace_bytes(const CfnHandle* h, int64_t n_points);
+int tc_debug_profile(CfnHandle* h, unsigned long long* out_host, int n);
 int tc_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts, const float* viewdirs,
                    int64_t B, int N, float* flow_params, void* ws, size_t ws_bytes, cudaStream_t s);
 }  // namespace cfn

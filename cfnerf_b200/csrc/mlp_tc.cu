@@ -25,10 +25,10 @@
 
 namespace cfn {
 
-constexpr int TC_MAX_STEPS = 24;
-constexpr int TC_MAX_KCH = 10;
+constexpr int TC_MAX_STEPS = 20;
+constexpr int TC_MAX_KCH = 12;
 constexpr int TC_CHUNK_BYTES = 128 * 128;   // 128 rows x 64 columns x 2 bytes
-constexpr int TC_SRC_GP = 8, TC_SRC_GD = 9;
+constexpr int TC_SRC_GP = 8, TC_SRC_GD = 9;   // host-side source ids; the device sees smem chunk indices AC / AC+1
 constexpr int TC_THREADS = 384;             // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
 constexpr int TC_MAX_STAGES = 8;
 
@@ -39,9 +39,10 @@ struct TcStep {
   int n_parts;
   int order_rev;  // issue the parts in reverse order (lets a pending drain of TMEM columns 0..63 finish)
   int n_k;        // K chunks
-  int ksrc[TC_MAX_KCH];    // 0..7: activation chunk, 8: gamma(p), 9: gamma(d)
-  int ksteps[TC_MAX_KCH];  // K=16 instructions issued on that chunk (1..4)
-  int bias_off;   // floats into the table: bias[n_total] (then flags[n_total] for kind 2)
+  // per K chunk, packed: bits 0..7 shared-memory chunk index of the A operand (0..AC-1 activation chunk, AC = gamma(p),
+  // AC+1 = gamma(d)); bits 8..15 first K=16 slice of the 64-column chunk; bits 16..23 number of K=16 instructions
+  unsigned int kinfo[TC_MAX_KCH];
+  int bias_off;   // kind 2 only: floats into the table: bias[n_total] then tanh flags[n_total]
   int out_col;    // kind 2: first column in the flow-parameter record
   int n_valid;    // kind 2: valid output columns
   int row0;       // first row of this step's blocks in the weight stream (rows of 64 elements)
@@ -50,6 +51,7 @@ struct TcStep {
 struct TcPlanDev {
   int n_steps;
   int act_chunks;
+  int stage_out;   // 1: the last step's outputs are staged in shared memory and written to HBM coalesced
   TcStep steps[TC_MAX_STEPS];
 };
 
@@ -60,6 +62,7 @@ struct TcArgs {
   float* flow_params; int PP;
   int64_t n_units;      // tiles of 128*CG points
   int stages; int stage_bytes;
+  unsigned long long* prof;   // optional timestamp buffer (CFN_TC_PROFILE=1): 3 roles x 4096 stamps of CTA 0
 };
 
 struct TcPlan {
@@ -76,13 +79,14 @@ struct TcPlan {
   size_t smem_bytes;
   int num_sms;
   // pack recipe: one entry per 64-column block of the stream
-  struct Block { int src; int row0, rows_valid, col0, cols_valid, rows_padded; int64_t stream_row; };
+  struct Block { int src; int row0, rows_valid, col0, cols_valid, rows_padded; int64_t stream_row; int bias_src; };
   std::vector<Block> blocks;
   int* blocks_dev;
   // bias recipe
   struct BiasSeg { int src; int n_valid; int n_padded; int off; int with_flags; int flag_off; };
   std::vector<BiasSeg> bias_segs;
   int table_floats;
+  unsigned long long* prof_dev;
 };
 
 // ======================================================================================================
@@ -104,16 +108,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 // arrive on a barrier addressed in the shared::cluster window (own CTA or the pair's leader)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar_cluster_addr) : "memory");
+  // default .release.cta semantics, as cutlass::arch::ClusterBarrier::arrive: a cluster-scope release costs a
+  // MEMBAR.ALL.GPU per arrival; the generic->async proxy fence issued before it is what orders the smem writes
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      // default .acquire.cta: a cluster-scope acquire makes ptxas emit CCTL.IVALL (L1 invalidate) after every wait,
+      // which round 1's first profile showed to be the single largest stall of the MMA-issuing thread
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -198,8 +211,23 @@ __device__ __forceinline__ uint32_t make_idesc(bool fp16, int M, int N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// tanh through one exp and one fast division (abs error ~1e-6, far inside the operand rounding of this mode); the
+// accurate tanhf costs ~40 dependent instructions per call and sat on the tile-boundary critical path
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float t = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, t + 1.0f);
+}
+
 // byte offset of the 16-byte unit u (0..7) of row r inside a 128B-swizzled 128x64 chunk
 __device__ __forceinline__ uint32_t swz(int r, int u) { return (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4)); }
+
+constexpr int TC_PROF_N = 4096;
+struct Prof {
+  unsigned long long* p; int n;
+  __device__ __forceinline__ void stamp() {
+    if (p && n < TC_PROF_N) p[n++] = clock64();
+  }
+};
 
 // ======================================================================================================
 // the kernel
@@ -215,23 +243,28 @@ struct TcBarriers {
   uint32_t pad;
 };
 
-template <bool FP16>
+template <bool FP16, bool ONES>
 __device__ __forceinline__ void encode_row(float x, float y, float z, int L, uint32_t chunk_base, int r) {
   // [x, sin(2^l x), cos(2^l x)]_l in blocks of 3 (run_nerf_helpers.py:29-51), zero padded to 64 columns
   float e[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) e[i] = 0.f;
   e[0] = x; e[1] = y; e[2] = z;
-  float f = 1.0f;
+  if (ONES) { e[62] = 1.0f; e[63] = 1.0f; }   // multiplies the (hi, lo) split of the fp32 bias in the weight stream
+  // sin/cos of 2^l x by the double-angle recurrence from one accurate sincosf per coordinate: the absolute error
+  // grows to ~2^9 * 1e-7 = 5e-5 at the top octave, far below the operand rounding of this mode (bf16 2e-3, fp16 5e-4)
+  float sx, cx, sy, cy, sz, cz;
+  sincosf(x, &sx, &cx); sincosf(y, &sy, &cy); sincosf(z, &sz, &cz);
 #pragma unroll
   for (int l = 0; l < 10; ++l) {
     if (l < L) {
-      float s, c;
-      sincosf(x * f, &s, &c); e[3 + 6 * l + 0] = s; e[3 + 6 * l + 3] = c;
-      sincosf(y * f, &s, &c); e[3 + 6 * l + 1] = s; e[3 + 6 * l + 4] = c;
-      sincosf(z * f, &s, &c); e[3 + 6 * l + 2] = s; e[3 + 6 * l + 5] = c;
+      e[3 + 6 * l + 0] = sx; e[3 + 6 * l + 1] = sy; e[3 + 6 * l + 2] = sz;
+      e[3 + 6 * l + 3] = cx; e[3 + 6 * l + 4] = cy; e[3 + 6 * l + 5] = cz;
+      float t;
+      t = 2.0f * sx * cx; cx = fmaf(-2.0f * sx, sx, 1.0f); sx = t;
+      t = 2.0f * sy * cy; cy = fmaf(-2.0f * sy, sy, 1.0f); sy = t;
+      t = 2.0f * sz * cz; cz = fmaf(-2.0f * sz, sz, 1.0f); sz = t;
     }
-    f *= 2.0f;
   }
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
@@ -249,8 +282,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
               const __grid_constant__ TcPlanDev plan, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B; the dynamic segment is the only shared allocation
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();   // the dynamic segment is the only shared allocation: its base is 1024-aligned
+  uint8_t* smem_gen = smem_raw;
   const int act_chunks = plan.act_chunks;
   const uint32_t act_base = smem_base;
   const uint32_t gp_base = act_base + act_chunks * TC_CHUNK_BYTES;
@@ -270,7 +304,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
     for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(bar_local(&bars->full[s]), CG); mbar_init(bar_local(&bars->empty[s]), 1); }
     for (int j = 0; j < 8; ++j) mbar_init(bar_local(&bars->act_ready[j]), 4 * CG);
     mbar_init(bar_local(&bars->acc_full), 1);
-    mbar_init(bar_local(&bars->out_done), 4 * CG);
+    mbar_init(bar_local(&bars->out_done), 8 * CG);
     mbar_init(bar_local(&bars->in_ready), 8 * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -289,45 +323,53 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_ptr);
 
   if (warp == 0) {
-    // ================================= TMA producer (one lane, both CTAs) =================================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
-        for (int g = 0; g < plan.n_steps; ++g) {
-          const TcStep& st = plan.steps[g];
-          const int rows = st.n_part / CG;           // rows of each weight block this CTA stages
-          int blk = 0;
-          for (int pp = 0; pp < st.n_parts; ++pp) {
-            for (int kc = 0; kc < st.n_k; ++kc, ++blk) {
-              mbar_wait(bar_local(&bars->empty[stage]), phase ^ 1u);
-              const uint32_t full_leader = bar_local(&bars->full[stage]);   // peer bit cleared inside tma_load_2d
-              if (rank == 0) mbar_expect_tx(bar_local(&bars->full[stage]), (uint32_t)(rows * 128 * CG));
-              else mbar_arrive_cluster(bar_leader(&bars->full[stage]));
-              const int row_g = st.row0 + blk * st.n_part + (int)rank * rows;
-              const uint32_t dst = stage_base + (uint32_t)stage * a.stage_bytes;
-              int r = 0;
-              for (; rows - r >= 128; r += 128) tma_load_2d<CG>(dst + r * 128, &tm_big, 0, row_g + r, full_leader);
-              for (; r < rows; r += 16) tma_load_2d<CG>(dst + r * 128, &tm_small, 0, row_g + r, full_leader);
-              if (++stage == a.stages) { stage = 0; phase ^= 1u; }
-            }
+    // ================================= TMA producer (whole warp walks the schedule, one elected lane issues) ==========
+    int stage = 0; uint32_t phase = 0;
+    Prof prof{(a.prof && blockIdx.x == 0 && lane == 0) ? a.prof + 2 * TC_PROF_N : nullptr, 0};
+    for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
+      for (int g = 0; g < plan.n_steps; ++g) {
+        const TcStep& st = plan.steps[g];
+        const int rows = st.n_part / CG;           // rows of each weight block this CTA stages
+        const int n_blk = st.n_parts * st.n_k;
+        for (int blk = 0; blk < n_blk; ++blk) {
+          mbar_wait(bar_local(&bars->empty[stage]), phase ^ 1u);
+          prof.stamp();
+          if (elect_one()) {
+            const uint32_t full_bar = bar_local(&bars->full[stage]);   // peer bit cleared inside tma_load_2d (CG == 2)
+            if (rank == 0) mbar_expect_tx(full_bar, (uint32_t)(rows * 128 * CG));
+            else mbar_arrive_cluster(bar_leader(&bars->full[stage]));
+            const int row_g = st.row0 + blk * st.n_part + (int)rank * rows;
+            const uint32_t dst = stage_base + (uint32_t)stage * a.stage_bytes;
+            int r = 0;
+            for (; rows - r >= 128; r += 128) tma_load_2d<CG>(dst + r * 128, &tm_big, 0, row_g + r, full_bar);
+            for (; r < rows; r += 16) tma_load_2d<CG>(dst + r * 128, &tm_small, 0, row_g + r, full_bar);
           }
+          __syncwarp();
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================= MMA issuer (one lane of the leader CTA) =================================
-    if (rank == 0 && lane == 0) {
+    // ================================= MMA issuer (leader CTA) =================================
+    // The WHOLE warp runs the schedule so that every descriptor is a warp-uniform value (uniform registers, no
+    // per-lane waterfall around the tcgen05 instructions); one elected lane issues.
+    if (rank == 0) {
       int stage = 0; uint32_t phase = 0;
       uint32_t act_gen = 0, in_cnt = 0, out_cnt = 0;
       bool pending_out = false;
-      uint32_t waited[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) waited[j] = 0;
+      Prof prof{(a.prof && blockIdx.x == 0 && lane == 0) ? a.prof + 1 * TC_PROF_N : nullptr, 0};
+      unsigned long long waited = 0ull;   // eight 8-bit generation counters, one per activation chunk
       // wait until activation chunk j of generation `gen` is written (and its TMEM columns drained); barriers are
       // always consumed one phase at a time so a parity can never alias an older phase
       auto wait_act = [&](int j, uint32_t gen) {
-        while (waited[j] < gen) { mbar_wait(bar_local(&bars->act_ready[j]), waited[j] & 1u); ++waited[j]; }
+        uint32_t w = (uint32_t)(waited >> (8 * j)) & 0xffu;
+        if (w != (gen & 0xffu)) {
+          while (w != (gen & 0xffu)) { mbar_wait(bar_local(&bars->act_ready[j]), w & 1u); w = (w + 1u) & 0xffu; }
+          waited = (waited & ~(0xffull << (8 * j))) | ((unsigned long long)w << (8 * j));
+        }
       };
+      const uint32_t full_bar0 = bar_local(&bars->full[0]), empty_bar0 = bar_local(&bars->empty[0]);
+      const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
       for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
         mbar_wait(bar_local(&bars->in_ready), in_cnt & 1u); ++in_cnt;
         for (int g = 0; g < plan.n_steps; ++g) {
@@ -338,131 +380,206 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
             const int c0 = pp * st.n_part;
             if (pending_out && c0 < 64) { mbar_wait(bar_local(&bars->out_done), (out_cnt - 1u) & 1u); pending_out = false; }
             for (int j = c0 / 64; j <= (c0 + st.n_part - 1) / 64 && j < act_chunks; ++j) wait_act(j, act_gen);
+            const uint32_t d_tmem = tmem_base + (uint32_t)c0;
             for (int kc = 0; kc < st.n_k; ++kc) {
-              const int src = st.ksrc[kc];
-              if (src < 8) wait_act(src, act_gen);
-              mbar_wait(bar_local(&bars->full[stage]), phase);
+              const uint32_t info = st.kinfo[kc];
+              const int src = info & 0xff, ks0 = (info >> 8) & 0xff, nks = (info >> 16) & 0xff;
+              if (src < act_chunks) wait_act(src, act_gen);
+              mbar_wait(full_bar0 + 8u * stage, phase);
+              prof.stamp();
               tc_fence_after();
-              const uint32_t a_addr = (src < 8) ? (act_base + src * TC_CHUNK_BYTES) : (src == TC_SRC_GP ? gp_base : gd_base);
-              const uint64_t adesc = make_sdesc(a_addr);
-              const uint64_t bdesc = make_sdesc(stage_base + (uint32_t)stage * a.stage_bytes);
-              for (int ks = 0; ks < st.ksteps[kc]; ++ks)
-                umma<CG>(tmem_base + (uint32_t)c0, adesc + 2 * ks, bdesc + 2 * ks, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-              umma_commit<CG>(bar_local(&bars->empty[stage]));
+              const uint64_t adesc = desc_hi | (uint64_t)((((act_base + (uint32_t)src * TC_CHUNK_BYTES) & 0x3FFFFu) >> 4) + 2u * ks0);
+              const uint64_t bdesc = desc_hi | (uint64_t)((((stage_base + (uint32_t)stage * a.stage_bytes) & 0x3FFFFu) >> 4) + 2u * ks0);
+              if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  if (ks < nks) umma<CG>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                umma_commit<CG>(empty_bar0 + 8u * stage);
+              }
+              __syncwarp();
               if (++stage == a.stages) { stage = 0; phase ^= 1u; }
             }
           }
-          umma_commit<CG>(bar_local(&bars->acc_full));
+          if (elect_one()) umma_commit<CG>(bar_local(&bars->acc_full));
+          __syncwarp();
+          prof.stamp();
           if (st.kind == 2) { pending_out = true; ++out_cnt; } else { ++act_gen; }
         }
       }
     }
   } else if (warp >= 4) {
-    // ================================= encode + epilogue warps =================================
+    // ================================= encode + epilogue warps (256 threads) =================================
     const int e = warp - 4, q = warp & 3, hh = e >> 2;
+    const int tid_e = threadIdx.x - 128;
     const int row = q * 32 + lane;                         // TMEM lane == row of the tile owned by this thread
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t acc_cnt = 0;
+    Prof prof{(a.prof && blockIdx.x == 0 && warp == 4 && lane == 0) ? a.prof : nullptr, 0};
+    float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + sizeof(TcBarriers));   // 512 floats
+    auto epi_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    // stage the fp32 bias (and tanh flags) of step g into shared memory: read back as warp-wide broadcasts
+    auto load_bias = [&](int g) {
+      const TcStep& st = plan.steps[g];
+      if (st.kind != 2) return;      // hidden layers carry their bias inside the GEMM (ones columns of gamma(d))
+      for (int i = tid_e; i < 2 * st.n_total; i += 256) sbias[i] = __ldg(a.table + st.bias_off + i);
+    };
+    // positional encoding of this thread's row of tile `unit` straight into the swizzled A tiles
+    auto encode_tile = [&](int64_t unit) {
+      const int64_t m = (unit * CG + rank) * 128 + row;
+      const bool valid = m < a.M;
+      const int64_t b = valid ? (m / a.N) : 0;
+      if (hh == 0) {
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (valid) {
+          if (a.pts) { px = a.pts[m * 3 + 0]; py = a.pts[m * 3 + 1]; pz = a.pts[m * 3 + 2]; }
+          else {
+            const float* r = a.rays + b * 11; const float z = a.z_vals[m];
+            px = __fadd_rn(r[0], __fmul_rn(r[3], z)); py = __fadd_rn(r[1], __fmul_rn(r[4], z)); pz = __fadd_rn(r[2], __fmul_rn(r[5], z));
+          }
+        }
+        encode_row<FP16, false>(px, py, pz, a.L_pos, gp_base, row);
+      } else {
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (valid) {
+          const float* vd = a.viewdirs ? (a.viewdirs + b * 3) : (a.rays + b * 11 + 8);
+          dx = vd[0]; dy = vd[1]; dz = vd[2];
+        }
+        encode_row<FP16, true>(dx, dy, dz, a.L_dir, gd_base, row);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->in_ready));
+    };
+    // gamma(p) is last read by the skip layer and gamma(d) by the view layer: once the view layer's accumulator is
+    // complete both tiles are free, so the NEXT tile is encoded while the last (small) GEMM of this tile runs
+    const int enc_step = plan.n_steps - 2;
+    if (unit0 < a.n_units) { load_bias(0); encode_tile(unit0); }
     for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
+      prof.stamp();
       const int64_t m = (unit * CG + rank) * 128 + row;    // global point index of this row
       const bool valid = m < a.M;
-      // ---- positional encoding straight into the swizzled A tiles ----
-      {
-        const int64_t b = valid ? (m / a.N) : 0;
-        if (hh == 0) {
-          float px = 0.f, py = 0.f, pz = 0.f;
-          if (valid) {
-            if (a.pts) { px = a.pts[m * 3 + 0]; py = a.pts[m * 3 + 1]; pz = a.pts[m * 3 + 2]; }
-            else {
-              const float* r = a.rays + b * 11; const float z = a.z_vals[m];
-              px = __fadd_rn(r[0], __fmul_rn(r[3], z)); py = __fadd_rn(r[1], __fmul_rn(r[4], z)); pz = __fadd_rn(r[2], __fmul_rn(r[5], z));
-            }
-          }
-          encode_row<FP16>(px, py, pz, a.L_pos, gp_base, row);
-        } else {
-          float dx = 0.f, dy = 0.f, dz = 0.f;
-          if (valid) {
-            const float* vd = a.viewdirs ? (a.viewdirs + b * 3) : (a.rays + b * 11 + 8);
-            dx = vd[0]; dy = vd[1]; dz = vd[2];
-          }
-          encode_row<FP16>(dx, dy, dz, a.L_dir, gd_base, row);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->in_ready));
-      }
+      prof.stamp();
       for (int g = 0; g < plan.n_steps; ++g) {
         const TcStep& st = plan.steps[g];
         mbar_wait(bar_local(&bars->acc_full), acc_cnt & 1u); ++acc_cnt;
+        prof.stamp();
         tc_fence_after();
-        const float* bias = a.table + st.bias_off;
         if (st.kind == 2) {
-          if (hh == 0) {
-            float* out = a.flow_params + m * a.PP + st.out_col;
-            const float* flags = bias + st.n_total;
-            for (int c0 = 0; c0 < st.n_total; c0 += 16) {
-              uint32_t v[16];
-              tmem_ld16(tmem_row + (uint32_t)c0, v);
-              tmem_ld_wait();
+          epi_sync();                                 // this step's bias / flags are in shared memory
+          // 16-column groups alternate between the two warps of a lane quarter; TMEM is released as soon as the
+          // values are in registers, the tanh / stores happen afterwards
+          uint32_t v[2][16];
+          const int n_grp = st.n_total / 16;
+          float* out = a.flow_params + m * a.PP + st.out_col;
+          const float* flags = sbias + st.n_total;
+          // the last step stages its outputs in the (now free) upper half of the activation tile so that the record
+          // rows leave the SM as contiguous, coalesced stores instead of 32 scattered sectors per instruction
+          const bool staged = plan.stage_out && g == plan.n_steps - 1;
+          const int ld_stage = st.n_valid + 1;
+          float* stg = reinterpret_cast<float*>(smem_gen + (size_t)(act_chunks / 2) * TC_CHUNK_BYTES);
+          auto emit = [&](int c, float o) {
+            if (c < st.n_valid) {
+              if (staged) stg[row * ld_stage + c] = o;
+              else if (valid) out[c] = o;
+            }
+          };
+          for (int t = 2; 2 * t + hh < n_grp; ++t) {   // wider outputs than 64 columns (n_flows > 4): plain path
+            const int gi = 2 * t + hh;
+            if (gi * 16 >= st.n_valid) break;
+            uint32_t w[16];
+            tmem_ld16(tmem_row + (uint32_t)(gi * 16), w);
+            tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                if (c0 + i < st.n_valid) {
-                  const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
-                  const float4 ff = __ldg(reinterpret_cast<const float4*>(flags + c0 + i));
-                  float o[4];
-                  o[0] = __uint_as_float(v[i + 0]) + bb.x; o[1] = __uint_as_float(v[i + 1]) + bb.y;
-                  o[2] = __uint_as_float(v[i + 2]) + bb.z; o[3] = __uint_as_float(v[i + 3]) + bb.w;
-                  if (ff.x != 0.f) o[0] = tanhf(o[0]);
-                  if (ff.y != 0.f) o[1] = tanhf(o[1]);
-                  if (ff.z != 0.f) o[2] = tanhf(o[2]);
-                  if (ff.w != 0.f) o[3] = tanhf(o[3]);
+            for (int i = 0; i < 16; ++i) {
+              const int c = gi * 16 + i;
+              float o = __uint_as_float(w[i]) + sbias[c];
+              if (flags[c] != 0.f) o = tanh_fast(o);
+              emit(c, o);
+            }
+          }
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    if (valid && c0 + i + k < st.n_valid) out[c0 + i + k] = o[k];   // record rows are only 8-byte aligned for odd F
-                }
+          for (int t = 0; t < 2; ++t) {
+            const int gi = 2 * t + hh;
+            if (gi < n_grp && gi * 16 < st.n_valid) tmem_ld16(tmem_row + (uint32_t)(gi * 16), v[t]);
+          }
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->out_done));
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int gi = 2 * t + hh;
+            if (gi < n_grp && gi * 16 < st.n_valid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int c = gi * 16 + i;
+                float o = __uint_as_float(v[t][i]) + sbias[c];
+                if (flags[c] != 0.f) o = tanh_fast(o);
+                emit(c, o);
               }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->out_done));
+          }
+          if (staged) {
+            epi_sync();
+            const int64_t m0 = (unit * CG + rank) * 128;
+            const int nv = st.n_valid;
+            for (int r = e; r < 128; r += 8) {          // one warp per record row: contiguous 128-byte stores
+              if (m0 + r < a.M) {
+                float* dst = a.flow_params + (m0 + r) * a.PP + st.out_col;
+                for (int c = lane; c < nv; c += 32) dst[c] = stg[r * ld_stage + c];
+              }
+            }
           }
         } else {
           const int n_out_chunks = st.n_total / 64;
+          // software pipeline over this warp's (chunk, half) pieces: the next TMEM load is in flight while the
+          // current 32 columns are biased, activated, packed and stored
+          uint32_t va[32], vb[32];
+          const int n_mine = (n_out_chunks > hh) ? ((n_out_chunks - hh + 1) / 2) * 2 : 0;   // pieces = chunks * 2 halves
+          if (n_mine > 0) tmem_ld32(tmem_row + (uint32_t)(hh * 64), va);
+          auto process = [&](uint32_t (&v)[32], int j, int half) {
+            const uint32_t chunk = act_base + j * TC_CHUNK_BYTES;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float x0 = __uint_as_float(v[8 * u + 0]), x1 = __uint_as_float(v[8 * u + 1]);
+              const float x2 = __uint_as_float(v[8 * u + 2]), x3 = __uint_as_float(v[8 * u + 3]);
+              const float x4 = __uint_as_float(v[8 * u + 4]), x5 = __uint_as_float(v[8 * u + 5]);
+              const float x6 = __uint_as_float(v[8 * u + 6]), x7 = __uint_as_float(v[8 * u + 7]);
+              uint32_t p0, p1, p2, p3;
+              if (st.kind == 0) {
+                p0 = pack2<FP16, true>(x0, x1); p1 = pack2<FP16, true>(x2, x3);
+                p2 = pack2<FP16, true>(x4, x5); p3 = pack2<FP16, true>(x6, x7);
+              } else {
+                p0 = pack2<FP16, false>(x0, x1); p1 = pack2<FP16, false>(x2, x3);
+                p2 = pack2<FP16, false>(x4, x5); p3 = pack2<FP16, false>(x6, x7);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};"
+                           :: "r"(chunk + swz(row, half * 4 + u)), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+            }
+          };
           for (int j = hh; j < act_chunks; j += 2) {
             if (j < n_out_chunks) {
-              const uint32_t chunk = act_base + j * TC_CHUNK_BYTES;
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                uint32_t v[32];
-                tmem_ld32(tmem_row + (uint32_t)(j * 64 + half * 32), v);
-                tmem_ld_wait();
-                const float4* bp = reinterpret_cast<const float4*>(bias + j * 64 + half * 32);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float4 b0 = __ldg(bp + 2 * u), b1 = __ldg(bp + 2 * u + 1);
-                  const float x0 = __uint_as_float(v[8 * u + 0]) + b0.x, x1 = __uint_as_float(v[8 * u + 1]) + b0.y;
-                  const float x2 = __uint_as_float(v[8 * u + 2]) + b0.z, x3 = __uint_as_float(v[8 * u + 3]) + b0.w;
-                  const float x4 = __uint_as_float(v[8 * u + 4]) + b1.x, x5 = __uint_as_float(v[8 * u + 5]) + b1.y;
-                  const float x6 = __uint_as_float(v[8 * u + 6]) + b1.z, x7 = __uint_as_float(v[8 * u + 7]) + b1.w;
-                  uint32_t p0, p1, p2, p3;
-                  if (st.kind == 0) {
-                    p0 = pack2<FP16, true>(x0, x1); p1 = pack2<FP16, true>(x2, x3);
-                    p2 = pack2<FP16, true>(x4, x5); p3 = pack2<FP16, true>(x6, x7);
-                  } else {
-                    p0 = pack2<FP16, false>(x0, x1); p1 = pack2<FP16, false>(x2, x3);
-                    p2 = pack2<FP16, false>(x4, x5); p3 = pack2<FP16, false>(x6, x7);
-                  }
-                  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};"
-                               :: "r"(chunk + swz(row, half * 4 + u)), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
-                }
-              }
+              tmem_ld_wait();                                                            // va = (j, half 0)
+              tmem_ld32(tmem_row + (uint32_t)(j * 64 + 32), vb);
+              process(va, j, 0);
+              tmem_ld_wait();                                                            // vb = (j, half 1)
+              if (j + 2 < n_out_chunks) tmem_ld32(tmem_row + (uint32_t)((j + 2) * 64), va);
+              process(vb, j, 1);
               fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
               tc_fence_before();
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->act_ready[j]));
           }
+          (void)n_mine;
         }
+        if (st.kind == 2) epi_sync();                 // everyone is done with this step's bias (and the staged outputs)
+        {
+          const int gn = (g + 1 < plan.n_steps) ? g + 1 : 0;
+          if (gn != 0 || unit + n_grid_units < a.n_units) load_bias(gn);
+        }
+        if (g == enc_step && unit + n_grid_units < a.n_units) encode_tile(unit + n_grid_units);
+        prof.stamp();
       }
     }
   }
@@ -485,14 +602,21 @@ struct PackSrcTable { PackSrc s[64]; };
 // one CUDA block per stream block: [rows_padded][64] 2-byte elements, zero padded
 template <bool FP16>
 __global__ void pack_stream_kernel(PackSrcTable srcs, const int* __restrict__ blocks, uint16_t* __restrict__ stream) {
-  const int* b = blocks + blockIdx.x * 8;
+  const int* b = blocks + blockIdx.x * 10;
   const int src = b[0], row0 = b[1], rows_valid = b[2], col0 = b[3], cols_valid = b[4], rows_padded = b[5];
   const int64_t stream_row = ((int64_t)(uint32_t)b[7] << 31) | (uint32_t)b[6];
+  const int bias_src = b[8];
   const PackSrc S = srcs.s[src];
   for (int i = threadIdx.x; i < rows_padded * 64; i += blockDim.x) {
     const int r = i >> 6, c = i & 63;
     float v = 0.f;
     if (r < rows_valid && c < cols_valid) v = S.ptr[(int64_t)(row0 + r) * S.ld + col0 + c];
+    if (bias_src >= 0 && c >= 62 && r < rows_valid) {
+      // fp32 bias as a (hi, lo) pair of 16-bit values multiplied by the two ones columns: exact to ~2^-17 relative
+      const float bv = srcs.s[bias_src].ptr[row0 + r];
+      const float hi = FP16 ? __half2float(__float2half_rn(bv)) : __bfloat162float(__float2bfloat16_rn(bv));
+      v = (c == 62) ? hi : (bv - hi);
+    }
     uint16_t o;
     if (FP16) o = __half_as_ushort(__float2half_rn(v));
     else o = __bfloat16_as_ushort(__float2bfloat16_rn(v));
@@ -544,7 +668,7 @@ static int make_tensor_map(CUtensorMap* map, void* base, int64_t rows, int box_r
 }
 
 // source ids for the pack recipe
-enum { SRC_COMP_A = 62, SRC_COMP_C = 63 };   // 0..61: parameter slot index of the source weight matrix
+enum { SRC_COMP_A_B = 60, SRC_COMP_C_B = 61, SRC_COMP_A = 62, SRC_COMP_C = 63 };   // 0..59: parameter slot index
 
 int tc_create(CfnHandle* h) {
   const CfnConfig& c = h->cfg;
@@ -553,12 +677,14 @@ int tc_create(CfnHandle* h) {
   CFN_CHECK_ARG(h->in_pos <= 64 && h->in_dir <= 32, "tensor-core path: multires %d / multires_views %d unsupported (<=10 / <=4)", c.L_pos, c.L_dir);
   CFN_CHECK_ARG(15 * F <= 256, "tensor-core path: n_flows %d unsupported", F);
   CFN_CHECK_ARG(D + 4 <= TC_MAX_STEPS, "tensor-core path: netdepth %d unsupported", D);
-  CFN_CHECK_ARG(h->slots.size() <= 62, "too many parameter tensors");
+  CFN_CHECK_ARG(h->in_dir <= 32, "tensor-core path: multires_views %d unsupported", c.L_dir);
+  CFN_CHECK_ARG(h->slots.size() <= 60, "too many parameter tensors");
   TcPlan* p = new TcPlan();
   h->tc = p;
   p->cg = 2;
   if (const char* e = getenv("CFN_TC_CTA_GROUP")) p->cg = (atoi(e) == 1) ? 1 : 2;
   const int CG = p->cg;
+  p->prof_dev = nullptr;
   p->stream_dev = nullptr; p->table_dev = nullptr; p->compA = p->compA_b = p->compC = p->compC_b = nullptr; p->blocks_dev = nullptr;
   TcPlanDev& dev = p->dev;
   memset(&dev, 0, sizeof(dev));
@@ -567,9 +693,11 @@ int tc_create(CfnHandle* h) {
   int64_t stream_row = 0;
   int table_off = 0;
 
-  auto add_step = [&](int kind, int n_valid, int n_part_max, bool rev, std::vector<std::pair<int, int>> kch,
-                      // per K chunk: (source matrix id, first column) ; rows come from the part
-                      int src_mat, std::vector<int> kcol0, std::vector<int> kcols_valid, int bias_src, int out_col) {
+  struct KCh { int src, kstart, ksteps, col0, cols_valid, with_bias; };
+  // every kind 0/1 step multiplies the ones columns (62, 63) of the gamma(d) tile by the (hi, lo) split of its fp32
+  // bias, so the epilogue is a pure convert-and-store; kind 2 steps add their (tiny) bias in the epilogue
+  auto add_step = [&](int kind, int n_valid, int n_part_max, bool rev, std::vector<KCh> kch, int src_mat, int bias_src,
+                      int out_col) {
     TcStep& st = dev.steps[dev.n_steps++];
     st.kind = kind;
     const int gran = 16 * CG;                       // UMMA N granularity (16 per CTA)
@@ -579,8 +707,16 @@ int tc_create(CfnHandle* h) {
     st.n_part = n_total < n_part_max ? n_total : n_part_max;
     st.n_parts = (n_total + st.n_part - 1) / st.n_part;
     st.order_rev = rev ? 1 : 0;
+    if (kind != 2) {
+      bool has_gd = false;
+      for (auto& k : kch) if (k.src == TC_SRC_GD) { k.kstart = 0; k.ksteps = 4; k.with_bias = 1; has_gd = true; }
+      if (!has_gd) kch.push_back({TC_SRC_GD, 3, 1, 0, 0, 1});
+    }
     st.n_k = (int)kch.size();
-    for (int i = 0; i < st.n_k; ++i) { st.ksrc[i] = kch[i].first; st.ksteps[i] = kch[i].second; }
+    for (int i = 0; i < st.n_k; ++i) {
+      const int idx = kch[i].src == TC_SRC_GP ? AC : (kch[i].src == TC_SRC_GD ? AC + 1 : kch[i].src);
+      st.kinfo[i] = (unsigned)idx | ((unsigned)kch[i].kstart << 8) | ((unsigned)kch[i].ksteps << 16);
+    }
     st.bias_off = table_off;
     st.out_col = out_col;
     st.n_valid = n_valid;
@@ -593,49 +729,57 @@ int tc_create(CfnHandle* h) {
         b.src = src_mat;
         b.row0 = pp * st.n_part;
         b.rows_valid = std::max(0, std::min(st.n_part, n_valid - b.row0));
-        b.col0 = kcol0[i];
-        b.cols_valid = kcols_valid[i];
+        b.col0 = kch[i].col0;
+        b.cols_valid = kch[i].cols_valid;
         b.rows_padded = st.n_part;
         b.stream_row = stream_row;
+        b.bias_src = kch[i].with_bias ? bias_src : -1;
         p->blocks.push_back(b);
         stream_row += st.n_part;
       }
     }
-    TcPlan::BiasSeg bs{bias_src, n_valid, n_total, table_off, kind == 2 ? 1 : 0, out_col};
-    p->bias_segs.push_back(bs);
-    table_off += n_total * (kind == 2 ? 2 : 1);
+    if (kind == 2) {
+      TcPlan::BiasSeg bs{bias_src, n_valid, n_total, table_off, 1, out_col};
+      p->bias_segs.push_back(bs);
+      table_off += 2 * n_total;
+    }
   };
 
   // trunk
   for (int i = 0; i < D; ++i) {
-    std::vector<std::pair<int, int>> kch; std::vector<int> col0, cv;
+    std::vector<KCh> kch;
     const int slot = h->s_pts(i, 0);
-    if (i == 0) { kch.push_back({TC_SRC_GP, 4}); col0.push_back(0); cv.push_back(h->in_pos); }
+    if (i == 0) kch.push_back({TC_SRC_GP, 0, 4, 0, h->in_pos, 0});
     else if (h->skip >= 0 && i == h->skip + 1) {
-      kch.push_back({TC_SRC_GP, 4}); col0.push_back(0); cv.push_back(h->in_pos);           // cat[gamma(p), h] (models.py:171-172)
-      for (int j = 0; j < AC; ++j) { kch.push_back({j, 4}); col0.push_back(h->in_pos + 64 * j); cv.push_back(64); }
+      kch.push_back({TC_SRC_GP, 0, 4, 0, h->in_pos, 0});                                      // cat[gamma(p), h] (models.py:171-172)
+      for (int j = 0; j < AC; ++j) kch.push_back({j, 0, 4, h->in_pos + 64 * j, 64, 0});
     } else {
-      for (int j = 0; j < AC; ++j) { kch.push_back({j, 4}); col0.push_back(64 * j); cv.push_back(64); }
+      for (int j = 0; j < AC; ++j) kch.push_back({j, 0, 4, 64 * j, 64, 0});
     }
-    add_step(0, W, 256, false, kch, slot, col0, cv, slot + 1, 0);
+    add_step(0, W, 256, false, kch, slot, slot + 1, 0);
   }
   // composed alpha conditioning from h7 (N = 3F), then the feature layer (parts reversed so that the drain of
   // TMEM columns 0..63 by the alpha epilogue overlaps the first feature MMAs)
   {
-    std::vector<std::pair<int, int>> kch; std::vector<int> col0, cv;
-    for (int j = 0; j < AC; ++j) { kch.push_back({j, 4}); col0.push_back(64 * j); cv.push_back(64); }
-    add_step(2, 3 * F, 256, false, kch, SRC_COMP_A, col0, cv, SRC_COMP_A, 0);
-    add_step(1, W, 256, true, kch, h->s_feat, col0, cv, h->s_feat + 1, 0);
-    // view layer on cat[feature, gamma(d)] (models.py:177-181)
-    kch.push_back({TC_SRC_GD, 2}); col0.push_back(W); cv.push_back(h->in_dir);
-    add_step(0, W / 2, 256, false, kch, h->s_views, col0, cv, h->s_views + 1, 0);
+    std::vector<KCh> kch;
+    for (int j = 0; j < AC; ++j) kch.push_back({j, 0, 4, 64 * j, 64, 0});
+    add_step(2, 3 * F, 256, false, kch, SRC_COMP_A, SRC_COMP_A_B, 0);
+    add_step(1, W, 256, true, kch, h->s_feat, h->s_feat + 1, 0);
+    // view layer on cat[feature, gamma(d)] (models.py:177-181); its gamma(d) block also carries the bias columns
+    kch.push_back({TC_SRC_GD, 0, 4, W, h->in_dir, 1});
+    add_step(0, W / 2, 256, false, kch, h->s_views, h->s_views + 1, 0);
   }
   // composed rgb conditioning from the view features (N = 15F)
   {
-    std::vector<std::pair<int, int>> kch; std::vector<int> col0, cv;
-    for (int j = 0; j < (W / 2 + 63) / 64; ++j) { kch.push_back({j, (W / 2 - 64 * j) >= 64 ? 4 : (W / 2 - 64 * j) / 16}); col0.push_back(64 * j); cv.push_back(std::min(64, W / 2 - 64 * j)); }
-    add_step(2, 15 * F, 256, false, kch, SRC_COMP_C, col0, cv, SRC_COMP_C, 3 * F);
+    std::vector<KCh> kch;
+    for (int j = 0; j < (W / 2 + 63) / 64; ++j) {
+      const int cols = std::min(64, W / 2 - 64 * j);
+      kch.push_back({j, 0, cols / 16, 64 * j, cols, 0});
+    }
+    add_step(2, 15 * F, 256, false, kch, SRC_COMP_C, SRC_COMP_C_B, 3 * F);
   }
+  // staging the last step's record rows needs 128 x (15F+1) floats in the upper half of the activation tile
+  dev.stage_out = ((size_t)128 * (15 * F + 1) * sizeof(float) <= (size_t)(AC - AC / 2) * TC_CHUNK_BYTES) ? 1 : 0;
   p->stream_rows = stream_row;
   p->table_floats = table_off;
 
@@ -646,7 +790,7 @@ int tc_create(CfnHandle* h) {
   if (prop.major != 10) { set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor); return CFN_EINVAL; }
   p->num_sms = prop.multiProcessorCount;
   p->stage_bytes = (256 / CG) * 128;
-  const size_t fixed = (size_t)(AC + 2) * TC_CHUNK_BYTES + sizeof(TcBarriers) + 1024;
+  const size_t fixed = (size_t)(AC + 2) * TC_CHUNK_BYTES + sizeof(TcBarriers) + 2048;   // + bias staging (512 floats)
   const size_t smem_max = (size_t)prop.sharedMemPerBlockOptin;
   int stages = (int)((smem_max - fixed) / p->stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -654,6 +798,10 @@ int tc_create(CfnHandle* h) {
   p->stages = stages;
   p->smem_bytes = fixed + (size_t)stages * p->stage_bytes;
 
+  if (getenv("CFN_TC_PROFILE")) {
+    if (cudaMalloc(&p->prof_dev, 3 * TC_PROF_N * sizeof(unsigned long long)) != cudaSuccess) return fail("cudaMalloc(prof)");
+    cudaMemset(p->prof_dev, 0, 3 * TC_PROF_N * sizeof(unsigned long long));
+  }
   if (cudaMalloc(&p->stream_dev, (size_t)p->stream_rows * 128) != cudaSuccess) return fail("cudaMalloc(stream)");
   if (cudaMalloc(&p->table_dev, (size_t)p->table_floats * sizeof(float)) != cudaSuccess) return fail("cudaMalloc(table)");
   if (cudaMalloc(&p->compA, (size_t)3 * F * W * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
@@ -665,6 +813,7 @@ int tc_create(CfnHandle* h) {
     flat.push_back(b.src); flat.push_back(b.row0); flat.push_back(b.rows_valid); flat.push_back(b.col0);
     flat.push_back(b.cols_valid); flat.push_back(b.rows_padded);
     flat.push_back((int)(b.stream_row & 0x7FFFFFFF)); flat.push_back((int)(b.stream_row >> 31));
+    flat.push_back(b.bias_src); flat.push_back(0);
   }
   if (cudaMalloc(&p->blocks_dev, flat.size() * sizeof(int)) != cudaSuccess) return fail("cudaMalloc(blocks)");
   if (cudaMemcpy(p->blocks_dev, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return fail("cudaMemcpy(blocks)");
@@ -693,7 +842,7 @@ void tc_destroy(CfnHandle* h) {
   TcPlan* p = h->tc;
   if (!p) return;
   cudaFree(p->stream_dev); cudaFree(p->table_dev); cudaFree(p->compA); cudaFree(p->compA_b); cudaFree(p->compC);
-  cudaFree(p->compC_b); cudaFree(p->blocks_dev);
+  cudaFree(p->compC_b); cudaFree(p->blocks_dev); cudaFree(p->prof_dev);
   delete p;
   h->tc = nullptr;
 }
@@ -723,12 +872,14 @@ int tc_pack(CfnHandle* h, cudaStream_t s) {
   for (size_t i = 0; i < h->slots.size(); ++i) { t.s[i].ptr = h->w32 + h->slots[i].offset; t.s[i].ld = h->slots[i].cols; }
   t.s[SRC_COMP_A] = {p->compA, W};
   t.s[SRC_COMP_C] = {p->compC, W / 2};
+  t.s[SRC_COMP_A_B] = {p->compA_b, 1};
+  t.s[SRC_COMP_C_B] = {p->compC_b, 1};
   const bool fp16 = c.precision == CFN_PREC_FP16;
   if (fp16) pack_stream_kernel<true><<<(unsigned)p->blocks.size(), 256, 0, s>>>(t, p->blocks_dev, (uint16_t*)p->stream_dev);
   else pack_stream_kernel<false><<<(unsigned)p->blocks.size(), 256, 0, s>>>(t, p->blocks_dev, (uint16_t*)p->stream_dev);
   CFN_LAUNCH_CHECK();
   for (auto& bs : p->bias_segs) {
-    const float* src = bs.src == SRC_COMP_A ? p->compA_b : (bs.src == SRC_COMP_C ? p->compC_b : h->w32 + h->slots[bs.src].offset);
+    const float* src = bs.src == SRC_COMP_A_B ? p->compA_b : (bs.src == SRC_COMP_C_B ? p->compC_b : h->w32 + h->slots[bs.src].offset);
     pack_bias_kernel<<<(bs.n_padded + 127) / 128, 128, 0, s>>>(src, p->table_dev + bs.off, bs.n_valid, bs.n_padded);
   }
   CFN_LAUNCH_CHECK();
@@ -736,6 +887,15 @@ int tc_pack(CfnHandle* h, cudaStream_t s) {
 }
 
 size_t tc_workspace_bytes(const CfnHandle*, int64_t) { return 256; }
+
+int tc_debug_profile(CfnHandle* h, unsigned long long* out_host, int n) {
+  TcPlan* p = h->tc;
+  if (!p || !p->prof_dev) { set_error("profiling buffer not enabled (set CFN_TC_PROFILE=1 before cfn_create)"); return CFN_ESTATE; }
+  if (n > 3 * TC_PROF_N) n = 3 * TC_PROF_N;
+  CFN_CUDA(cudaDeviceSynchronize());
+  CFN_CUDA(cudaMemcpy(out_host, p->prof_dev, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return CFN_OK;
+}
 
 int tc_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts, const float* viewdirs,
                    int64_t B, int N, float* flow_params, void*, size_t, cudaStream_t s) {
@@ -747,6 +907,7 @@ int tc_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const f
   a.table = p->table_dev; a.flow_params = flow_params; a.PP = h->PP;
   a.n_units = (a.M + 128 * CG - 1) / (128 * CG);
   a.stages = p->stages; a.stage_bytes = p->stage_bytes;
+  a.prof = p->prof_dev;
   int64_t units_grid = p->num_sms / CG;
   if (units_grid > a.n_units) units_grid = a.n_units;
   cudaLaunchConfig_t cfg{};

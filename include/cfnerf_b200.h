@@ -138,6 +138,12 @@ int cfn_merge_sorted_f32(const float* a, const float* b, float* out, int64_t B, 
 /* mean over K of weights (B,N,K) -> (B,N)  (the shared fine grid decision) */
 int cfn_mean_over_k_f32(const float* w, float* out, int64_t rows, int K, void* stream);
 
+/* ---- diagnostics ---------------------------------------------------------------------------------- */
+/* When CFN_TC_PROFILE=1 is set in the environment at cfn_create time, the tensor-core network kernel records
+ * clock64() stamps of CTA 0 (3 roles x 4096: epilogue warp, MMA thread, TMA producer); this copies them to HOST
+ * memory after a device synchronise.  Used by scripts/k1_timeline.py only; not part of the data path. */
+int cfn_debug_profile(CfnHandle* h, uint64_t* out_host, int n);
+
 #ifdef __cplusplus
 }
 #endif
