@@ -62,7 +62,7 @@ struct TcArgs {
   float* flow_params; int PP;
   int64_t n_units;      // tiles of 128*CG points
   int stages; int stage_bytes;
-  unsigned long long* prof;   // optional timestamp buffer (CFN_TC_PROFILE=1): 3 roles x 4096 stamps of CTA 0
+  unsigned long long* prof;   // optional timestamp buffer (CFN_TC_PROFILE=1): 4 roles x 4096 stamps of CTA 0
 };
 
 struct TcPlan {
@@ -415,6 +415,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t acc_cnt = 0;
     Prof prof{(a.prof && blockIdx.x == 0 && warp == 4 && lane == 0) ? a.prof : nullptr, 0};
+    Prof prof2{(a.prof && blockIdx.x == 0 && warp == 4 && lane == 0) ? a.prof + 3 * TC_PROF_N : nullptr, 0};
     float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + sizeof(TcBarriers));   // 512 floats
     auto epi_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     // stage the fp32 bias (and tanh flags) of step g into shared memory: read back as warp-wide broadcasts
@@ -465,7 +466,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
         prof.stamp();
         tc_fence_after();
         if (st.kind == 2) {
+          prof2.stamp();
           epi_sync();                                 // this step's bias / flags are in shared memory
+          prof2.stamp();
           // 16-column groups alternate between the two warps of a lane quarter; TMEM is released as soon as the
           // values are in registers, the tanh / stores happen afterwards
           uint32_t v[2][16];
@@ -506,30 +509,61 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->out_done));
+          prof2.stamp();
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const int gi = 2 * t + hh;
             if (gi < n_grp && gi * 16 < st.n_valid) {
+              // bias and flags first (vector broadcasts), then branch-free math, then the stores: nothing in between
+              // can alias, so the sixteen outputs are processed with full instruction-level parallelism
+              float bb[16], ff[16], o[16];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 b4 = reinterpret_cast<const float4*>(sbias + gi * 16)[i];
+                const float4 f4 = reinterpret_cast<const float4*>(flags + gi * 16)[i];
+                bb[4 * i] = b4.x; bb[4 * i + 1] = b4.y; bb[4 * i + 2] = b4.z; bb[4 * i + 3] = b4.w;
+                ff[4 * i] = f4.x; ff[4 * i + 1] = f4.y; ff[4 * i + 2] = f4.z; ff[4 * i + 3] = f4.w;
+              }
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const int c = gi * 16 + i;
-                float o = __uint_as_float(v[t][i]) + sbias[c];
-                if (flags[c] != 0.f) o = tanh_fast(o);
-                emit(c, o);
+                const float x = __uint_as_float(v[t][i]) + bb[i];
+                o[i] = (ff[i] != 0.f) ? tanh_fast(x) : x;
               }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) emit(gi * 16 + i, o[i]);
             }
           }
+          prof2.stamp();
           if (staged) {
             epi_sync();
+            prof2.stamp();
             const int64_t m0 = (unit * CG + rank) * 128;
             const int nv = st.n_valid;
-            for (int r = e; r < 128; r += 8) {          // one warp per record row: contiguous 128-byte stores
-              if (m0 + r < a.M) {
-                float* dst = a.flow_params + (m0 + r) * a.PP + st.out_col;
-                for (int c = lane; c < nv; c += 32) dst[c] = stg[r * ld_stage + c];
+            // one warp per record row, four rows per batch: all shared-memory reads first, then contiguous stores
+            for (int r0 = e; r0 < 128; r0 += 32) {
+              float val[4][4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int q2 = 0; q2 < 4; ++q2) {
+                  const int c = lane + 32 * q2;
+                  val[k][q2] = (c < nv) ? stg[(r0 + 8 * k) * ld_stage + c] : 0.f;
+                }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int r = r0 + 8 * k;
+                if (m0 + r < a.M) {
+                  float* dst = a.flow_params + (m0 + r) * a.PP + st.out_col;
+#pragma unroll
+                  for (int q2 = 0; q2 < 4; ++q2) {
+                    const int c = lane + 32 * q2;
+                    if (c < nv) dst[c] = val[k][q2];
+                  }
+                }
               }
             }
           }
+          prof2.stamp();
         } else {
           const int n_out_chunks = st.n_total / 64;
           // software pipeline over this warp's (chunk, half) pieces: the next TMEM load is in flight while the
@@ -799,8 +833,8 @@ int tc_create(CfnHandle* h) {
   p->smem_bytes = fixed + (size_t)stages * p->stage_bytes;
 
   if (getenv("CFN_TC_PROFILE")) {
-    if (cudaMalloc(&p->prof_dev, 3 * TC_PROF_N * sizeof(unsigned long long)) != cudaSuccess) return fail("cudaMalloc(prof)");
-    cudaMemset(p->prof_dev, 0, 3 * TC_PROF_N * sizeof(unsigned long long));
+    if (cudaMalloc(&p->prof_dev, 4 * TC_PROF_N * sizeof(unsigned long long)) != cudaSuccess) return fail("cudaMalloc(prof)");
+    cudaMemset(p->prof_dev, 0, 4 * TC_PROF_N * sizeof(unsigned long long));
   }
   if (cudaMalloc(&p->stream_dev, (size_t)p->stream_rows * 128) != cudaSuccess) return fail("cudaMalloc(stream)");
   if (cudaMalloc(&p->table_dev, (size_t)p->table_floats * sizeof(float)) != cudaSuccess) return fail("cudaMalloc(table)");
@@ -891,7 +925,7 @@ size_t tc_workspace_bytes(const CfnHandle*, int64_t) { return 256; }
 int tc_debug_profile(CfnHandle* h, unsigned long long* out_host, int n) {
   TcPlan* p = h->tc;
   if (!p || !p->prof_dev) { set_error("profiling buffer not enabled (set CFN_TC_PROFILE=1 before cfn_create)"); return CFN_ESTATE; }
-  if (n > 3 * TC_PROF_N) n = 3 * TC_PROF_N;
+  if (n > 4 * TC_PROF_N) n = 4 * TC_PROF_N;
   CFN_CUDA(cudaDeviceSynchronize());
   CFN_CUDA(cudaMemcpy(out_host, p->prof_dev, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return CFN_OK;

@@ -25,9 +25,9 @@ for _ in range(2):
     eng.network(rays.shape[0], 128, rays=rays, z_vals=z)
 torch.cuda.synchronize()
 N = 4096
-buf = (C.c_uint64 * (3 * N))()
-cf._lib.check(eng.lib.cfn_debug_profile(eng.h, buf, 3 * N))
-roles = {"epilogue": list(buf[0:N]), "mma": list(buf[N:2 * N]), "tma": list(buf[2 * N:3 * N])}
+buf = (C.c_uint64 * (4 * N))()
+cf._lib.check(eng.lib.cfn_debug_profile(eng.h, buf, 4 * N))
+roles = {"epilogue": list(buf[0:N]), "mma": list(buf[N:2 * N]), "tma": list(buf[2 * N:3 * N]), "detail": list(buf[3 * N:4 * N])}
 roles = {k: [x for x in v if x] for k, v in roles.items()}
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/k1_timeline.json"
 os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
@@ -47,3 +47,7 @@ for g in range(n_steps):
     print(f" step {g:2d}: waited acc_full {a-prev:7d}  epilogue {b-a:7d}   (t={a-base})")
     prev = b
 print(f" tile total {prev-base}")
+
+det = roles["detail"]
+if det:
+    print("kind-2 epilogue detail (last 11 stamps, deltas):", [det[i + 1] - det[i] for i in range(len(det) - 11, len(det) - 1)])
