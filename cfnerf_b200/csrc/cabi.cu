@@ -240,7 +240,9 @@ extern "C" int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, co
     set_error("cfn_flow_composite_fwd: call cfn_pack_weights first");
     return CFN_ESTATE;
   }
-  return launch_flow_composite_fwd(h->cfg.F, h->cfg.K, h->globals, flow_params, z_vals, rays_d, rays_d_stride,
+  // training (log-det sums requested) and the fp32 check mode keep the accurate functions
+  const int fast = (h->cfg.precision != CFN_PREC_FP32 && logdet_sums == nullptr) ? 1 : 0;
+  return launch_flow_composite_fwd(fast, h->cfg.F, h->cfg.K, h->globals, flow_params, z_vals, rays_d, rays_d_stride,
                                    eps_alpha, eps_rgb, B, N, white_bkgd, rgb_map, disp_map, depth_map, raw, weights,
                                    logdet_sums, kstats, (cudaStream_t)stream);
 }

@@ -29,10 +29,26 @@ void set_error(const char* fmt, ...);
 
 #define CFN_LAUNCH_CHECK() CFN_CUDA(cudaGetLastError())
 
-// ---- accurate fp32 math used by every non-GEMM kernel (no fast-math anywhere) -----------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// ---- fp32 math of the non-GEMM kernels (the library is compiled WITHOUT --use_fast_math) --------------
+// Two flavours.  FAST = false: accurate libdevice functions, used by the fp32 "check" path (1e-5 bar).
+// FAST = true: one MUFU exp / log / reciprocal per transcendental (absolute error <= ~3e-7 on the bounded outputs
+// sigmoid / tanh / alpha), used behind the bf16 / fp16 tensor-core network stage whose bar is 2e-3: the streaming
+// kernels are instruction-bound on these functions, not HBM-bound.
+template <bool FAST> __device__ __forceinline__ float exp_(float x) { return FAST ? __expf(x) : expf(x); }
+template <bool FAST> __device__ __forceinline__ float sigmoid_(float x) {
+  return FAST ? __fdividef(1.0f, 1.0f + __expf(-x)) : 1.0f / (1.0f + expf(-x));
+}
 // F.softplus(beta=1, threshold=20) (run_nerf_uncertainty_NF.py:424)
-__device__ __forceinline__ float softplusf_(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+template <bool FAST> __device__ __forceinline__ float softplus_(float x) {
+  if (FAST) return x > 20.0f ? x : __logf(1.0f + __expf(x));
+  return x > 20.0f ? x : log1pf(expf(x));
+}
+template <bool FAST> __device__ __forceinline__ float tanh_(float x) {
+  if (FAST) { const float t = __expf(2.0f * x); return 1.0f - __fdividef(2.0f, t + 1.0f); }
+  return tanhf(x);
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return sigmoid_<false>(x); }
+__device__ __forceinline__ float softplusf_(float x) { return softplus_<false>(x); }
 
 // flow-parameter record per 3-D point: [alpha d1[F] | alpha d2[F] | alpha b[F] | rgb flow 0 (15) | ... ]
 // rgb flow f (15): R1_00 R1_01 R1_02 R1_11 R1_12 R1_22 | R2_00 R2_01 R2_02 R2_11 R2_12 R2_22 | b0 b1 b2
@@ -50,7 +66,7 @@ int launch_sample_pdf(const float* bins, const float* weights, const float* u, f
 int launch_merge_sorted(const float* a, const float* b, float* out, int64_t B, int Na, int Nb, cudaStream_t s);
 int launch_mean_over_k(const float* w, float* out, int64_t rows, int K, cudaStream_t s);
 
-int launch_flow_composite_fwd(int F, int K, const float* globals, const float* flow_params, const float* z_vals,
+int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
                               int64_t B, int N, int white_bkgd, float* rgb_map, float* disp_map, float* depth_map,
                               float* raw, float* weights, float* logdet_sums, float* kstats, cudaStream_t s);

@@ -38,9 +38,9 @@ __device__ __forceinline__ void chunk_store(float* dst, int n_floats, int lane, 
 // MAXV float4 per lane must cover kChunk*PP/4 float4 per chunk: PP = 18F -> 72F float4 / 32 lanes.
 // F <= 8 -> at most 18 float4 per lane.  We instantiate for F<=4 (MAXV=9) and F<=8 (MAXV=18).
 
-template <int MAXV, bool TRAIN>
+template <int MAXV, bool TRAIN, bool FAST, int FT>
 __global__ void __launch_bounds__(128)
-flow_composite_fwd_kernel(int F, int K, const float* __restrict__ globals, const float* __restrict__ flow_params,
+flow_composite_fwd_kernel(int F_rt, int K, const float* __restrict__ globals, const float* __restrict__ flow_params,
                           const float* __restrict__ z_vals, const float* __restrict__ rays_d, int rays_d_stride,
                           const float* __restrict__ eps_alpha, const float* __restrict__ eps_rgb, int64_t B, int N,
                           int white_bkgd, float* __restrict__ rgb_map, float* __restrict__ disp_map,
@@ -48,6 +48,9 @@ flow_composite_fwd_kernel(int F, int K, const float* __restrict__ globals, const
                           float* __restrict__ logdet_sums, float* __restrict__ kstats) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // FT > 0: the number of flows is a compile-time constant (the shipped recipe, F = 4): a point's 18F scalars are
+  // read as 128-bit shared-memory broadcasts into registers and every flow loop is unrolled
+  const int F = FT > 0 ? FT : F_rt;
   const int PP = 18 * F;
   const int per_warp = (kChunk * PP + 2 * N + 3) & ~3;   // keeps every warp's chunk buffer 16-byte aligned
   float* sp = smem + warp * per_warp;  // chunk of parameters
@@ -111,24 +114,35 @@ flow_composite_fwd_kernel(int F, int K, const float* __restrict__ globals, const
 
       for (int i = 0; i < npts; ++i) {
         const int n = n0 + i;
+        float rec[FT > 0 ? 18 * FT : 4];
         const float* P = sp + i * PP;
+        if (FT > 0) {
+#pragma unroll
+          for (int j = 0; j < (18 * FT) / 4; ++j) {
+            const float4 q4 = reinterpret_cast<const float4*>(sp + i * PP)[j];
+            rec[4 * j] = q4.x; rec[4 * j + 1] = q4.y; rec[4 * j + 2] = q4.z; rec[4 * j + 3] = q4.w;
+          }
+          P = rec;
+        }
         // ---- alpha stack (z_size 1; the flip is the identity) ----
         float za = za0, lda = 0.f;
+#pragma unroll
         for (int f = 0; f < F; ++f) {
           const float d1 = P[f], d2 = P[F + f], bb = P[2 * F + f];
-          const float t = tanhf(d2 * za + bb);
+          const float t = tanh_<FAST>(d2 * za + bb);
           za += d1 * t;
           if (TRAIN) lda += logf(fabsf((1.0f - t * t) * (d1 * d2) + 1.0f) + 1e-8f);
         }
         // ---- rgb stack (z_size 3; components reversed on odd flows, models.py:404-408) ----
         float z0 = zc00, z1 = zc01, z2 = zc02, ldc = 0.f;
+#pragma unroll
         for (int f = 0; f < F; ++f) {
           const float* Q = P + 3 * F + kRgbFlowRec * f;
           const bool odd = f & 1;
           const float p0 = odd ? z2 : z0, p1 = z1, p2 = odd ? z0 : z2;
-          const float t0 = tanhf(Q[6] * p0 + Q[7] * p1 + Q[8] * p2 + Q[12]);
-          const float t1 = tanhf(Q[9] * p1 + Q[10] * p2 + Q[13]);
-          const float t2 = tanhf(Q[11] * p2 + Q[14]);
+          const float t0 = tanh_<FAST>(Q[6] * p0 + Q[7] * p1 + Q[8] * p2 + Q[12]);
+          const float t1 = tanh_<FAST>(Q[9] * p1 + Q[10] * p2 + Q[13]);
+          const float t2 = tanh_<FAST>(Q[11] * p2 + Q[14]);
           const float s0 = Q[0] * t0 + Q[1] * t1 + Q[2] * t2;
           const float s1 = Q[3] * t1 + Q[4] * t2;
           const float s2 = Q[5] * t2;
@@ -142,16 +156,16 @@ flow_composite_fwd_kernel(int F, int K, const float* __restrict__ globals, const
           }
         }
         if (TRAIN && active) {
-          ld_a_sum += lda + (za - softplusf_(za));                                           // models.py:263
-          ld_c_sum += ldc + ((z0 + z1 + z2) - 2.0f * (softplusf_(z0) + softplusf_(z1) + softplusf_(z2)));  // :278
+          ld_a_sum += lda + (za - softplus_<FAST>(za));                                           // models.py:263
+          ld_c_sum += ldc + ((z0 + z1 + z2) - 2.0f * (softplus_<FAST>(z0) + softplus_<FAST>(z1) + softplus_<FAST>(z2)));  // :278
         }
         // ---- compositing (raw2outputs) ----
-        const float alpha = 1.0f - expf(-softplusf_(za) * sd[n]);
+        const float alpha = 1.0f - exp_<FAST>(-softplus_<FAST>(za) * sd[n]);
         const float w = alpha * T;
         T = T * ((1.0f - alpha) + 1e-10f);
-        cr += w * sigmoidf_(z0);
-        cg += w * sigmoidf_(z1);
-        cb += w * sigmoidf_(z2);
+        cr += w * sigmoid_<FAST>(z0);
+        cg += w * sigmoid_<FAST>(z1);
+        cb += w * sigmoid_<FAST>(z2);
         depth += w * sz[n];
         acc += w;
         if (active) {
@@ -227,7 +241,7 @@ flow_composite_fwd_kernel(int F, int K, const float* __restrict__ globals, const
 
 static size_t fwd_smem_bytes(int F, int N) { return (size_t)4 * ((kChunk * 18 * F + 2 * N + 3) & ~3) * sizeof(float); }
 
-int launch_flow_composite_fwd(int F, int K, const float* globals, const float* flow_params, const float* z_vals,
+int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
                               int64_t B, int N, int white_bkgd, float* rgb_map, float* disp_map, float* depth_map,
                               float* raw, float* weights, float* logdet_sums, float* kstats, cudaStream_t s) {
@@ -239,7 +253,8 @@ int launch_flow_composite_fwd(int F, int K, const float* globals, const float* f
   const bool train = logdet_sums != nullptr;
 #define CFN_FWD_LAUNCH(MAXV, TR)                                                                                  \
   do {                                                                                                            \
-    auto kern = flow_composite_fwd_kernel<MAXV, TR>;                                                              \
+    auto kern = fast_math ? (F == 4 ? flow_composite_fwd_kernel<MAXV, TR, true, 4> : flow_composite_fwd_kernel<MAXV, TR, true, 0>)\
+                          : (F == 4 ? flow_composite_fwd_kernel<MAXV, TR, false, 4> : flow_composite_fwd_kernel<MAXV, TR, false, 0>);                                                            \
     if (smem > 48 * 1024) CFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, 128, smem, s>>>(F, K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N, \
                                  white_bkgd, rgb_map, disp_map, depth_map, raw, weights, logdet_sums, kstats);    \

@@ -1,8 +1,4 @@
 mkdir -p gpurun_out
-echo "=== TC tests"; timeout -s KILL 300 python -m pytest tests -m gpu -q -k "tensor_core" 2>&1 | tail -4
-CFN_TC_PROFILE=1 timeout -s KILL 300 python scripts/k1_timeline.py gpurun_out/k1_timeline_cg2.json | tail -18
-echo "=== bench"; timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tmp.json 2> gpurun_out/bench.err; python - <<PY
-import json
-d=json.loads(open("gpurun_out/bench_tmp.json").read().strip().splitlines()[-1])
-print("value",d["value"],"e2e",d["e2e"]["value"],"ms",d["ms_per_step"],"roofline",d["roofline"]["achieved"],d["roofline"]["frac"],"k1share",d["roofline"]["k1_share_of_step"],d["clocks"])
-PY
+echo "=== all gpu tests"; timeout -s KILL 900 python -m pytest tests -m gpu -q 2>&1 | tail -8
+echo "=== kernel rooflines"; timeout -s KILL 600 python scripts/kernel_rooflines.py gpurun_out/kernel_rooflines.json
+echo "=== bench"; timeout -s KILL 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r01.json 2> gpurun_out/bench.err; cat gpurun_out/bench_r01.json; tail -3 gpurun_out/bench.err

@@ -338,3 +338,83 @@ def test_tensor_core_full_image_tile_properties(cf, dev):
     out_p = cf.render_rays(rays[perm], net, None, 128, False, False, precision="bf16")
     for k in ("rgb_map", "depth_map"):
         assert torch.equal(out_p[k], out[k][perm]), k
+
+
+# ------------------------------------------------------------------------------------------------
+# drop-in: install() behind the reference's caller side (render -> batchify_rays -> render_rays)
+# ------------------------------------------------------------------------------------------------
+def test_install_behind_reference_render(cf, dev):
+    from oracle import ref_driver
+    R = ref_driver.make_module()
+    cf.install(R, precision="fp32")
+    cfg = O.CfnConfig()
+    p = O.make_params(cfg, 0, "lively")
+    sa, sr = O.make_latents(cfg, 0)
+    net = torch.nn.DataParallel(make_net(cf, cfg, p, sa, sr, dev), device_ids=[0])   # create_nerf wraps it (main:330)
+    kwargs_test = dict(network_fn=net, network_query_fn=None, N_samples=128, is_train=False, uniformsample=False,
+                       retraw=True, lindisp=False, K_samples=cfg.K, perturb=0., N_importance=0, network_fine=None,
+                       white_bkgd=False, raw_noise_std=0.)                                        # main:382-407
+    H, W, focal = 6, 8, 7.0
+    c2w = torch.eye(4)[:3].to(dev)
+    rgb, disp, depth, extras = R.render(H, W, focal, chunk=20, c2w=c2w, ndc=False, near=1.2, far=8.0,
+                                        use_viewdirs=True, **kwargs_test)
+    assert rgb.shape == (H, W, 3, cfg.K) and disp.shape == (H, W, cfg.K) and depth.shape == (H, W, cfg.K)
+    assert extras == {}
+    o, d = O.get_rays(H, W, focal, torch.eye(4)[:3])
+    rays = O.pack_ray_batch(o, d, 1.2, 8.0)
+    ea, er = O.test_latents(sa, sr)
+    with torch.no_grad():
+        ref = O.render_rays(p, cfg, rays, ea, er, False, faithful=False)
+    assert (rgb.reshape(-1, 3, cfg.K).cpu() - ref["rgb_map"]).abs().max().item() <= TOL_FP32
+    assert (depth.reshape(-1, cfg.K).cpu() - ref["depth_map"]).abs().max().item() <= TOL_FP32
+    # stand-alone raw2outputs through the rebinding
+    g = torch.Generator().manual_seed(3)
+    raw = torch.randn(4, 16, 8, 4, generator=g).to(dev)
+    z = torch.sort(torch.rand(4, 16, generator=g) + 1, -1).values.to(dev)
+    dd = torch.randn(4, 3, generator=g).to(dev)
+    a = R.raw2outputs(raw, z, dd, 0.0, True)
+    b = O.raw2outputs(raw.cpu(), z.cpu(), dd.cpu(), True)
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(x.cpu().numpy(), y.numpy(), rtol=2e-6, atol=4e-6)
+
+
+def test_training_steps_track_the_oracle(cf, dev):
+    """PSNR after a fixed number of optimisation steps (north star: within 0.1 dB of the reference path).  Same
+    weights, rays, targets, noise draws and Adam on both sides; the CUDA path on the GPU, the oracle (autograd on the
+    CPU restatement that is pinned to the reference's own gradients) on the host."""
+    cfg = O.CfnConfig(W=256, K=64, h_alpha=32)
+    p0 = O.make_params(cfg, 5, "lively")
+    sa, sr = O.make_latents(cfg, 5)
+    net = make_net(cf, cfg, p0, sa, sr, dev)
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in p0.items()}
+    live = [k for k in p_ref if not k.startswith("alpha_linear") and not k.startswith("alpha_std_linear")]
+    opt_ref = torch.optim.Adam([p_ref[k] for k in live], lr=5e-4, betas=(0.9, 0.999))
+    opt = torch.optim.Adam([q for n, q in net.named_parameters()
+                            if not n.startswith("alpha_linear") and not n.startswith("alpha_std_linear")],
+                           lr=5e-4, betas=(0.9, 0.999))
+    B, steps = 16, 4
+    g = torch.Generator().manual_seed(12)
+    rays = O.synthetic_rays(B, 13)
+    target = torch.rand(B, 3, generator=g)
+    psnr_ref = psnr_mine = None
+    for it in range(steps):
+        t_rand = torch.rand(B, 128, generator=g)
+        ea, er = torch.randn(cfg.K, 1, generator=g), torch.randn(cfg.K, 3, generator=g)
+        out = O.render_rays(p_ref, cfg, rays, ea, er, True, t_rand=t_rand, faithful=False)
+        lr_ = O.kde_nll_loss(out["rgb_map"], target, out["loss_entropy"], cfg.K, 0.01)
+        opt_ref.zero_grad()
+        lr_["loss"].backward()
+        opt_ref.step()
+        o2 = cf.render_rays(rays.to(dev), net, None, 128, True, False, K_samples=cfg.K, perturb=1., raw_noise_std=1.,
+                            t_rand=t_rand.to(dev), eps_alpha=ea.to(dev), eps_rgb=er.to(dev))
+        l2 = cf.kde_nll_loss(o2["rgb_map"], target.to(dev), o2["loss_entropy"], cfg.K, 0.01)
+        opt.zero_grad()
+        l2["loss"].backward()
+        opt.step()
+        psnr_ref, psnr_mine = float(lr_["psnr"]), float(l2["psnr"])
+        assert abs(psnr_ref - psnr_mine) <= 0.1, (it, psnr_ref, psnr_mine)
+        assert abs(float(lr_["loss"]) - float(l2["loss"])) <= 2e-3 * max(1.0, abs(float(lr_["loss"]))), it
+    # the weights themselves stayed together
+    sd = net.state_dict()
+    worst = max((sd[k].cpu() - p_ref[k].detach()).abs().max().item() for k in live)
+    assert worst <= 5e-4, worst
