@@ -84,6 +84,21 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def k1_dram_traffic(points_per_launch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the K1 launch from the committed `ncu --set full` capture
+    (profiles/r01_prof_k1_summary.csv, same 4 194 304-point launch as the bench); None when it does not apply."""
+    path = os.path.join(ROOT, "profiles", "r01_prof_k1_summary.csv")
+    if not os.path.isfile(path) or points_per_launch != 4194304:
+        return None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for line in open(path):
+        f = line.strip().split(",")
+        if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(f[2]) * mult.get(f[1], 1.0)
+    return tot or None
+
+
 def cpu_reference_rays_per_s(n_rays: int, reps: int, threads: int | None = None):
     """The oracle port of the reference path (K-fold materialisation as in models.py:210-217) on the host."""
     from oracle import cfnerf_oracle as O
@@ -285,7 +300,10 @@ def main():
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": 3 * n_chunks * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "mlp_tc_kernel (network stage K1)",
+                         "frac": achieved / peak, "traffic": k1_dram_traffic(pts_per_launch),
+                         "traffic_note": "DRAM bytes per K1 launch from profiles/r01_prof_k1_summary.csv (ncu --set full); "
+                                         "algorithmic HBM bytes = 288 B/point of flow parameters written = 1.208e9",
+                         "kernel": "mlp_tc_kernel (network stage K1)",
                          "peak_source": f"{which} bf16_tflops_sustained",
                          "k1_share_of_step": k1_ms / ms, "points_per_launch": pts_per_launch},
             "clocks": sampler.summary(),
