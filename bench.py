@@ -31,6 +31,8 @@ H = W_IMG = 512
 FOCAL = 443.4
 NEAR, FAR = 1.2, 8.0
 N_SAMPLES = 128
+WORKLOAD = ("africa.txt full-image 512x512 uncertainty render (mean/variance/depth), N=128 samples, K=32 latent samples, "
+            "W=512 D=8, random-init weights, one image per GPU per step")
 
 
 def image_rays(h, w, focal, seed_pose: int):
@@ -99,11 +101,17 @@ def k1_dram_traffic(points_per_launch: int):
     return tot or None
 
 
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_rays_per_s(n_rays: int, reps: int, threads: int | None = None):
     """The oracle port of the reference path (K-fold materialisation as in models.py:210-217) on the host."""
     from oracle import cfnerf_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or host_threads())   # torchrun exports OMP_NUM_THREADS=1: use every host core
     cfg = O.CfnConfig()
     p = O.make_params(cfg, 0, "default")
     sa, sr = O.make_latents(cfg, 0)
@@ -125,6 +133,7 @@ def run_reference(args):
         return
     n_rays = args.cpu_rays
     times = []
+    torch.set_num_threads(host_threads())   # torchrun exports OMP_NUM_THREADS=1: the reference gets every host core
     from oracle import cfnerf_oracle as O
     cfg = O.CfnConfig()
     p = O.make_params(cfg, 0, "default")
@@ -146,8 +155,8 @@ def run_reference(args):
         "impl": "reference", "metric": "rays/sec (K-sample uncertainty render)", "value": v, "unit": "rays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"africa.txt 512x512 K-sample uncertainty render, bounded sample of {n_rays} rays per step "
-                               "(N=128, K=32, W=512, D=8), reference algorithm on host CPU"},
+        "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": H * W_IMG,
+                   "reference_sample": f"each step times {n_rays} evenly spaced rays of the image on the host CPU"},
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": f"{n_rays} rays of the 512x512 image per step, oracle port of the reference "
                                    "(faithful K-fold conditioning), torch CPU fp32"},
@@ -293,9 +302,7 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
             "data": "synthetic",
-            "config": {"workload": "africa.txt full-image 512x512 uncertainty render (mean/variance/depth), N=128 samples, "
-                                   "K=32 latent samples, W=512 D=8, random-init weights, one image per GPU per step",
-                       "rays_per_step_per_gpu": B, "chunk_rays": chunk,
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": B, "chunk_rays": chunk,
                        "l2": "no flush needed: each step streams a 9.7 GB flow-parameter buffer (>> 126 MB L2)"},
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": 3 * n_chunks * args.steps,
