@@ -172,7 +172,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"],
+                    help="operand type of the tensor-core GEMM chain (bf16 and fp16 run at the same rate)")
     ap.add_argument("--chunk", type=int, default=32768, help="rays per render_rays call (bounds the flow-parameter buffer)")
     ap.add_argument("--cpu-rays", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -22,7 +22,10 @@ from . import _lib
 from ._lib import check
 from .engine import Engine, _f32c, _ptr, _stream, _unwrap, engine_for
 
-DEFAULT_PRECISION = "bf16"
+# fp16 operands have an 11-bit significand (TF32-class) at the same tensor-core rate as bf16: with trained-like
+# ("stressed") conditioning heads bf16 drifts to 1e-2 on the predictive mean while fp16 stays at 1e-3, inside the
+# 2e-3 bar (tests/test_gpu_parity.py::test_stressed_heads_precision_report).  "bf16" and "fp32" remain selectable.
+DEFAULT_PRECISION = "fp16"
 
 
 # ------------------------------------------------------------------------------------------------------

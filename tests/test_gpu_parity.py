@@ -418,3 +418,86 @@ def test_training_steps_track_the_oracle(cf, dev):
     sd = net.state_dict()
     worst = max((sd[k].cpu() - p_ref[k].detach()).abs().max().item() for k in live)
     assert worst <= 5e-4, worst
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs 4 and 5 at oracle-sized slices
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16", TOL_TC)])
+def test_config4_ndc_hierarchical_k64(cf, dev, precision, tol):
+    """Config 4 shape: forward-facing NDC rays (ndc_rays, helpers:360-377), near=0 far=1, 64 coarse + 128 fine
+    samples, K=64, two networks — on a 6x8 crop so the CPU oracle finishes in seconds."""
+    cfg = O.CfnConfig(K=64)
+    pc, pf = O.make_params(cfg, 0, "lively"), O.make_params(cfg, 1, "lively")
+    sa, sr = O.make_latents(cfg, 0)
+    net_c, net_f = make_net(cf, cfg, pc, sa, sr, dev), make_net(cf, cfg, pf, sa, sr, dev)
+    H, W, focal = 6, 8, 815.1 * 8 / 1008
+    o, d = O.get_rays(H, W, focal, torch.eye(4)[:3])
+    o, d = O.ndc_rays(H, W, focal, 1.0, o + torch.tensor([0.0, 0.0, 0.3]), d)
+    vd = d / d.norm(dim=-1, keepdim=True)
+    rays = torch.cat([o.reshape(-1, 3), d.reshape(-1, 3), torch.zeros(H * W, 1), torch.ones(H * W, 1),
+                      vd.reshape(-1, 3)], -1).float()
+    ea, er = O.test_latents(sa, sr)
+    with torch.no_grad():
+        ref = O.render_rays_hier(pc, pf, cfg, rays, ea, er, False, 64, 128)
+    out = cf.render_rays(rays.to(dev), net_c, None, 64, False, False, K_samples=cfg.K, N_importance=128,
+                         network_fine=net_f, precision=precision)
+    assert out["rgb_map"].shape == (H * W, 3, 64) and out["z_vals"].shape == (H * W, 192)
+    for k in ("rgb0", "depth0"):
+        assert (out[k].cpu() - ref[k]).abs().max().item() <= tol, k
+    # the fine grid is a discontinuous function of the coarse weights (inverse CDF): compare the fine maps loosely in
+    # fp32 and at the documented bar in the tensor-core mode
+    for k in ("rgb_map", "depth_map"):
+        assert (out[k].cpu() - ref[k]).abs().max().item() <= max(tol, 5e-4), k
+    assert bool((out["z_vals"][:, 1:] >= out["z_vals"][:, :-1]).all())
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16", TOL_TC), ("fp16", TOL_TC)])
+def test_config5_white_background_k128(cf, dev, precision, tol):
+    """Config 5 shape: 360-degree pose (pose_spherical recipe, load_blender.py:29-34), near=2 far=6, white background,
+    K=128 latent samples — on 16 rays of one view."""
+    import math
+    cfg = O.CfnConfig(K=128)
+    p = O.make_params(cfg, 2, "lively")
+    sa, sr = O.make_latents(cfg, 2)
+    net = make_net(cf, cfg, p, sa, sr, dev)
+    th, phi, radius = math.radians(40.0), math.radians(-30.0), 4.0
+    trans = torch.eye(4); trans[2, 3] = radius
+    rphi = torch.tensor([[1, 0, 0, 0], [0, math.cos(phi), -math.sin(phi), 0], [0, math.sin(phi), math.cos(phi), 0], [0, 0, 0, 1.0]])
+    rth = torch.tensor([[math.cos(th), 0, -math.sin(th), 0], [0, 1, 0, 0], [math.sin(th), 0, math.cos(th), 0], [0, 0, 0, 1.0]])
+    c2w = torch.tensor([[-1.0, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]) @ rth @ rphi @ trans
+    o, d = O.get_rays(4, 4, 1111.1 * 4 / 800, c2w[:3])
+    rays = O.pack_ray_batch(o, d, 2.0, 6.0)
+    ea, er = O.test_latents(sa, sr)
+    with torch.no_grad():
+        ref = O.render_rays(p, cfg, rays, ea, er, False, white_bkgd=True, faithful=False)
+    out = cf.render_rays(rays.to(dev), net, None, 128, False, False, K_samples=128, white_bkgd=True,
+                         precision=precision, want_kstats=True)
+    for k in ("rgb_map", "depth_map"):
+        assert (out[k].cpu() - ref[k]).abs().max().item() <= tol, k
+    # the K-reduction the caller does (main:1122-1131): mean, "uncertainty" std, mean depth
+    m, s, dm = O.k_reduce(ref["rgb_map"], ref["depth_map"], 128)
+    ks = out["kstats"].cpu()
+    assert (ks[:, 0:3] - m).abs().max().item() <= tol
+    assert (ks[:, 3:6] - s).abs().max().item() <= tol
+    assert (ks[:, 6] - dm).abs().max().item() <= tol
+
+
+def test_stressed_heads_precision_report(cf, dev):
+    """SURVEY §8(d) 'stressed heads' variant (amortisation x8, heads x4): default init hides GEMM rounding.  fp16
+    operands (11-bit significand) must stay inside the 2e-3 bar where bf16 may not; both are reported."""
+    cfg = O.CfnConfig()
+    p = O.make_params(cfg, 2, "stressed")
+    sa, sr = O.make_latents(cfg, 2)
+    net = make_net(cf, cfg, p, sa, sr, dev)
+    rays = O.synthetic_rays(64, 21).to(dev)
+    ref = cf.render_rays(rays, net, None, 128, False, False, precision="fp32", want_kstats=True)
+    errs = {}
+    for prec in ("bf16", "fp16"):
+        out = cf.render_rays(rays, net, None, 128, False, False, precision=prec, want_kstats=True)
+        errs[prec] = {"rgb_mean": (out["kstats"][:, 0:3] - ref["kstats"][:, 0:3]).abs().max().item(),
+                      "rgb_std": (out["kstats"][:, 3:6] - ref["kstats"][:, 3:6]).abs().max().item(),
+                      "depth_mean": (out["kstats"][:, 6] - ref["kstats"][:, 6]).abs().max().item()}
+    print("stressed-heads drift vs fp32 check mode:", errs)
+    assert errs["fp16"]["rgb_mean"] <= TOL_TC and errs["fp16"]["depth_mean"] <= TOL_TC
+    assert errs["fp16"]["rgb_mean"] <= errs["bf16"]["rgb_mean"] * 1.5 + 1e-4
