@@ -25,6 +25,8 @@ SYMBOLS = {
     "cfn_pack_weights": (_i32, [_vp, C.POINTER(_vp), _i32, _vp]),
     "cfn_flow_param_width": (_i32, [_vp]),
     "cfn_zvals_f32": (_i32, [_f32p, _f32p, _f32p, _i32, _f32p, _i64, _i32, _vp]),
+    "cfn_rays_from_pose_f32": (_i32, [_i32, _i32, C.c_double, C.POINTER(C.c_float), C.c_double, C.c_double, _i32, C.c_double,
+                               _f32p, _vp]),
     "cfn_workspace_bytes": (_i32, [_vp, _i64, _i32, C.POINTER(_sz)]),
     "cfn_network_fwd": (_i32, [_vp, _f32p, _f32p, _f32p, _f32p, _i64, _i32, _f32p, _vp, _sz, _i32, _vp]),
     "cfn_network_bwd": (_i32, [_vp, _f32p, _i64, _i32, _vp, _sz, C.POINTER(_vp), _i32, _vp]),
@@ -36,6 +38,7 @@ SYMBOLS = {
     "cfn_sample_pdf_f32": (_i32, [_f32p, _f32p, _f32p, _f32p, _vp, _i64, _i32, _i32, _vp]),
     "cfn_merge_sorted_f32": (_i32, [_f32p, _f32p, _f32p, _i64, _i32, _i32, _vp]),
     "cfn_mean_over_k_f32": (_i32, [_f32p, _f32p, _i64, _i32, _vp]),
+    "cfn_kde_nll_f32": (_i32, [_f32p, _f32p, _i64, _i32, C.c_float, _f32p, _f32p, _vp]),
     "cfn_debug_profile": (_i32, [_vp, _vp, _i32]),
 }
 

@@ -311,6 +311,35 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=128, is_
     return ret
 
 
+def rays_from_pose(H, W, focal, c2w, near=0., far=1., ndc=False, device=None):
+    """The ray batch `render(H, W, focal, c2w=pose, use_viewdirs=True)` assembles (main:129-158) — (H*W,11) on the
+    device, generated by one kernel from the 3x4 pose instead of six (H,W,3) torch intermediates."""
+    lib = _lib.load()
+    c = torch.as_tensor(c2w, dtype=torch.float32).detach().cpu()[:3, :4].contiguous()
+    dev = torch.device(device) if device is not None else (c2w.device if isinstance(c2w, torch.Tensor) and c2w.is_cuda
+                                                           else torch.device("cuda", torch.cuda.current_device()))
+    rays = torch.empty(H * W, 11, dtype=torch.float32, device=dev)
+    arr = (C.c_float * 12)(*c.reshape(-1).tolist())
+    with torch.cuda.device(dev):
+        check(lib.cfn_rays_from_pose_f32(int(H), int(W), float(focal), arr, float(near), float(far), int(bool(ndc)), 1.0,
+                                         _ptr(rays), _stream()), "cfn_rays_from_pose_f32")
+    return rays
+
+
+def render_image(H, W, focal, c2w, network_fn, near=0., far=1., ndc=False, chunk=1024 * 32, **render_kwargs):
+    """`render(H, W, focal, chunk, c2w=pose, near=, far=, use_viewdirs=True, **render_kwargs_test)` (main:103-170,
+    the full-image branch): returns [rgb_map (H,W,3,K), disp_map (H,W,K), depth_map (H,W,K), extras]."""
+    dev = next(_unwrap(network_fn).parameters()).device
+    rays = rays_from_pose(H, W, focal, c2w, near, far, ndc, dev)
+    rets = [render_rays(rays[i:i + chunk], network_fn, **render_kwargs) for i in range(0, rays.shape[0], chunk)]
+    allr = {k: torch.cat([r[k] for r in rets], 0) for k in rets[0]}
+    for k in allr:
+        if k not in ("loss_entropy", "loss_entropy_uniformsample"):
+            allr[k] = allr[k].reshape([H, W] + list(allr[k].shape[1:]))
+    ex = ["rgb_map", "disp_map", "depth_map"]
+    return [allr[k] for k in ex] + [{k: v for k, v in allr.items() if k not in ex}]
+
+
 def install(ref_module, precision: str | None = None):
     """Rebind the reference's module-global names: `batchify_rays` looks `render_rays` up by global
     name (main:93) and `render_rays` looks `raw2outputs` up the same way (main:540)."""
@@ -325,7 +354,41 @@ def install(ref_module, precision: str | None = None):
 # ------------------------------------------------------------------------------------------------------
 # A11: the caller's K-reduction and KDE-NLL loss (main:1027-1050), kept in torch for round 1
 # ------------------------------------------------------------------------------------------------------
-def kde_nll_loss(rgb_map, target, loss_entropy, K, beta1=0.01):
+class _KdeNllFn(torch.autograd.Function):
+    """cfn_kde_nll_f32: loss_nll and mse in one kernel, the gradient seed w.r.t. rgb_map computed in the same pass."""
+
+    @staticmethod
+    def forward(ctx, rgb_map, target):
+        lib = _lib.load()
+        dev = rgb_map.device
+        x, t = _f32c(rgb_map.detach(), dev), _f32c(target, dev)
+        B, _, K = x.shape
+        partial = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        g = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            check(lib.cfn_kde_nll_f32(_ptr(x), _ptr(t), B, K, 1.0 / (3.0 * B), _ptr(partial), _ptr(g), _stream()),
+                  "cfn_kde_nll_f32")
+        ctx.save_for_backward(g)
+        tot = partial.sum(0) / (3.0 * B)
+        ctx.mark_non_differentiable(tot[1])
+        return tot[0], tot[1]
+
+    @staticmethod
+    def backward(ctx, g_nll, g_mse):
+        (g,) = ctx.saved_tensors
+        return g * g_nll, None
+
+
+def kde_nll_loss(rgb_map, target, loss_entropy, K, beta1=0.01, fused=None):
+    """main:1027-1050.  On CUDA tensors the K-reduction, the KDE-NLL and its gradient run in one kernel (F1); the
+    torch expression below is the CPU form used by the host-side tests."""
+    if fused is None:
+        fused = rgb_map.is_cuda
+    if fused:
+        nll, mse = _KdeNllFn.apply(rgb_map, target)
+        psnr = -10. * torch.log(mse) / math.log(10.)
+        loss = nll + beta1 * loss_entropy.mean() if beta1 else nll
+        return {"loss": loss, "loss_nll": nll, "mse": mse, "psnr": psnr}
     eps = 1e-05
     rgb_mean = rgb_map.mean(-1)
     mse = torch.mean((rgb_mean - target) ** 2)

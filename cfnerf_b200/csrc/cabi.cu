@@ -194,6 +194,12 @@ extern "C" int cfn_zvals_f32(const float* rays, const float* t_vals, const float
   return launch_zvals(rays, t_vals, t_rand, lindisp, z_vals, B, N, (cudaStream_t)stream);
 }
 
+extern "C" int cfn_rays_from_pose_f32(int H, int W, double focal, const float* c2w_host, double near, double far, int ndc,
+                                      double ndc_near, float* rays, void* stream) {
+  CFN_CHECK_ARG(c2w_host && rays, "cfn_rays_from_pose_f32: null argument");
+  return launch_rays_from_pose(H, W, focal, c2w_host, near, far, ndc, ndc_near, rays, (cudaStream_t)stream);
+}
+
 extern "C" int cfn_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts,
                                const float* viewdirs, int64_t B, int N, float* flow_params, void* workspace,
                                size_t workspace_bytes, int save_for_backward, void* stream) {
@@ -295,4 +301,10 @@ extern "C" int cfn_mean_over_k_f32(const float* w, float* out, int64_t rows, int
 extern "C" int cfn_debug_profile(CfnHandle* h, uint64_t* out_host, int n) {
   CFN_CHECK_ARG(h && out_host && n > 0, "cfn_debug_profile: bad argument");
   return tc_debug_profile(h, (unsigned long long*)out_host, n);
+}
+
+extern "C" int cfn_kde_nll_f32(const float* rgb_map, const float* target, int64_t B, int K, float grad_scale, float* partial,
+                               float* g_rgb_map, void* stream) {
+  CFN_CHECK_ARG(B >= 0 && (B == 0 || (rgb_map && target && partial)), "cfn_kde_nll_f32: null argument");
+  return launch_kde_nll(rgb_map, target, B, K, grad_scale, partial, g_rgb_map, (cudaStream_t)stream);
 }

@@ -58,12 +58,16 @@ __host__ __device__ inline int flow_param_width(int F) { return 18 * F; }
 // ---- kernels implemented across the .cu files ----------------------------------------------------
 int launch_zvals(const float* rays, const float* t_vals, const float* t_rand, int lindisp, float* z_vals, int64_t B,
                  int N, cudaStream_t s);
+int launch_rays_from_pose(int H, int W, double focal, const float* c2w12, double near, double far, int ndc, double ndc_near,
+                          float* rays, cudaStream_t s);
 int launch_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride, int white_bkgd,
                        float* rgb_map, float* disp_map, float* weights, float* depth_map, int64_t B, int N, int K,
                        cudaStream_t s);
 int launch_sample_pdf(const float* bins, const float* weights, const float* u, float* samples, int32_t* below,
                       int64_t B, int M, int Nf, cudaStream_t s);
 int launch_merge_sorted(const float* a, const float* b, float* out, int64_t B, int Na, int Nb, cudaStream_t s);
+int launch_kde_nll(const float* rgb_map, const float* target, int64_t B, int K, float grad_scale, float* partial, float* g,
+                   cudaStream_t s);
 int launch_mean_over_k(const float* w, float* out, int64_t rows, int K, cudaStream_t s);
 
 int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,

@@ -1,6 +1,8 @@
 // Per-ray streaming kernels: sample schedule (A1), stand-alone raw2outputs (A8, "K2'"), sample_pdf and
 // sorted merge (A9, "K3"), K-mean of weights.  All fp32, HBM-bound, one warp per ray (lane = latent sample k
 // or lane = sample along the ray), coalesced 128-bit loads.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace cfn {
@@ -41,6 +43,66 @@ int launch_zvals(const float* rays, const float* t_vals, const float* t_rand, in
   if (B == 0) return CFN_OK;
   int64_t total = B * N;
   zvals_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(rays, t_vals, t_rand, lindisp, z_vals, B, N);
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// F2: ray generation for a full image (`render(..., c2w=pose)`: run_nerf_uncertainty_NF.py:129-158 with get_rays,
+// run_nerf_helpers.py:288-297, and ndc_rays, helpers:360-377).  One thread per pixel writes the (11)-float ray record
+// [o d near far viewdir]; the fp32 operation order of the reference expressions is kept with explicit intrinsics.
+// ------------------------------------------------------------------------------------------------
+struct Pose { float m[12]; };   // c2w[:3,:4] row-major
+
+__global__ void rays_from_pose_kernel(int H, int W, float focal, Pose c2w, float near, float far, int ndc, float ndc_near,
+                                      float sW, float sH, float two_near, float* __restrict__ rays) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  const int row = p / W, col = p - row * W;
+  // dirs = [(i - W/2)/focal, -(j - H/2)/focal, -1]
+  const float d0 = __fdiv_rn(__fsub_rn((float)col, (float)W * 0.5f), focal);
+  const float d1 = -__fdiv_rn(__fsub_rn((float)row, (float)H * 0.5f), focal);
+  const float d2 = -1.0f;
+  float dx[3], ox[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {   // rays_d[k] = sum_c dirs[c] * c2w[k][c]
+    dx[k] = __fadd_rn(__fadd_rn(__fmul_rn(d0, c2w.m[4 * k + 0]), __fmul_rn(d1, c2w.m[4 * k + 1])), __fmul_rn(d2, c2w.m[4 * k + 2]));
+    ox[k] = c2w.m[4 * k + 3];
+  }
+  // viewdirs are taken BEFORE the NDC warp (main:136-144)
+  const float nrm = sqrtf(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
+  const float v0 = __fdiv_rn(dx[0], nrm), v1 = __fdiv_rn(dx[1], nrm), v2 = __fdiv_rn(dx[2], nrm);
+  if (ndc) {
+    const float t = __fdiv_rn(-__fadd_rn(ndc_near, ox[2]), dx[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ox[k] = __fadd_rn(ox[k], __fmul_rn(t, dx[k]));
+    const float o0 = __fdiv_rn(__fmul_rn(sW, ox[0]), ox[2]);
+    const float o1 = __fdiv_rn(__fmul_rn(sH, ox[1]), ox[2]);
+    const float o2 = __fadd_rn(1.0f, __fdiv_rn(two_near, ox[2]));
+    const float e0 = __fmul_rn(sW, __fsub_rn(__fdiv_rn(dx[0], dx[2]), __fdiv_rn(ox[0], ox[2])));
+    const float e1 = __fmul_rn(sH, __fsub_rn(__fdiv_rn(dx[1], dx[2]), __fdiv_rn(ox[1], ox[2])));
+    const float e2 = __fdiv_rn(-two_near, ox[2]);
+    ox[0] = o0; ox[1] = o1; ox[2] = o2;
+    dx[0] = e0; dx[1] = e1; dx[2] = e2;
+  }
+  float* r = rays + (int64_t)p * 11;
+  r[0] = ox[0]; r[1] = ox[1]; r[2] = ox[2];
+  r[3] = dx[0]; r[4] = dx[1]; r[5] = dx[2];
+  r[6] = near; r[7] = far;
+  r[8] = v0; r[9] = v1; r[10] = v2;
+}
+
+int launch_rays_from_pose(int H, int W, double focal, const float* c2w12, double near, double far, int ndc, double ndc_near,
+                          float* rays, cudaStream_t s) {
+  CFN_CHECK_ARG(H > 0 && W > 0 && focal > 0 && (int64_t)H * W < (1ll << 31), "rays_from_pose: bad image size");
+  Pose pz;
+  for (int i = 0; i < 12; ++i) pz.m[i] = c2w12[i];
+  // the python scalars of ndc_rays are evaluated in double and rounded once when they meet an fp32 tensor
+  const float sW = (float)(-1.0 / ((double)W / (2.0 * focal))), sH = (float)(-1.0 / ((double)H / (2.0 * focal)));
+  const float two_near = (float)(2.0 * ndc_near);
+  const int n = H * W;
+  rays_from_pose_kernel<<<(n + 255) / 256, 256, 0, s>>>(H, W, (float)focal, pz, (float)near, (float)far, ndc, (float)ndc_near,
+                                                        sW, sH, two_near, rays);
   CFN_LAUNCH_CHECK();
   return CFN_OK;
 }
@@ -230,6 +292,65 @@ __global__ void mean_over_k_kernel(const float* __restrict__ w, float* __restric
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) out[row] = s / (float)K;
+}
+
+// ------------------------------------------------------------------------------------------------
+// F1: the caller's K-reduction + KDE negative log-likelihood (run_nerf_uncertainty_NF.py:1027-1042) and its
+// gradient seed in one pass.  One warp per ray, lanes stride over the K latent samples.
+//   mean_k, unbiased std * K/(K-1) (main:1034), bandwidth h = std * (0.8/K)^(-1/7) + 1e-5 (detached, main:1036),
+//   p_k = exp(-(x_k - t)^2 / (2 h^2)) * (2 pi)^(-1.5) / h, nll = -log(mean_k p_k + 1e-5).
+// partial (B,2) = [sum_c nll_c, sum_c (mean_c - t_c)^2]; g (B,3,K) = grad_scale * d(sum_c nll_c)/d x.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void kde_nll_kernel(const float* __restrict__ rgb_map, const float* __restrict__ target, int64_t B, int K,
+                               float bw_factor, float grad_scale, float* __restrict__ partial, float* __restrict__ g) {
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float nll_sum = 0.f, mse_sum = 0.f;
+  const float c_norm = 0.06349363593424097f;   // (2*pi)^(-1.5)
+  for (int c = 0; c < 3; ++c) {
+    const float* x = rgb_map + (b * 3 + c) * K;
+    const float t = target[b * 3 + c];
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s += x[k];
+    const float m = warp_sum(s) / (float)K;
+    float q = 0.f;
+    for (int k = lane; k < K; k += 32) { const float dlt = x[k] - m; q += dlt * dlt; }
+    const float var = warp_sum(q) / (float)(K - 1);
+    const float sd = sqrtf(var) * (float)K / (float)(K - 1);
+    const float h = sd * bw_factor + 1e-5f;
+    const float inv2h2 = 1.0f / (2.0f * h * h);
+    float ps = 0.f;
+    for (int k = lane; k < K; k += 32) { const float dlt = x[k] - t; ps += expf(-(dlt * dlt) * inv2h2) * (c_norm / h); }
+    const float pm = warp_sum(ps) / (float)K;
+    nll_sum += -logf(pm + 1e-5f);
+    mse_sum += (m - t) * (m - t);
+    if (g) {
+      const float coef = grad_scale / ((pm + 1e-5f) * (float)K * h * h);
+      for (int k = lane; k < K; k += 32) {
+        const float dlt = x[k] - t;
+        g[(b * 3 + c) * K + k] = coef * expf(-(dlt * dlt) * inv2h2) * (c_norm / h) * dlt;
+      }
+    }
+  }
+  if (lane == 0) { partial[b * 2 + 0] = nll_sum; partial[b * 2 + 1] = mse_sum; }
+}
+
+int launch_kde_nll(const float* rgb_map, const float* target, int64_t B, int K, float grad_scale, float* partial, float* g,
+                   cudaStream_t s) {
+  if (B == 0) return CFN_OK;
+  CFN_CHECK_ARG(K >= 2, "kde_nll: K_samples must be >= 2 (unbiased std)");
+  const float bw = (float)pow(0.8 / (double)K, -1.0 / 7.0);
+  int64_t threads = B * 32;
+  kde_nll_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(rgb_map, target, B, K, bw, grad_scale, partial, g);
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
 }
 
 int launch_mean_over_k(const float* w, float* out, int64_t rows, int K, cudaStream_t s) {

@@ -81,6 +81,13 @@ int cfn_flow_param_width(const CfnHandle* h);
 int cfn_zvals_f32(const float* rays, const float* t_vals, const float* t_rand, int lindisp, float* z_vals,
                   int64_t B, int N, void* stream);
 
+/* ---- F2: ray generation for a full image (render(..., c2w=pose), run_nerf_uncertainty_NF.py:129-158) ---------- */
+/* c2w_host: 12 floats in HOST memory, the rows of c2w[:3,:4].  Writes rays (H*W,11) = [o d near far viewdir] on the
+ * device: get_rays (run_nerf_helpers.py:288-297), viewdirs = d/|d| taken before the optional NDC warp
+ * (ndc_rays(H,W,focal,ndc_near,...), helpers:360-377; the reference passes ndc_near = 1). */
+int cfn_rays_from_pose_f32(int H, int W, double focal, const float* c2w_host, double near, double far, int ndc,
+                           double ndc_near, float* rays, void* stream);
+
 /* ---- A2-A5: positional encoding + MLP trunk/heads + flow conditioning ------------------------ */
 /* Bytes of caller-provided workspace cfn_network_fwd needs for n_points points.
  * save_for_backward != 0 sizes it for the training path (activations kept for cfn_network_bwd). */
@@ -137,6 +144,13 @@ int cfn_sample_pdf_f32(const float* bins, const float* weights, const float* u, 
 int cfn_merge_sorted_f32(const float* a, const float* b, float* out, int64_t B, int Na, int Nb, void* stream);
 /* mean over K of weights (B,N,K) -> (B,N)  (the shared fine grid decision) */
 int cfn_mean_over_k_f32(const float* w, float* out, int64_t rows, int K, void* stream);
+
+/* ---- F1: K-reduction + KDE negative log-likelihood of the trainer (run_nerf_uncertainty_NF.py:1027-1042) ------ */
+/* rgb_map (B,3,K), target (B,3) -> partial (B,2) = per-ray [sum_c nll_c, sum_c (mean_k rgb - target)^2] and, when
+ * g_rgb_map != NULL, g_rgb_map (B,3,K) = grad_scale * d(sum_c nll_c)/d rgb_map (bandwidth detached as in main:1036).
+ * The trainer's loss_nll is sum(partial[:,0]) / (3B); pass grad_scale = 1/(3B) to get its gradient directly. */
+int cfn_kde_nll_f32(const float* rgb_map, const float* target, int64_t B, int K, float grad_scale, float* partial,
+                    float* g_rgb_map, void* stream);
 
 /* ---- diagnostics ---------------------------------------------------------------------------------- */
 /* When CFN_TC_PROFILE=1 is set in the environment at cfn_create time, the tensor-core network kernel records

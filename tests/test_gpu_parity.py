@@ -501,3 +501,58 @@ def test_stressed_heads_precision_report(cf, dev):
     print("stressed-heads drift vs fp32 check mode:", errs)
     assert errs["fp16"]["rgb_mean"] <= TOL_TC and errs["fp16"]["depth_mean"] <= TOL_TC
     assert errs["fp16"]["rgb_mean"] <= errs["bf16"]["rgb_mean"] * 1.5 + 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# F2: ray generation from a pose (render(..., c2w=pose))
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ndc", [False, True])
+def test_rays_from_pose_matches_reference_ray_setup(cf, dev, ndc):
+    import math
+    H, W, focal = 37, 53, 61.7
+    th = 0.3
+    c2w = torch.tensor([[math.cos(th), 0.1, math.sin(th), 0.2], [0.0, 1.0, 0.05, -0.1],
+                        [-math.sin(th), 0.0, math.cos(th), 0.4]])
+    o, d = O.get_rays(H, W, focal, c2w)
+    vd = (d / torch.norm(d, dim=-1, keepdim=True)).reshape(-1, 3)
+    if ndc:
+        o, d = O.ndc_rays(H, W, focal, 1.0, o, d)
+    near, far = (0.0, 1.0) if ndc else (1.2, 8.0)
+    rays = cf.rays_from_pose(H, W, focal, c2w, near, far, ndc, dev).cpu()
+    assert rays.shape == (H * W, 11)
+    assert torch.equal(rays[:, 0:3], o.reshape(-1, 3).contiguous()), "origins differ bitwise"
+    assert torch.equal(rays[:, 3:6], d.reshape(-1, 3).contiguous()), "directions differ bitwise"
+    n32, f32_ = float(torch.tensor(near, dtype=torch.float32)), float(torch.tensor(far, dtype=torch.float32))
+    assert float(rays[:, 6].min()) == n32 == float(rays[:, 6].max()) and float(rays[:, 7].max()) == f32_
+    assert (rays[:, 8:11] - vd).abs().max().item() <= 2e-7
+
+
+def test_render_image_equals_render_rays_on_the_same_rays(cf, dev):
+    cfg = O.CfnConfig(W=256, K=64, h_alpha=32)
+    net = make_net(cf, cfg, O.make_params(cfg, 0, "lively"), *O.make_latents(cfg, 0), dev)
+    H, W, focal = 5, 7, 6.0
+    c2w = torch.eye(4)[:3]
+    rgb, disp, depth, extras = cf.render_image(H, W, focal, c2w, net, near=1.2, far=8.0, chunk=16, precision="fp32")
+    assert rgb.shape == (H, W, 3, 64) and disp.shape == (H, W, 64) and extras == {}
+    o, d = O.get_rays(H, W, focal, c2w)
+    ref = cf.render_rays(O.pack_ray_batch(o, d, 1.2, 8.0).to(dev), net, precision="fp32")
+    assert (rgb.reshape(-1, 3, 64) - ref["rgb_map"]).abs().max().item() <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# F1: fused K-reduction + KDE-NLL loss and its gradient
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,K", [(16, 32), (7, 64), (5, 128), (3, 5)])
+def test_fused_kde_nll_matches_trainer_loss_and_gradient(cf, dev, B, K):
+    g = torch.Generator().manual_seed(B + K)
+    rgb = (torch.rand(B, 3, K, generator=g) * 0.6 + 0.2).requires_grad_(True)
+    tgt = torch.rand(B, 3, generator=g)
+    ent = torch.tensor(0.41)
+    ref = O.kde_nll_loss(rgb, tgt, ent, K, 0.01)
+    ref["loss"].backward()
+    x = rgb.detach().to(dev).requires_grad_(True)
+    out = cf.kde_nll_loss(x, tgt.to(dev), ent.to(dev).expand(B * 128, K, 1), K, 0.01)
+    for k in ("loss", "loss_nll", "mse", "psnr"):
+        assert abs(float(out[k]) - float(ref[k])) <= 2e-5 * max(1.0, abs(float(ref[k]))), k
+    out["loss"].backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), rgb.grad.numpy(), rtol=2e-4, atol=2e-6 * float(rgb.grad.abs().max()))
