@@ -39,6 +39,8 @@ SYMBOLS = {
     "cfn_merge_sorted_f32": (_i32, [_f32p, _f32p, _f32p, _i64, _i32, _i32, _vp]),
     "cfn_mean_over_k_f32": (_i32, [_f32p, _f32p, _i64, _i32, _vp]),
     "cfn_kde_nll_f32": (_i32, [_f32p, _f32p, _i64, _i32, C.c_float, _f32p, _f32p, _vp]),
+    "cfn_adam_step_f32": (_i32, [_i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64),
+                          C.c_float, C.c_float, C.c_float, C.c_float, _i32, C.c_float, _vp]),
     "cfn_debug_profile": (_i32, [_vp, _vp, _i32]),
 }
 

@@ -308,3 +308,11 @@ extern "C" int cfn_kde_nll_f32(const float* rgb_map, const float* target, int64_
   CFN_CHECK_ARG(B >= 0 && (B == 0 || (rgb_map && target && partial)), "cfn_kde_nll_f32: null argument");
   return launch_kde_nll(rgb_map, target, B, K, grad_scale, partial, g_rgb_map, (cudaStream_t)stream);
 }
+
+extern "C" int cfn_adam_step_f32(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                                 float* const* exp_avg_sq, const int64_t* numels, float lr, float beta1, float beta2,
+                                 float eps, int step, float grad_scale, void* stream) {
+  CFN_CHECK_ARG(n_tensors == 0 || (params && grads && exp_avg && exp_avg_sq && numels), "cfn_adam_step_f32: null argument");
+  return launch_adam(n_tensors, params, grads, exp_avg, exp_avg_sq, numels, lr, beta1, beta2, eps, step, grad_scale,
+                     (cudaStream_t)stream);
+}

@@ -68,6 +68,9 @@ int launch_sample_pdf(const float* bins, const float* weights, const float* u, f
 int launch_merge_sorted(const float* a, const float* b, float* out, int64_t B, int Na, int Nb, cudaStream_t s);
 int launch_kde_nll(const float* rgb_map, const float* target, int64_t B, int K, float grad_scale, float* partial, float* g,
                    cudaStream_t s);
+int launch_adam(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                float* const* exp_avg_sq, const int64_t* numels, float lr, float beta1, float beta2, float eps, int step,
+                float grad_scale, cudaStream_t s);
 int launch_mean_over_k(const float* w, float* out, int64_t rows, int K, cudaStream_t s);
 
 int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,

@@ -32,6 +32,16 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_WEIGHTS_EPOCH = 0
+
+
+def bump_weights_epoch():
+    """Called by code that updates parameters without going through torch in-place ops (FusedAdam): every Engine
+    re-packs its weights on its next use."""
+    global _WEIGHTS_EPOCH
+    _WEIGHTS_EPOCH += 1
+
+
 class Engine:
     """Owns a CfnHandle for `module` on `device` at one precision mode ("fp32" | "bf16" | "fp16")."""
 
@@ -73,7 +83,7 @@ class Engine:
 
     # ---- weights --------------------------------------------------------------------------------------
     def _version(self):
-        return tuple(p._version for p in self.params) + tuple(p.data_ptr() for p in self.params)
+        return (_WEIGHTS_EPOCH,) + tuple(p._version for p in self.params) + tuple(p.data_ptr() for p in self.params)
 
     def pack(self, force: bool = False):
         """Re-pack the fp32 master weights when any parameter changed since the last call."""

@@ -152,6 +152,14 @@ int cfn_mean_over_k_f32(const float* w, float* out, int64_t rows, int K, void* s
 int cfn_kde_nll_f32(const float* rgb_map, const float* target, int64_t B, int K, float grad_scale, float* partial,
                     float* g_rgb_map, void* stream);
 
+/* ---- F3: fused optimiser step (torch.optim.Adam, run_nerf_uncertainty_NF.py:339, 1065-1077) ------------------- */
+/* One launch over all n_tensors parameter tensors.  The four pointer arrays and numels live in HOST memory and hold
+ * DEVICE pointers / element counts; `step` is the 1-based step count (bias correction), `lr` the already decayed
+ * learning rate (main:1073-1077), `grad_scale` multiplies every gradient first (1/world after a sum all-reduce). */
+int cfn_adam_step_f32(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                      float* const* exp_avg_sq, const int64_t* numels, float lr, float beta1, float beta2, float eps,
+                      int step, float grad_scale, void* stream);
+
 /* ---- diagnostics ---------------------------------------------------------------------------------- */
 /* When CFN_TC_PROFILE=1 is set in the environment at cfn_create time, the tensor-core network kernel records
  * clock64() stamps of CTA 0 (3 roles x 4096: epilogue warp, MMA thread, TMA producer); this copies them to HOST

@@ -556,3 +556,30 @@ def test_fused_kde_nll_matches_trainer_loss_and_gradient(cf, dev, B, K):
         assert abs(float(out[k]) - float(ref[k])) <= 2e-5 * max(1.0, abs(float(ref[k]))), k
     out["loss"].backward()
     np.testing.assert_allclose(x.grad.cpu().numpy(), rgb.grad.numpy(), rtol=2e-4, atol=2e-6 * float(rgb.grad.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# F3: fused Adam step
+# ------------------------------------------------------------------------------------------------
+def test_fused_adam_matches_torch_adam(cf, dev):
+    from cfnerf_b200.optim import FusedAdam, decayed_lr
+    g = torch.Generator().manual_seed(0)
+    shapes = [(512, 575), (512,), (3,), (1,), (36, 64), (257, 33)]
+    a = [torch.nn.Parameter(torch.randn(*s, generator=g).to(dev)) for s in shapes]
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    oa, ob = FusedAdam(a, lr=5e-4), torch.optim.Adam(b, lr=5e-4, betas=(0.9, 0.999))
+    for it in range(5):
+        lr = decayed_lr(5e-4, 250, it * 1000)
+        for opt in (oa, ob):
+            for gp in opt.param_groups:
+                gp["lr"] = lr                       # the reference's decay loop (main:1076-1077)
+        for pa, pb in zip(a, b):
+            gr = torch.randn(pa.shape, generator=g).to(dev) * (0.1 + it)
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        from cfnerf_b200 import engine as E
+        e0 = E._WEIGHTS_EPOCH
+        oa.step(); ob.step()
+        assert E._WEIGHTS_EPOCH > e0                # the engines' re-pack trigger
+        for pa, pb in zip(a, b):
+            assert (pa - pb).abs().max().item() <= 2e-6 * max(1.0, float(pb.abs().max())), it
+    assert abs(decayed_lr(5e-4, 250, 250000) - 5e-5) < 1e-12
