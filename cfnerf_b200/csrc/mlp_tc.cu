@@ -29,7 +29,8 @@ constexpr int TC_MAX_STEPS = 20;
 constexpr int TC_MAX_KCH = 12;
 constexpr int TC_CHUNK_BYTES = 128 * 128;   // 128 rows x 64 columns x 2 bytes
 constexpr int TC_SRC_GP = 8, TC_SRC_GD = 9;   // host-side source ids; the device sees smem chunk indices AC / AC+1
-constexpr int TC_THREADS = 384;             // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int TC_THREADS = 384;             // warps 0..7 encode/epilogue, 8 TMEM alloc, 9 (profiling), 10 TMA, 11 MMA
+constexpr int TC_W_ALLOC = 8, TC_W_WATCH = 9, TC_W_TMA = 10, TC_W_MMA = 11;   // the scheduler favours high warp ids
 constexpr int TC_MAX_STAGES = 8;
 
 struct TcStep {
@@ -40,7 +41,8 @@ struct TcStep {
   int order_rev;  // issue the parts in reverse order (lets a pending drain of TMEM columns 0..63 finish)
   int n_k;        // K chunks
   // per K chunk, packed: bits 0..7 shared-memory chunk index of the A operand (0..AC-1 activation chunk, AC = gamma(p),
-  // AC+1 = gamma(d)); bits 8..15 first K=16 slice of the 64-column chunk; bits 16..23 number of K=16 instructions
+  // AC+1 = gamma(d)); bits 8..15 first K=16 slice of the 64-column chunk; bits 16..23 number of K=16 instructions; bit 24: bias entry
+  // (its B tile is a [rows][16] SWIZZLE_32B tile instead of a [rows][64] SWIZZLE_128B block)
   unsigned int kinfo[TC_MAX_KCH];
   int bias_off;   // kind 2 only: floats into the table: bias[n_total] then tanh flags[n_total]
   int out_col;    // kind 2: first column in the flow-parameter record
@@ -62,6 +64,7 @@ struct TcArgs {
   float* flow_params; int PP;
   int64_t n_units;      // tiles of 128*CG points
   int stages; int stage_bytes;
+  int stagger;                // cycles of start-up delay per CTA pair index (de-synchronises the weight-stream reads)
   unsigned long long* prof;   // optional timestamp buffer (CFN_TC_PROFILE=1): 4 roles x 4096 stamps of CTA 0
 };
 
@@ -74,12 +77,12 @@ struct TcPlan {
   std::vector<float> table_host_flags;   // unused placeholder for symmetry
   float* compA; float* compA_b; // composed alpha conditioning (3F x W), (3F)
   float* compC; float* compC_b; // composed rgb conditioning (15F x W/2), (15F)
-  CUtensorMap tm_big, tm_small;
-  int stages, stage_bytes;
+  CUtensorMap tm_big, tm_small, tm_bias;
+  int stages, stage_bytes, stagger;
   size_t smem_bytes;
   int num_sms;
   // pack recipe: one entry per 64-column block of the stream
-  struct Block { int src; int row0, rows_valid, col0, cols_valid, rows_padded; int64_t stream_row; int bias_src; };
+  struct Block { int src; int row0, rows_valid, col0, cols_valid, rows_padded; int64_t stream_row; int bias_src; int bias_col; };
   std::vector<Block> blocks;
   int* blocks_dev;
   // bias recipe
@@ -118,10 +121,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_LOOP:\n\t"
       // default .acquire.cta: a cluster-scope acquire makes ptxas emit CCTL.IVALL (L1 invalidate) after every wait,
       // which round 1's first profile showed to be the single largest stall of the MMA-issuing thread
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      // the suspend-time hint lets the warp SLEEP in hardware until the phase completes (woken by the arrival) instead of
+      // re-issuing the probe every few hundred ns: spinning waiters steal issue slots from the MMA-issuing warp
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+      "DONE:\n\t}" :: "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -279,6 +284,7 @@ __device__ __forceinline__ void encode_row(float x, float y, float z, int L, uin
 template <int CG, bool FP16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant__ CUtensorMap tm_small,
+              const __grid_constant__ CUtensorMap tm_bias,
               const __grid_constant__ TcPlanDev plan, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B; the dynamic segment is the only shared allocation
@@ -308,7 +314,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
     mbar_init(bar_local(&bars->in_ready), 8 * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == TC_W_ALLOC) {
     if (CG == 1) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&bars->tmem_ptr)), "r"(512) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -321,8 +327,15 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_ptr);
+  // All CTA pairs walk the SAME weight stream; started together they hit the same L2 lines at the same instant.
+  // A one-off start-up skew (persistent kernel, uniform tiles: the skew persists) spreads the reads over the stream.
+  if (a.stagger > 0) {
+    const long long t0 = clock64();
+    const long long wait = (long long)unit0 * a.stagger;
+    while (clock64() - t0 < wait) { }
+  }
 
-  if (warp == 0) {
+  if (warp == TC_W_TMA) {
     // ================================= TMA producer (whole warp walks the schedule, one elected lane issues) ==========
     int stage = 0; uint32_t phase = 0;
     Prof prof{(a.prof && blockIdx.x == 0 && lane == 0) ? a.prof + 2 * TC_PROF_N : nullptr, 0};
@@ -334,22 +347,32 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
         for (int blk = 0; blk < n_blk; ++blk) {
           mbar_wait(bar_local(&bars->empty[stage]), phase ^ 1u);
           prof.stamp();
+          const bool bias_tile = (st.kinfo[blk % st.n_k] >> 24) & 1u;
           if (elect_one()) {
             const uint32_t full_bar = bar_local(&bars->full[stage]);   // peer bit cleared inside tma_load_2d (CG == 2)
-            if (rank == 0) mbar_expect_tx(full_bar, (uint32_t)(rows * 128 * CG));
-            else mbar_arrive_cluster(bar_leader(&bars->full[stage]));
             const int row_g = st.row0 + blk * st.n_part + (int)rank * rows;
             const uint32_t dst = stage_base + (uint32_t)stage * a.stage_bytes;
-            int r = 0;
-            for (; rows - r >= 128; r += 128) tma_load_2d<CG>(dst + r * 128, &tm_big, 0, row_g + r, full_bar);
-            for (; r < rows; r += 16) tma_load_2d<CG>(dst + r * 128, &tm_small, 0, row_g + r, full_bar);
+            if (bias_tile) {
+              // one K=16 slice: [rows][16] elements = 32 bytes per row, whole 128-row boxes (the tail of a short block
+              // just re-reads the next rows of the stream; the MMA never touches them)
+              const int n_box = (rows + 127) / 128;
+              if (rank == 0) mbar_expect_tx(full_bar, (uint32_t)(n_box * 128 * 32 * CG));
+              else mbar_arrive_cluster(bar_leader(&bars->full[stage]));
+              for (int bx = 0; bx < n_box; ++bx) tma_load_2d<CG>(dst + bx * 128 * 32, &tm_bias, 0, row_g + bx * 128, full_bar);
+            } else {
+              if (rank == 0) mbar_expect_tx(full_bar, (uint32_t)(rows * 128 * CG));
+              else mbar_arrive_cluster(bar_leader(&bars->full[stage]));
+              int r = 0;
+              for (; rows - r >= 128; r += 128) tma_load_2d<CG>(dst + r * 128, &tm_big, 0, row_g + r, full_bar);
+              for (; r < rows; r += 16) tma_load_2d<CG>(dst + r * 128, &tm_small, 0, row_g + r, full_bar);
+            }
           }
           __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == TC_W_MMA) {
     // ================================= MMA issuer (leader CTA) =================================
     // The WHOLE warp runs the schedule so that every descriptor is a warp-uniform value (uniform registers, no
     // per-lane waterfall around the tcgen05 instructions); one elected lane issues.
@@ -358,18 +381,35 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
       uint32_t act_gen = 0, in_cnt = 0, out_cnt = 0;
       bool pending_out = false;
       Prof prof{(a.prof && blockIdx.x == 0 && lane == 0) ? a.prof + 1 * TC_PROF_N : nullptr, 0};
-      unsigned long long waited = 0ull;   // eight 8-bit generation counters, one per activation chunk
-      // wait until activation chunk j of generation `gen` is written (and its TMEM columns drained); barriers are
-      // always consumed one phase at a time so a parity can never alias an older phase
-      auto wait_act = [&](int j, uint32_t gen) {
-        uint32_t w = (uint32_t)(waited >> (8 * j)) & 0xffu;
-        if (w != (gen & 0xffu)) {
-          while (w != (gen & 0xffu)) { mbar_wait(bar_local(&bars->act_ready[j]), w & 1u); w = (w + 1u) & 0xffu; }
-          waited = (waited & ~(0xffull << (8 * j))) | ((unsigned long long)w << (8 * j));
-        }
+      // Activation chunks of the current generation become ready in index order (0,1,2,...), and every generation is
+      // consumed completely before the next one is produced, so one counter replaces per-chunk bookkeeping:
+      // chunks [0, ready_upto) of generation act_gen are known to be written (and their TMEM columns drained).
+      int ready_upto = 0;
+      const uint32_t act_bar0 = bar_local(&bars->act_ready[0]);
+      auto wait_act = [&](int j) {
+        if (act_gen == 0) return;
+        while (ready_upto <= j) { mbar_wait(act_bar0 + 8u * ready_upto, (act_gen - 1u) & 1u); ++ready_upto; }
+      };
+      // non-blocking probe (no suspend hint): issued BEFORE the MMAs of the current chunk so that its ~90-cycle
+      // latency overlaps their issue; the blocking wait afterwards is only taken when the probe failed
+      auto probe = [&](uint32_t bar, uint32_t parity) -> bool {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        return ok != 0;
       };
       const uint32_t full_bar0 = bar_local(&bars->full[0]), empty_bar0 = bar_local(&bars->empty[0]);
+      const uint64_t desc_sw32 = ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61) | ((uint64_t)1 << 16);
       const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+      // total number of weight blocks this CTA pair will consume (to know when there is no "next stage" to probe)
+      int64_t blocks_left = 0;
+      {
+        int per_tile = 0;
+        for (int g = 0; g < plan.n_steps; ++g) per_tile += plan.steps[g].n_parts * plan.steps[g].n_k;
+        const int64_t my_tiles = (a.n_units > unit0) ? (a.n_units - unit0 + n_grid_units - 1) / n_grid_units : 0;
+        blocks_left = my_tiles * per_tile;
+      }
+      bool cur_full_ready = false;      // the full barrier of `stage` is already known complete
       for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
         mbar_wait(bar_local(&bars->in_ready), in_cnt & 1u); ++in_cnt;
         for (int g = 0; g < plan.n_steps; ++g) {
@@ -379,17 +419,31 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
             const int pp = st.order_rev ? (st.n_parts - 1 - pi) : pi;
             const int c0 = pp * st.n_part;
             if (pending_out && c0 < 64) { mbar_wait(bar_local(&bars->out_done), (out_cnt - 1u) & 1u); pending_out = false; }
-            for (int j = c0 / 64; j <= (c0 + st.n_part - 1) / 64 && j < act_chunks; ++j) wait_act(j, act_gen);
+            {   // TMEM write-after-read: the columns of this part must have been drained
+              int jl = (c0 + st.n_part - 1) / 64;
+              if (jl > act_chunks - 1) jl = act_chunks - 1;
+              wait_act(jl);
+            }
             const uint32_t d_tmem = tmem_base + (uint32_t)c0;
             for (int kc = 0; kc < st.n_k; ++kc) {
               const uint32_t info = st.kinfo[kc];
               const int src = info & 0xff, ks0 = (info >> 8) & 0xff, nks = (info >> 16) & 0xff;
-              if (src < act_chunks) wait_act(src, act_gen);
-              mbar_wait(full_bar0 + 8u * stage, phase);
+              if (src < act_chunks) wait_act(src);
+              if (!cur_full_ready) mbar_wait(full_bar0 + 8u * stage, phase);
               prof.stamp();
               tc_fence_after();
+              const uint32_t b_addr = stage_base + (uint32_t)stage * a.stage_bytes;
               const uint64_t adesc = desc_hi | (uint64_t)((((act_base + (uint32_t)src * TC_CHUNK_BYTES) & 0x3FFFFu) >> 4) + 2u * ks0);
-              const uint64_t bdesc = desc_hi | (uint64_t)((((stage_base + (uint32_t)stage * a.stage_bytes) & 0x3FFFFu) >> 4) + 2u * ks0);
+              uint64_t bdesc = desc_hi | (uint64_t)(((b_addr & 0x3FFFFu) >> 4) + 2u * ks0);
+              if ((info >> 24) & 1u)   // bias tile: K-major SWIZZLE_32B, 8-row groups 256 bytes apart, a single K=16 slice
+                bdesc = desc_sw32 | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+              // probes for the NEXT chunk, overlapped with the issue of this one
+              const int nstage = (stage + 1 == a.stages) ? 0 : stage + 1;
+              const uint32_t nphase = (stage + 1 == a.stages) ? (phase ^ 1u) : phase;
+              --blocks_left;
+              const bool next_full = (blocks_left > 0) ? probe(full_bar0 + 8u * nstage, nphase) : false;
+              const bool can_probe_act = act_gen > 0 && ready_upto < act_chunks;
+              const bool next_act = can_probe_act ? probe(act_bar0 + 8u * ready_upto, (act_gen - 1u) & 1u) : false;
               if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
@@ -397,25 +451,42 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
                 umma_commit<CG>(empty_bar0 + 8u * stage);
               }
               __syncwarp();
-              if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+              if (next_act) ++ready_upto;          // that phase has been observed complete: consumed
+              cur_full_ready = next_full;
+              stage = nstage; phase = nphase;
             }
           }
           if (elect_one()) umma_commit<CG>(bar_local(&bars->acc_full));
           __syncwarp();
           prof.stamp();
-          if (st.kind == 2) { pending_out = true; ++out_cnt; } else { ++act_gen; }
+          if (st.kind == 2) { pending_out = true; ++out_cnt; } else { ++act_gen; ready_upto = 0; }
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp == TC_W_WATCH) {
+    // profiling only: time at which each stage's TMA data has landed (independent of the MMA thread's progress)
+    if (a.prof && blockIdx.x == 0 && rank == 0) {
+      int stage = 0; uint32_t phase = 0;
+      Prof prof{lane == 0 ? a.prof + 3 * TC_PROF_N : nullptr, 0};
+      for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units)
+        for (int g = 0; g < plan.n_steps; ++g) {
+          const int n_blk = plan.steps[g].n_parts * plan.steps[g].n_k;
+          for (int blk = 0; blk < n_blk; ++blk) {
+            mbar_wait(bar_local(&bars->full[stage]), phase);
+            prof.stamp();
+            if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+    }
+  } else if (warp < 8) {
     // ================================= encode + epilogue warps (256 threads) =================================
-    const int e = warp - 4, q = warp & 3, hh = e >> 2;
-    const int tid_e = threadIdx.x - 128;
+    const int e = warp, q = warp & 3, hh = e >> 2;
+    const int tid_e = threadIdx.x;
     const int row = q * 32 + lane;                         // TMEM lane == row of the tile owned by this thread
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t acc_cnt = 0;
-    Prof prof{(a.prof && blockIdx.x == 0 && warp == 4 && lane == 0) ? a.prof : nullptr, 0};
-    Prof prof2{(a.prof && blockIdx.x == 0 && warp == 4 && lane == 0) ? a.prof + 3 * TC_PROF_N : nullptr, 0};
+    Prof prof{(a.prof && blockIdx.x == 0 && warp == 0 && lane == 0) ? a.prof : nullptr, 0};
+    Prof prof2{nullptr, 0};   // (role 3 of the profile buffer is used by the TMA-landing watcher in warp 3)
     float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + sizeof(TcBarriers));   // 512 floats
     auto epi_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     // stage the fp32 bias (and tanh flags) of step g into shared memory: read back as warp-wide broadcasts
@@ -621,7 +692,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
   // teardown: everything issued has been consumed (the epilogue waited for the last commit)
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == 2) {
+  if (warp == TC_W_ALLOC) {
     if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
   }
@@ -639,17 +710,17 @@ __global__ void pack_stream_kernel(PackSrcTable srcs, const int* __restrict__ bl
   const int* b = blocks + blockIdx.x * 10;
   const int src = b[0], row0 = b[1], rows_valid = b[2], col0 = b[3], cols_valid = b[4], rows_padded = b[5];
   const int64_t stream_row = ((int64_t)(uint32_t)b[7] << 31) | (uint32_t)b[6];
-  const int bias_src = b[8];
+  const int bias_src = b[8], bias_col = b[9];
   const PackSrc S = srcs.s[src];
   for (int i = threadIdx.x; i < rows_padded * 64; i += blockDim.x) {
     const int r = i >> 6, c = i & 63;
     float v = 0.f;
     if (r < rows_valid && c < cols_valid) v = S.ptr[(int64_t)(row0 + r) * S.ld + col0 + c];
-    if (bias_src >= 0 && c >= 62 && r < rows_valid) {
+    if (bias_src >= 0 && (c == bias_col || c == bias_col + 1) && r < rows_valid) {
       // fp32 bias as a (hi, lo) pair of 16-bit values multiplied by the two ones columns: exact to ~2^-17 relative
       const float bv = srcs.s[bias_src].ptr[row0 + r];
       const float hi = FP16 ? __half2float(__float2half_rn(bv)) : __bfloat162float(__float2bfloat16_rn(bv));
-      v = (c == 62) ? hi : (bv - hi);
+      v = (c == bias_col) ? hi : (bv - hi);
     }
     uint16_t o;
     if (FP16) o = __half_as_ushort(__float2half_rn(v));
@@ -681,7 +752,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_tensor_map(CUtensorMap* map, void* base, int64_t rows, int box_rows, bool fp16) {
+static int make_tensor_map(CUtensorMap* map, void* base, int64_t rows, int box_rows, bool fp16, int box_cols = 64) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -692,10 +763,11 @@ static int make_tensor_map(CUtensorMap* map, void* base, int64_t rows, int box_r
   }
   cuuint64_t gdim[2] = {64, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {128};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CFN_ECUDA; }
   return CFN_OK;
@@ -718,6 +790,8 @@ int tc_create(CfnHandle* h) {
   p->cg = 2;
   if (const char* e = getenv("CFN_TC_CTA_GROUP")) p->cg = (atoi(e) == 1) ? 1 : 2;
   const int CG = p->cg;
+  p->stagger = 0;
+  if (const char* e = getenv("CFN_TC_STAGGER")) p->stagger = atoi(e);
   p->prof_dev = nullptr;
   p->stream_dev = nullptr; p->table_dev = nullptr; p->compA = p->compA_b = p->compC = p->compC_b = nullptr; p->blocks_dev = nullptr;
   TcPlanDev& dev = p->dev;
@@ -744,12 +818,13 @@ int tc_create(CfnHandle* h) {
     if (kind != 2) {
       bool has_gd = false;
       for (auto& k : kch) if (k.src == TC_SRC_GD) { k.kstart = 0; k.ksteps = 4; k.with_bias = 1; has_gd = true; }
-      if (!has_gd) kch.push_back({TC_SRC_GD, 3, 1, 0, 0, 1});
+      if (!has_gd) kch.push_back({TC_SRC_GD, 3, 1, 0, 0, 2});   // with_bias == 2: stand-alone bias entry (SWIZZLE_32B tile)
     }
     st.n_k = (int)kch.size();
     for (int i = 0; i < st.n_k; ++i) {
       const int idx = kch[i].src == TC_SRC_GP ? AC : (kch[i].src == TC_SRC_GD ? AC + 1 : kch[i].src);
-      st.kinfo[i] = (unsigned)idx | ((unsigned)kch[i].kstart << 8) | ((unsigned)kch[i].ksteps << 16);
+      st.kinfo[i] = (unsigned)idx | ((unsigned)kch[i].kstart << 8) | ((unsigned)kch[i].ksteps << 16) |
+                    ((unsigned)(kch[i].with_bias == 2 ? 1 : 0) << 24);
     }
     st.bias_off = table_off;
     st.out_col = out_col;
@@ -768,6 +843,7 @@ int tc_create(CfnHandle* h) {
         b.rows_padded = st.n_part;
         b.stream_row = stream_row;
         b.bias_src = kch[i].with_bias ? bias_src : -1;
+        b.bias_col = kch[i].with_bias == 2 ? 14 : 62;   // stand-alone tile: K slice 48..63 -> tile columns 0..15
         p->blocks.push_back(b);
         stream_row += st.n_part;
       }
@@ -847,7 +923,7 @@ int tc_create(CfnHandle* h) {
     flat.push_back(b.src); flat.push_back(b.row0); flat.push_back(b.rows_valid); flat.push_back(b.col0);
     flat.push_back(b.cols_valid); flat.push_back(b.rows_padded);
     flat.push_back((int)(b.stream_row & 0x7FFFFFFF)); flat.push_back((int)(b.stream_row >> 31));
-    flat.push_back(b.bias_src); flat.push_back(0);
+    flat.push_back(b.bias_src); flat.push_back(b.bias_col);
   }
   if (cudaMalloc(&p->blocks_dev, flat.size() * sizeof(int)) != cudaSuccess) return fail("cudaMalloc(blocks)");
   if (cudaMemcpy(p->blocks_dev, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return fail("cudaMemcpy(blocks)");
@@ -862,6 +938,7 @@ int tc_create(CfnHandle* h) {
   int rc;
   if ((rc = make_tensor_map(&p->tm_big, p->stream_dev, p->stream_rows, 128, fp16))) return rc;
   if ((rc = make_tensor_map(&p->tm_small, p->stream_dev, p->stream_rows, 16, fp16))) return rc;
+  if ((rc = make_tensor_map(&p->tm_bias, p->stream_dev, p->stream_rows, 128, fp16, 16))) return rc;   // [128 rows][16 cols], SWIZZLE_32B
   auto set_attr = [&](const void* fnp) {
     return cudaFuncSetAttribute(fnp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) == cudaSuccess;
   };
@@ -942,6 +1019,7 @@ int tc_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const f
   a.n_units = (a.M + 128 * CG - 1) / (128 * CG);
   a.stages = p->stages; a.stage_bytes = p->stage_bytes;
   a.prof = p->prof_dev;
+  a.stagger = p->stagger;
   int64_t units_grid = p->num_sms / CG;
   if (units_grid > a.n_units) units_grid = a.n_units;
   cudaLaunchConfig_t cfg{};
@@ -955,10 +1033,10 @@ int tc_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const f
   cfg.attrs = attr; cfg.numAttrs = 1;
   const bool fp16 = h->cfg.precision == CFN_PREC_FP16;
   cudaError_t e;
-  if (CG == 1) e = fp16 ? cudaLaunchKernelEx(&cfg, mlp_tc_kernel<1, true>, p->tm_big, p->tm_small, p->dev, a)
-                        : cudaLaunchKernelEx(&cfg, mlp_tc_kernel<1, false>, p->tm_big, p->tm_small, p->dev, a);
-  else e = fp16 ? cudaLaunchKernelEx(&cfg, mlp_tc_kernel<2, true>, p->tm_big, p->tm_small, p->dev, a)
-                : cudaLaunchKernelEx(&cfg, mlp_tc_kernel<2, false>, p->tm_big, p->tm_small, p->dev, a);
+  if (CG == 1) e = fp16 ? cudaLaunchKernelEx(&cfg, mlp_tc_kernel<1, true>, p->tm_big, p->tm_small, p->tm_bias, p->dev, a)
+                        : cudaLaunchKernelEx(&cfg, mlp_tc_kernel<1, false>, p->tm_big, p->tm_small, p->tm_bias, p->dev, a);
+  else e = fp16 ? cudaLaunchKernelEx(&cfg, mlp_tc_kernel<2, true>, p->tm_big, p->tm_small, p->tm_bias, p->dev, a)
+                : cudaLaunchKernelEx(&cfg, mlp_tc_kernel<2, false>, p->tm_big, p->tm_small, p->tm_bias, p->dev, a);
   if (e != cudaSuccess) { set_error("mlp_tc_kernel launch failed: %s", cudaGetErrorString(e)); return CFN_ECUDA; }
   return CFN_OK;
 }
