@@ -1021,6 +1021,7 @@ int tc_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const f
   a.prof = p->prof_dev;
   a.stagger = p->stagger;
   int64_t units_grid = p->num_sms / CG;
+  if (const char* e = getenv("CFN_TC_MAX_SMS")) { int v = atoi(e); if (v >= CG && v / CG < units_grid) units_grid = v / CG; }   // experiments only
   if (units_grid > a.n_units) units_grid = a.n_units;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(units_grid * CG));
