@@ -60,11 +60,13 @@ class CfnConfig:
 
     @property
     def skip(self) -> int:
-        return self.D // 2  # skips=[netdepth/2] (main:327)
+        # skips=[netdepth/2] with TRUE division (main:327): for an odd depth the list holds x.5 and `i in skips`
+        # (models:39, 171) never matches -> no skip connection at all
+        return self.D // 2 if self.D % 2 == 0 else -1
 
     def n_params(self) -> int:
         W, ip, idr = self.W, self.in_pos, self.in_dir
-        n = ip * W + W + (self.D - 2) * (W * W + W) + ((W + ip) * W + W)
+        n = ip * W + W + (self.D - 2) * (W * W + W) + ((W + (ip if self.skip >= 0 else 0)) * W + W)
         n += (W + idr) * (W // 2) + W // 2 + W * W + W + 2 * (W + 1)
         n += W * self.h_alpha + self.h_alpha + (W // 2) * self.h_rgb + self.h_rgb + 8
         for z, h in ((1, self.h_alpha), (3, self.h_rgb)):

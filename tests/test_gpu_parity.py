@@ -583,3 +583,48 @@ def test_fused_adam_matches_torch_adam(cf, dev):
         for pa, pb in zip(a, b):
             assert (pa - pb).abs().max().item() <= 2e-6 * max(1.0, float(pb.abs().max())), it
     assert abs(decayed_lr(5e-4, 250, 250000) - 5e-5) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# generality of the tensor-core path: other architectures / shapes against the fp32 check mode of the same library
+# (the fp32 mode itself is pinned to the oracle above)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw,n_rays,N", [
+    (dict(W=256, K=40, h_alpha=32, F=2), 37, 128),       # K not a multiple of 32, two flows, ragged ray count
+    (dict(W=512, K=32, D=6), 5, 64),                     # shallower trunk (skip after layer 3), 64 samples
+    (dict(W=384, K=64, h_rgb=32, F=3), 130, 192),        # 6 activation chunks, odd flow count, 192 samples
+    (dict(W=128, K=32, L_pos=6, L_dir=2), 1, 128),       # single ray, narrow net (no staged output), fewer octaves
+    (dict(W=512, K=128, D=7), 9, 128),                   # odd depth: no skip connection at all (main:327)
+])
+def test_tensor_core_path_other_architectures(cf, dev, kw, n_rays, N):
+    cfg = O.CfnConfig(**kw)
+    p = O.make_params(cfg, 3, "lively")
+    sa, sr = O.make_latents(cfg, 3)
+    net = make_net(cf, cfg, p, sa, sr, dev)
+    rays = O.synthetic_rays(n_rays, 17).to(dev)
+    ref = cf.render_rays(rays, net, None, N, False, False, precision="fp32", want_kstats=True)
+    # the fp32 mode against the CPU oracle on this architecture too
+    ea, er = O.test_latents(sa, sr)
+    if N == 128:
+        with torch.no_grad():
+            orc = O.render_rays(p, cfg, rays.cpu(), ea, er, False, faithful=False)
+        assert (ref["rgb_map"].cpu() - orc["rgb_map"]).abs().max().item() <= TOL_FP32
+    for prec in ("bf16", "fp16"):
+        out = cf.render_rays(rays, net, None, N, False, False, precision=prec, want_kstats=True)
+        for k in ("rgb_map", "depth_map"):
+            err = (out[k] - ref[k]).abs().max().item()
+            assert err <= TOL_TC, (kw, prec, k, err)
+
+
+
+
+def test_large_ragged_batch_tensor_core_vs_fp32(cf, dev):
+    """A ray count that is neither a multiple of the 256-point pair tile nor of the chunking (10 007 rays)."""
+    cfg = O.CfnConfig()
+    net = make_net(cf, cfg, O.make_params(cfg, 0, "lively"), *O.make_latents(cfg, 0), dev)
+    rays = O.synthetic_rays(10007, 23).to(dev)
+    a = cf.render_rays(rays, net, None, 128, False, False, precision="fp16")
+    b = cf.render_rays(rays, net, None, 128, False, False, precision="fp32")
+    for k in ("rgb_map", "depth_map"):
+        assert (a[k] - b[k]).abs().max().item() <= TOL_TC, k
+    assert torch.isfinite(a["disp_map"]).all()

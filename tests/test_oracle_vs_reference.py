@@ -55,3 +55,19 @@ def test_get_rays_and_ndc_live():
     o2r, d2r = main.ndc_rays(12, 16, 20.0, 1.0, o_ref + torch.tensor([0.0, 0.0, 0.5]), d_ref)
     o2, d2 = O.ndc_rays(12, 16, 20.0, 1.0, o + torch.tensor([0.0, 0.0, 0.5]), d)
     assert torch.equal(o2r, o2) and torch.equal(d2r, d2)
+
+
+def test_odd_depth_has_no_skip_connection_live():
+    """skips=[netdepth/2] uses true division (main:327): D=7 gives [3.5] and the model has no skip layer."""
+    cfg = O.CfnConfig(D=7, W=64, K=8, h_alpha=16, h_rgb=16)
+    assert cfg.skip == -1
+    p = O.make_params(cfg, 0, "lively")
+    sa, sr = O.make_latents(cfg, 0)
+    main, model, nq = refload.build_reference_model(cfg, p, sa, sr)
+    assert all(l.in_features == (cfg.in_pos if i == 0 else cfg.W) for i, l in enumerate(model.pts_linears))
+    rays = O.synthetic_rays(6, 2)
+    with torch.no_grad():
+        ref = main.render_rays(rays, model, nq, 128, False, False, K_samples=cfg.K, perturb=0.0, raw_noise_std=0.0)
+        ea, er = O.test_latents(sa, sr)
+        mine = O.render_rays(p, cfg, rays, ea, er, False)
+    assert (ref["rgb_map"] - mine["rgb_map"]).abs().max().item() <= 2e-6
