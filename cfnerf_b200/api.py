@@ -26,6 +26,9 @@ from .engine import Engine, _f32c, _ptr, _stream, _unwrap, engine_for
 # ("stressed") conditioning heads bf16 drifts to 1e-2 on the predictive mean while fp16 stays at 1e-3, inside the
 # 2e-3 bar (tests/test_gpu_parity.py::test_stressed_heads_precision_report).  "bf16" and "fp32" remain selectable.
 DEFAULT_PRECISION = "fp16"
+# Training (forward with saved activations + backward) runs layer by layer: "fp32" = CUDA-core FMA GEMMs (the exact
+# check mode), "tf32" / "bf16" / "fp16" = tcgen05 kind::tf32 GEMMs over fp32 storage with tf32-rounded operands.
+DEFAULT_TRAIN_PRECISION = "fp32"
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -230,7 +233,7 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=128, is_
     dev = ray_batch.device
     prec = precision or DEFAULT_PRECISION
     if is_train:
-        prec = "fp32" if precision is None else precision  # round 1: the training path runs the fp32 GEMMs
+        prec = precision or DEFAULT_TRAIN_PRECISION
     eng = engine_for(network_fn, dev, prec)
     if K_samples and K_samples != eng.K:
         raise ValueError(f"K_samples={K_samples} but the network was built with K={eng.K}")
@@ -400,3 +403,27 @@ def kde_nll_loss(rgb_map, target, loss_entropy, K, beta1=0.01, fused=None):
     nll = -torch.log((p1 * p2).mean(-1) + eps).mean()
     loss = nll + beta1 * loss_entropy.mean() if beta1 else nll
     return {"loss": loss, "loss_nll": nll, "mse": mse, "psnr": psnr}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the dense contraction primitive (unit tests / micro-benchmarks)
+# ---------------------------------------------------------------------------------------------------------
+def gemm(A, B, *, engine="tf32", bias=None, epilogue="none", aux=None, out=None, accumulate=False, split_k=1,
+         round_out=False):
+    """C = epi([C +] A @ B + bias) through cfn_gemm_f32.  A (M,K) and B (K,N) are fp32 CUDA tensors with ARBITRARY
+    strides (pass `.t()` views for the transposed flavours: the strides select the operand major, nothing is copied).
+    engine "fp32" = CUDA-core FMA, "tf32" = tcgen05 kind::tf32 fed by TMA."""
+    lib = _lib.load()
+    M, K = A.shape
+    K2, N = B.shape
+    assert K == K2 and A.dtype == torch.float32 and B.dtype == torch.float32 and A.is_cuda and B.is_cuda
+    if out is None:
+        out = torch.zeros(M, N, device=A.device) if (accumulate or split_k > 1) else torch.empty(M, N, device=A.device)
+    epi = {"none": 0, "relu": 1, "tanh_mask": 2, "relu_mask_mul": 3}[epilogue]
+    aux_rs = aux.stride(0) if (aux is not None and aux.dim() == 2) else 0
+    with torch.cuda.device(A.device):
+        check(lib.cfn_gemm_f32({"fp32": 0, "tf32": 1}[engine], _ptr(A), A.stride(0), A.stride(1), _ptr(B), B.stride(0),
+                               B.stride(1), _ptr(out), out.stride(0), _ptr(bias) if bias is not None else None,
+                               _ptr(aux) if aux is not None else None, aux_rs, M, N, K, epi, int(accumulate), int(split_k),
+                               int(round_out), _stream()), "cfn_gemm_f32")
+    return out

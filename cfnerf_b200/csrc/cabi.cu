@@ -1,6 +1,7 @@
 // C-ABI entry points (include/cfnerf_b200.h): handle lifetime, parameter table, argument checking and
 // dispatch to the kernels.  No torch types, no hidden device allocation outside create/pack.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "handle.h"
@@ -45,7 +46,7 @@ extern "C" int cfn_create(const CfnConfig* cfg, CfnHandle** out) {
   CFN_CHECK_ARG(cfg->h_alpha >= 1 && cfg->h_rgb >= 1, "h sizes must be positive");
   CFN_CHECK_ARG(cfg->F >= 1 && cfg->F <= 8, "n_flows %d unsupported (1..8)", cfg->F);
   CFN_CHECK_ARG(cfg->K >= 1 && cfg->K <= 1024, "K_samples %d unsupported", cfg->K);
-  CFN_CHECK_ARG(cfg->precision >= CFN_PREC_FP32 && cfg->precision <= CFN_PREC_FP16, "unknown precision mode");
+  CFN_CHECK_ARG(cfg->precision >= CFN_PREC_FP32 && cfg->precision <= CFN_PREC_TF32, "unknown precision mode");
   CfnHandle* h = new CfnHandle();
   h->cfg = *cfg;
   h->in_pos = 3 + 6 * cfg->L_pos;
@@ -56,6 +57,14 @@ extern "C" int cfn_create(const CfnConfig* cfg, CfnHandle** out) {
   h->n_floats = 0;
   h->packed = false;
   h->tc = nullptr;
+  h->gemm_tc = (cfg->precision != CFN_PREC_FP32) ? 1 : 0;
+  if (const char* e = getenv("CFN_TRAIN_GEMM")) {   // experiments: "fp32" forces the CUDA-core GEMMs, "tf32" the tensor cores
+    if (!strcmp(e, "fp32")) h->gemm_tc = 0;
+    if (!strcmp(e, "tf32")) h->gemm_tc = 1;
+  }
+  h->gp = (h->in_pos + 3) & ~3;
+  h->gd = (h->in_dir + 3) & ~3;
+  h->wg = h->amA_g = h->amC_g = nullptr;
   const int W = cfg->W, F = cfg->F;
   add_slot(h, "alpha_mean", 1, 1);
   add_slot(h, "alpha_std", 1, 1);
@@ -102,16 +111,43 @@ extern "C" int cfn_create(const CfnConfig* cfg, CfnHandle** out) {
     cfn_destroy(h);
     return CFN_ECUDA;
   };
+  // operand views: padded row strides, gap after gamma(p) in the skip layer
+  h->wg_floats = 0;
+  for (size_t i = 0; i < h->slots.size(); ++i) {
+    const ParamSlot& sl = h->slots[i];
+    WView v{nullptr, 0, 0, 0};
+    h->wg_offset.push_back(h->wg_floats);
+    const bool is_weight = sl.name.size() > 7 && sl.name.compare(sl.name.size() - 7, 7, ".weight") == 0;
+    if (is_weight) {
+      const bool skip_in = h->skip >= 0 && (int)i == h->s_pts(h->skip + 1, 0);
+      v.gap_at = skip_in ? h->in_pos : sl.cols;
+      v.gap = skip_in ? h->gp - h->in_pos : 0;
+      v.ld = (sl.cols + v.gap + 3) & ~3;
+      h->wg_floats += (int64_t)sl.rows * v.ld;
+    }
+    h->wv.push_back(v);
+  }
   h->w32 = h->amA = h->amA_b = h->amC = h->amC_b = h->tanh_flags = nullptr;
   h->gatherA_dev = h->gatherC_dev = nullptr;
   h->grads_table_dev = nullptr;
   if (cudaMalloc(&h->grads_table_dev, 64 * sizeof(float*)) != cudaSuccess) return fail("cudaMalloc");
   if (cudaMalloc(&h->w32, h->n_floats * sizeof(float)) != cudaSuccess) return fail("cudaMalloc(w32)");
   h->globals = h->w32;
+  if (cudaMalloc(&h->wg, (h->wg_floats + 4) * sizeof(float)) != cudaSuccess) return fail("cudaMalloc(wg)");
+  if (cudaMemset(h->wg, 0, (h->wg_floats + 4) * sizeof(float)) != cudaSuccess) return fail("cudaMemset(wg)");
+  for (size_t i = 0; i < h->slots.size(); ++i)
+    if (h->wv[i].ld) h->wv[i].p = h->wg + h->wg_offset[i];
   if (cudaMalloc(&h->amA, (size_t)3 * F * cfg->h_alpha * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
   if (cudaMalloc(&h->amA_b, (size_t)3 * F * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
   if (cudaMalloc(&h->amC, (size_t)15 * F * cfg->h_rgb * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
   if (cudaMalloc(&h->amC_b, (size_t)15 * F * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
+  if (h->gemm_tc) {
+    if (cudaMalloc(&h->amA_g, (size_t)3 * F * cfg->h_alpha * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc(&h->amC_g, (size_t)15 * F * cfg->h_rgb * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
+  } else {
+    h->amA_g = h->amA;
+    h->amC_g = h->amC;
+  }
   if (cudaMalloc(&h->tanh_flags, (size_t)h->PP * sizeof(float)) != cudaSuccess) return fail("cudaMalloc");
   if (cudaMalloc(&h->gatherA_dev, h->gatherA.size() * sizeof(GatherRow)) != cudaSuccess) return fail("cudaMalloc");
   if (cudaMalloc(&h->gatherC_dev, h->gatherC.size() * sizeof(GatherRow)) != cudaSuccess) return fail("cudaMalloc");
@@ -124,7 +160,7 @@ extern "C" int cfn_create(const CfnConfig* cfg, CfnHandle** out) {
       cudaMemcpy(h->gatherC_dev, h->gatherC.data(), h->gatherC.size() * sizeof(GatherRow), cudaMemcpyHostToDevice) !=
           cudaSuccess)
     return fail("cudaMemcpy(tables)");
-  if (cfg->precision != CFN_PREC_FP32) {
+  if (cfg->precision == CFN_PREC_BF16 || cfg->precision == CFN_PREC_FP16) {
     int rc = tc_create(h);
     if (rc != CFN_OK) {
       cfn_destroy(h);
@@ -139,6 +175,9 @@ extern "C" int cfn_destroy(CfnHandle* h) {
   if (!h) return CFN_OK;
   if (h->tc) tc_destroy(h);
   cudaFree(h->w32);
+  cudaFree(h->wg);
+  if (h->amA_g != h->amA) cudaFree(h->amA_g);
+  if (h->amC_g != h->amC) cudaFree(h->amC_g);
   cudaFree(h->amA);
   cudaFree(h->amA_b);
   cudaFree(h->amC);
@@ -301,6 +340,23 @@ extern "C" int cfn_mean_over_k_f32(const float* w, float* out, int64_t rows, int
 extern "C" int cfn_debug_profile(CfnHandle* h, uint64_t* out_host, int n) {
   CFN_CHECK_ARG(h && out_host && n > 0, "cfn_debug_profile: bad argument");
   return tc_debug_profile(h, (unsigned long long*)out_host, n);
+}
+
+extern "C" int cfn_gemm_f32(int engine, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
+                            int64_t b_cs, float* C, int64_t c_rs, const float* bias, const float* aux, int64_t aux_rs,
+                            int64_t M, int N, int64_t K, int epilogue, int accumulate, int split_k, int round_out,
+                            void* stream) {
+  CFN_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "cfn_gemm_f32: bad shape");
+  if (M == 0 || N == 0) return CFN_OK;
+  CFN_CHECK_ARG(A && B && C, "cfn_gemm_f32: null argument");
+  CFN_CHECK_ARG(engine == 0 || engine == 1, "cfn_gemm_f32: unknown engine %d", engine);
+  GemmArgs g{};
+  g.A = A; g.a_rs = a_rs; g.a_cs = a_cs;
+  g.B = B; g.b_rs = b_rs; g.b_cs = b_cs;
+  g.C = C; g.c_rs = c_rs; g.bias = bias; g.aux = aux; g.aux_rs = aux_rs;
+  g.M = M; g.N = N; g.K = K; g.epilogue = epilogue; g.accumulate = accumulate; g.split_k = split_k;
+  if (engine == 0) return launch_sgemm(g, (cudaStream_t)stream);
+  return launch_tgemm(g, round_out, (cudaStream_t)stream);
 }
 
 extern "C" int cfn_kde_nll_f32(const float* rgb_map, const float* target, int64_t B, int K, float grad_scale, float* partial,

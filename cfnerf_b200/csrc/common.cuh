@@ -97,5 +97,9 @@ struct GemmArgs {
   int split_k;                          // >1: atomicAdd partial sums into a pre-zeroed C (no bias/epilogue)
 };
 int launch_sgemm(const GemmArgs& g, cudaStream_t s);
+// same contract on the tensor cores (tcgen05.mma kind::tf32, TMA-fed; gemm_tf32.cu).  round_out: round the stored
+// outputs to the tf32 grid (they are the next GEMM's operands).
+bool tgemm_supported(const GemmArgs& g);
+int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s);
 
 }  // namespace cfn

@@ -1,0 +1,508 @@
+// K5-TC — general strided GEMM on the 5th-generation tensor cores with fp32 storage (tcgen05.mma kind::tf32).
+//
+//   C(m,n) = epi( [C(m,n) +] sum_k A(m,k) B(k,n) + bias[n] )        (same contract as sgemm.cu's launch_sgemm)
+//
+// This is the contraction of the TRAINING path (forward with saved activations, dgrad chain, split-K wgrad;
+// reference: loss.backward() through model/models.py:165-186, run_nerf_uncertainty_NF.py:1065-1067) and of the
+// CFN_PREC_TF32 render mode.  Operands stay fp32 in HBM exactly where mlp_fp32.cu's orchestration keeps them, so
+// the three GEMM flavours of a Linear need no transposed copies:
+//   forward   Y = X W^T      A = X  (K-major)   B = W  (K-major)
+//   dgrad     dX = dY W      A = dY (K-major)   B = W  (N-major: tcgen05 "MN-major" operand)
+//   wgrad     dW = dY^T X    A = dY (M-major)   B = X  (N-major), K = points, split over CTAs, fp32 atomics
+// Both majors are fed by the same TMA tensor maps over the row-major buffers (SWIZZLE_128B boxes of 32 floats);
+// only the shared-memory matrix descriptor and the instruction descriptor's major bits differ.
+//
+// Structure: persistent CTAs (or CTA pairs, cta_group::2: M = 256 rows per pair, each CTA stages half of B), tiles
+// of 128 x bn (bn <= 256) accumulated in TMEM, TWO accumulator buffers (2 x 256 columns) so the epilogue of tile i
+// overlaps the MMAs of tile i+1; a ring of TMA stages (A 16 KB + B <= 32 KB per 32-float K block); warp roles as
+// in K1 (warps 0-7 epilogue, 8 TMEM allocator, 10 TMA producer, 11 MMA issuer).
+// Out-of-range rows / columns / K tails are zero-filled by the TMA (the tensor maps carry the logical extents).
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace cfn {
+namespace {
+
+constexpr int TG_THREADS = 384;
+constexpr int TG_W_ALLOC = 8, TG_W_TMA = 10, TG_W_MMA = 11;
+constexpr int TG_MAX_STAGES = 6;
+constexpr int TG_A_BYTES = 128 * 128;   // 128 rows x 32 floats
+constexpr int TG_STG_LD = 36;           // floats per row of an epilogue staging tile (32 + 4: conflict-free float4 rows)
+constexpr int TG_STG_BYTES = 8 * 32 * TG_STG_LD * 4;   // one 32 x 32 tile per epilogue warp
+
+struct TgParams {
+  float* C; int64_t c_rs;
+  const float* bias; const float* aux; int64_t aux_rs;
+  int64_t M; int N; int64_t K;
+  int epilogue, accumulate, split_k, atomic, round_out, vec_ok;
+  int bn;              // N of one tcgen05.mma (multiple of 16, <= 256)
+  int b_rows_cta;      // B rows (n) staged by one CTA = bn / CG
+  int b_blocks;        // N-major B: 32-column blocks staged by one CTA
+  int64_t k_per_split; // multiple of 32
+  int64_t m_tiles; int n_tiles;
+  int64_t n_work;      // m_tiles * n_tiles * split_k
+  int stages; int stage_bytes;
+};
+
+// ---- PTX wrappers (same idioms as mlp_tc.cu) -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" :: "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  if (CG == 1)
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+  else   // both CTAs of the pair issue; the peer bit of the barrier address is cleared: bytes land on the leader's barrier
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// round-to-nearest (ties away) onto the 10-bit tf32 significand: the tensor core TRUNCATES fp32 operands, which is
+// a one-sided error that accumulates over the layers; operands written through this are read back exactly
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
+}
+
+struct TgBarriers {
+  uint64_t full[TG_MAX_STAGES];
+  uint64_t empty[TG_MAX_STAGES];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_ptr;
+  uint32_t pad;
+};
+
+// descriptor constants (cute::UMMA::SmemDescriptor): version 1 (bit 46), SWIZZLE_128B (2 << 61)
+//   K-major : rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused (1)
+//   MN-major: for 32-bit operands the only layout is SWIZZLE_128B_BASE32B (layout type 1; TMA swizzle 128B_ATOM_32B: the
+//             32-byte units of a 128-byte row are permuted by row % 4): 32-float column blocks `lbo` bytes apart (LBO),
+//             4-k-row groups 512 bytes apart (SBO)   (cute::UMMA::Layout_MN_SW128_32B_Atom)
+__device__ __forceinline__ uint64_t desc_hi_kmajor() {
+  return ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_hi_mnmajor(uint32_t lbo_bytes) {
+  return ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+
+template <int CG, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
+  TgBarriers* bars = reinterpret_cast<TgBarriers*>(smem_raw + (size_t)p.stages * p.stage_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int64_t unit0 = blockIdx.x / CG, n_grid_units = gridDim.x / CG;
+  auto bar_local = [&](const uint64_t* b) { return smem_u32(b); };
+  auto bar_leader = [&](const uint64_t* b) { return (CG == 2) ? mapa_rank(smem_u32(b), 0) : smem_u32(b); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TG_MAX_STAGES; ++s) { mbar_init(bar_local(&bars->full[s]), CG); mbar_init(bar_local(&bars->empty[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_local(&bars->acc_full[b]), 1); mbar_init(bar_local(&bars->acc_empty[b]), 8 * CG); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == TG_W_ALLOC) {
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&bars->tmem_ptr)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&bars->tmem_ptr)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_ptr);
+
+  // work item w -> (m tile, n tile, K split): n fastest, so the n tiles of one row panel run side by side (A from L2)
+  auto decode = [&](int64_t w, int64_t& mt, int& nt, int& z) {
+    nt = (int)(w % p.n_tiles);
+    const int64_t r = w / p.n_tiles;
+    mt = r % p.m_tiles;
+    z = (int)(r / p.m_tiles);
+  };
+  auto k_blocks = [&](int z, int64_t& k_begin) {
+    k_begin = (int64_t)z * p.k_per_split;
+    int64_t k_end = k_begin + p.k_per_split;
+    if (k_end > p.K) k_end = p.K;
+    return (int)((k_end - k_begin + 31) / 32);
+  };
+
+  if (warp == TG_W_TMA) {
+    // ================================= TMA producer =================================
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t b_tx = B_MN ? (uint32_t)p.b_blocks * 4096u : (uint32_t)p.b_rows_cta * 128u;
+    for (int64_t w = unit0; w < p.n_work; w += n_grid_units) {
+      int64_t mt; int nt, z; decode(w, mt, nt, z);
+      int64_t k_begin; const int nkb = k_blocks(z, k_begin);
+      const int m0 = (int)(mt * 128 * CG + rank * 128);
+      const int n0 = nt * p.bn + (int)rank * p.b_rows_cta;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(bar_local(&bars->empty[stage]), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t full_bar = bar_local(&bars->full[stage]);
+          if (rank == 0) mbar_expect_tx(full_bar, (uint32_t)(TG_A_BYTES + b_tx) * CG);
+          else mbar_arrive_cluster(bar_leader(&bars->full[stage]));
+          const uint32_t dstA = smem_base + (uint32_t)stage * p.stage_bytes;
+          const uint32_t dstB = dstA + TG_A_BYTES;
+          const int k0 = (int)(k_begin + (int64_t)kb * 32);
+          if (!A_MN) tma_load_2d<CG>(dstA, &tmA, k0, m0, full_bar);
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d<CG>(dstA + j * 4096, &tmA, m0 + 32 * j, k0, full_bar);
+          }
+          if (!B_MN) tma_load_2d<CG>(dstB, &tmB, k0, n0, full_bar);
+          else
+            for (int j = 0; j < p.b_blocks; ++j) tma_load_2d<CG>(dstB + j * 4096, &tmB, n0 + 32 * j, k0, full_bar);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == TG_W_MMA) {
+    // ================================= MMA issuer (leader CTA; whole warp walks, one elected lane issues) ============
+    if (rank == 0) {
+      int stage = 0; uint32_t phase = 0;
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A/B = tf32 (2), major bits 15 / 16
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+      const uint64_t a_hi = A_MN ? desc_hi_mnmajor(4096) : desc_hi_kmajor();
+      const uint64_t b_hi = B_MN ? desc_hi_mnmajor(4096) : desc_hi_kmajor();
+      const uint32_t a_step = A_MN ? (1024u >> 4) : (32u >> 4);     // one K = 8 slice: 8 k rows, or 32 bytes along the row
+      const uint32_t b_step = B_MN ? (1024u >> 4) : (32u >> 4);
+      uint32_t it = 0;
+      for (int64_t w = unit0; w < p.n_work; w += n_grid_units, ++it) {
+        int64_t mt; int nt, z; decode(w, mt, nt, z);
+        int64_t k_begin; const int nkb = k_blocks(z, k_begin);
+        const uint32_t buf = it & 1u;
+        mbar_wait(bar_local(&bars->acc_empty[buf]), ((it >> 1) & 1u) ^ 1u);   // the epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 256u;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(bar_local(&bars->full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + (uint32_t)stage * p.stage_bytes;
+          const uint32_t b_addr = a_addr + TG_A_BYTES;
+          const uint64_t adesc = a_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+          const uint64_t bdesc = b_hi | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32<CG>(d_tmem, adesc + (uint64_t)(a_step * ks), bdesc + (uint64_t)(b_step * ks), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            umma_commit<CG>(bar_local(&bars->empty[stage]));
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (elect_one()) umma_commit<CG>(bar_local(&bars->acc_full[buf]));
+        __syncwarp();
+      }
+    }
+  } else if (warp < 8) {
+    // ================================= epilogue warps =================================
+    const int q = warp & 3, hh = warp >> 2;
+    float* stg = reinterpret_cast<float*>(smem_raw + (size_t)p.stages * p.stage_bytes + 1024) + warp * (32 * TG_STG_LD);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t it = 0;
+    for (int64_t w = unit0; w < p.n_work; w += n_grid_units, ++it) {
+      int64_t mt; int nt, z; decode(w, mt, nt, z);
+      const uint32_t buf = it & 1u;
+      const int64_t tile_m0 = mt * 128 * CG + rank * 128;
+      const int n_tile0 = nt * p.bn;
+      int n_cols = p.N - n_tile0; if (n_cols > p.bn) n_cols = p.bn;
+      const int n_chunks = (n_cols + 31) / 32;
+      mbar_wait(bar_local(&bars->acc_full[buf]), (it >> 1) & 1u);
+      tc_fence_after();
+      const int sub_r = lane >> 3, c4 = (lane & 7) * 4;
+      for (int c = hh; c < n_chunks; c += 2) {
+        // phase 1: this warp's 32 x 32 accumulator block, TMEM -> registers (thread = row) -> padded shared-memory tile
+        uint32_t v[32];
+        tmem_ld32(tmem_row + buf * 256u + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          *reinterpret_cast<float4*>(stg + lane * TG_STG_LD + 4 * u) =
+              make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
+        __syncwarp();
+        // phase 2: 8 lanes per row, 4 rows per instruction: every global access of the warp is 4 full 128-byte lines
+        const int gn = n_tile0 + c * 32 + c4;
+        const bool vec = p.vec_ok && (gn + 3 < p.N);
+        float b4[4] = {0.f, 0.f, 0.f, 0.f}, f4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (gn + i < p.N) {
+            if (p.bias) b4[i] = __ldg(p.bias + gn + i);
+            if (p.epilogue == EPI_TANH_MASK) f4[i] = __ldg(p.aux + gn + i);
+          }
+#pragma unroll 2
+        for (int t = 0; t < 8; ++t) {
+          const int r = t * 4 + sub_r;
+          const int64_t gm = tile_m0 + q * 32 + r;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + r * TG_STG_LD + c4);
+          if (gm >= p.M || gn >= p.N) continue;
+          float x[4] = {a4.x, a4.y, a4.z, a4.w};
+          float* cp = p.C + gm * p.c_rs + gn;
+          if (p.atomic) {
+            if (vec) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(cp), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+            else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) if (gn + i < p.N) atomicAdd(cp + i, x[i]);
+            }
+            continue;
+          }
+          float cin[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {1.f, 1.f, 1.f, 1.f};
+          const float* ap = (p.epilogue == EPI_RELU_MASK_MUL) ? (p.aux + gm * p.aux_rs + gn) : nullptr;
+          if (vec) {
+            if (p.accumulate) { const float4 t4 = *reinterpret_cast<const float4*>(cp); cin[0] = t4.x; cin[1] = t4.y; cin[2] = t4.z; cin[3] = t4.w; }
+            if (ap) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(ap)); ax[0] = t4.x; ax[1] = t4.y; ax[2] = t4.z; ax[3] = t4.w; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (gn + i < p.N) {
+                if (p.accumulate) cin[i] = cp[i];
+                if (ap) ax[i] = __ldg(ap + i);
+              }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float y = x[i] + b4[i] + cin[i];
+            if (p.epilogue == EPI_RELU) y = fmaxf(y, 0.f);
+            else if (p.epilogue == EPI_TANH_MASK) { if (f4[i] != 0.f) y = tanhf(y); }
+            else if (p.epilogue == EPI_RELU_MASK_MUL) { if (!(ax[i] > 0.f)) y = 0.f; }
+            if (p.round_out) y = round_tf32(y);
+            x[i] = y;
+          }
+          if (vec) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+          else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (gn + i < p.N) cp[i] = x[i];
+          }
+        }
+        __syncwarp();   // the staging tile is rewritten by the next chunk
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->acc_empty[buf]));
+    }
+  }
+
+  // teardown: every MMA has completed (the epilogue waited for the last commit) and every TMA has been consumed
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == TG_W_ALLOC) {
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// row-major fp32 matrix (rows x cols, row stride ld floats) -> 2-D map with box {32 floats, box_rows}, SWIZZLE_128B
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool mn_major) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CFN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available from the driver"); return CFN_ECUDA; }
+    fn = (EncodeTiledFn)p;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rows %lld cols %lld ld %lld box_rows %d", (int)r, (long long)rows,
+              (long long)cols, (long long)ld, box_rows);
+    return CFN_ECUDA;
+  }
+  return CFN_OK;
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int CG, bool A_MN, bool B_MN>
+int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const TgParams& p, size_t smem, cudaStream_t s) {
+  static bool attr_set = false;
+  auto kern = tgemm_kernel<CG, A_MN, B_MN>;
+  if (!attr_set) {
+    CFN_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int64_t units = num_sms() / CG;
+  if (units > p.n_work) units = p.n_work;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(units * CG));
+  cfg.blockDim = dim3(TG_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  if (e != cudaSuccess) { set_error("tgemm_kernel launch failed: %s", cudaGetErrorString(e)); return CFN_ECUDA; }
+  return CFN_OK;
+}
+
+}  // namespace
+
+// Can this GEMM run on the TMA-fed tensor-core kernel?  (unit stride along one axis of each operand, 16-byte aligned
+// bases and row strides; everything the network stage issues qualifies once its odd-width matrices are padded)
+bool tgemm_supported(const GemmArgs& g) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return false;
+  if (g.M > 0x7fffffff || g.K > 0x7fffffff) return false;
+  const bool a_k = (g.a_cs == 1), a_mn = (g.a_rs == 1);
+  const bool b_k = (g.b_rs == 1), b_mn = (g.b_cs == 1);
+  if (!(a_k || a_mn) || !(b_k || b_mn)) return false;
+  const int64_t a_ld = a_k ? g.a_rs : g.a_cs, b_ld = b_k ? g.b_cs : g.b_rs;
+  if (a_ld % 4 || b_ld % 4 || a_ld <= 0 || b_ld <= 0) return false;
+  if (!aligned16(g.A) || !aligned16(g.B)) return false;
+  return true;
+}
+
+int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s) {
+  if (g.M == 0 || g.N == 0) return CFN_OK;
+  CFN_CHECK_ARG(tgemm_supported(g), "tgemm: operand layout not supported by the TMA path");
+  static int cg_env = -1;
+  if (cg_env < 0) { const char* e = getenv("CFN_TG_CTA_GROUP"); cg_env = e ? atoi(e) : 2; if (cg_env != 1) cg_env = 2; }
+  const bool a_mn = (g.a_cs != 1);
+  const bool b_mn = (g.b_rs != 1);
+  const int CG = (g.M <= 128) ? 1 : cg_env;
+
+  TgParams p{};
+  p.C = g.C; p.c_rs = g.c_rs; p.bias = g.bias; p.aux = g.aux; p.aux_rs = g.aux_rs;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.epilogue = g.epilogue; p.accumulate = g.accumulate; p.split_k = g.split_k > 1 ? g.split_k : 1;
+  p.round_out = round_out;
+  p.vec_ok = (g.c_rs % 4 == 0) && aligned16(g.C) &&
+             (g.epilogue != EPI_RELU_MASK_MUL || (g.aux_rs % 4 == 0 && aligned16(g.aux)));
+  int bn = (g.N + 15) / 16 * 16;
+  if (bn > 256) bn = 256;
+  p.bn = bn;
+  p.b_rows_cta = bn / CG;
+  p.b_blocks = (p.b_rows_cta + 31) / 32;
+  const int b_bytes = b_mn ? p.b_blocks * 4096 : ((p.b_rows_cta * 128 + 1023) / 1024) * 1024;
+  p.stage_bytes = TG_A_BYTES + b_bytes;
+  int stages = (int)((227 * 1024 - 1024 - TG_STG_BYTES) / p.stage_bytes);
+  if (stages > TG_MAX_STAGES) stages = TG_MAX_STAGES;
+  p.stages = stages;
+  // split-K (wgrad): the caller pre-zeroes C and every split adds its partial sum with fp32 atomics
+  p.atomic = g.split_k > 1 ? 1 : 0;
+  int64_t kps = (g.K + p.split_k - 1) / p.split_k;
+  kps = (kps + 31) / 32 * 32;
+  p.k_per_split = kps;
+  p.split_k = (int)((g.K + kps - 1) / kps);   // drop empty splits
+  p.m_tiles = (g.M + 128 * CG - 1) / (128 * CG);
+  p.n_tiles = (g.N + bn - 1) / bn;
+  p.n_work = p.m_tiles * p.n_tiles * p.split_k;
+  size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + TG_STG_BYTES;   // ring | barriers (1 KB) | staging tiles
+  if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each allocates all 512 TMEM columns
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn) rc = make_map(&tmA, g.A, g.M, g.K, g.a_rs, 128, false);
+  else rc = make_map(&tmA, g.A, g.K, g.M, g.a_cs, 32, true);
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(&tmB, g.B, g.N, g.K, g.b_cs, p.b_rows_cta, false);
+  else rc = make_map(&tmB, g.B, g.K, g.N, g.b_rs, 32, true);
+  if (rc) return rc;
+
+  if (CG == 1) {
+    if (!a_mn && !b_mn) return launch_variant<1, false, false>(tmA, tmB, p, smem, s);
+    if (!a_mn && b_mn) return launch_variant<1, false, true>(tmA, tmB, p, smem, s);
+    if (a_mn && !b_mn) return launch_variant<1, true, false>(tmA, tmB, p, smem, s);
+    return launch_variant<1, true, true>(tmA, tmB, p, smem, s);
+  }
+  if (!a_mn && !b_mn) return launch_variant<2, false, false>(tmA, tmB, p, smem, s);
+  if (!a_mn && b_mn) return launch_variant<2, false, true>(tmA, tmB, p, smem, s);
+  if (a_mn && !b_mn) return launch_variant<2, true, false>(tmA, tmB, p, smem, s);
+  return launch_variant<2, true, true>(tmA, tmB, p, smem, s);
+}
+
+}  // namespace cfn

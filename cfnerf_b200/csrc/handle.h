@@ -19,6 +19,14 @@ struct ParamSlot {
   int64_t offset;     // float offset inside w32
 };
 
+// GEMM-operand view of an nn.Linear weight: row stride padded to a multiple of 4 floats (TMA needs 16-byte strides) and,
+// for the skip layer, a gap after the gamma(p) columns so that the h columns start 16-byte aligned:
+// original column c lives at c + (c >= gap_at ? gap : 0); pad columns are zero.
+struct WView {
+  const float* p;
+  int ld, gap_at, gap;
+};
+
 namespace cfn { struct TcPlan; }  // tensor-core weight stream + launch plan (mlp_tc.cu)
 
 struct CfnHandle {
@@ -44,6 +52,15 @@ struct CfnHandle {
   int* gatherC_dev;  // (15F,4)
   std::vector<GatherRow> gatherA, gatherC;
   float** grads_table_dev;  // (n slots) scratch pointer table for cfn_network_bwd
+
+  // GEMM operands of the layer-by-layer network stage (mlp_fp32.cu): fp32 FMA (gemm_tc = 0) or tcgen05 kind::tf32
+  int gemm_tc;              // 1: contractions run on the tensor cores (every precision mode except CFN_PREC_FP32)
+  int gp, gd;               // in_pos / in_dir rounded up to a multiple of 4 (activation / weight column padding)
+  float* wg;                // padded operand copy of every weight matrix (tf32-rounded when gemm_tc)
+  int64_t wg_floats;
+  std::vector<WView> wv;    // per slot (biases: p = nullptr)
+  std::vector<int64_t> wg_offset;
+  float* amA_g; float* amC_g;   // operand copies of amA / amC (tf32-rounded when gemm_tc, else aliases)
 
   cfn::TcPlan* tc;   // nullptr in fp32 mode
 };

@@ -1,8 +1,10 @@
 // CFN_PREC_FP32 network stage: positional encoding (run_nerf_helpers.py:21-69), the 8x512 trunk with skip-concat,
 // the conditioning heads (model/models.py:165-186) and the amortised flow parameters (models.py:358-385, done ONCE
 // per point instead of K times), forward with optional saved activations and the full backward (dgrad chain +
-// split-K wgrad).  All contractions are fp32 CUDA-core FMAs (sgemm.cu): this is the 1e-5 "check" mode of the
-// render path and the round-1 training path.
+// split-K wgrad).  The contractions run as fp32 CUDA-core FMAs (sgemm.cu) in CFN_PREC_FP32 — the 1e-5 "check" mode
+// — and as TMA-fed tcgen05 kind::tf32 GEMMs (gemm_tf32.cu) in every other mode: that is the training path of the
+// bf16 / fp16 modes and the whole network stage of CFN_PREC_TF32.  In the tensor-core flavour every buffer that is a
+// later GEMM's operand (activations, gradients, weights) is stored ROUNDED to tf32, because the tensor core truncates.
 #include "handle.h"
 
 namespace cfn {
@@ -13,7 +15,7 @@ namespace cfn {
 struct Fp32Layout {
   int ld5, ldv, ldg;
   int64_t X5, V, H, v, ha, hr;            // forward
-  int64_t P, GP, G1, G2, gv, gh, dAm;      // saved outputs / backward scratch
+  int64_t P, GP, G1, G2, gv, gh, dAm, dWp;  // saved outputs / backward scratch
   int nH;
   int64_t total;
 };
@@ -21,8 +23,8 @@ struct Fp32Layout {
 static Fp32Layout make_layout(const CfnHandle* h, int64_t M, int save) {
   Fp32Layout L;
   const int W = h->cfg.W;
-  L.ld5 = h->in_pos + W;
-  L.ldv = W + h->in_dir;
+  L.ld5 = h->gp + W;          // [gamma(p) | pad to 4 | h]: the h columns start 16-byte aligned
+  L.ldv = W + h->gd;          // [feature | gamma(d) | pad to 4]
   L.ldg = L.ld5 > L.ldv ? L.ld5 : L.ldv;
   L.nH = save ? h->cfg.D : 2;
   int64_t o = 0;
@@ -33,7 +35,7 @@ static Fp32Layout make_layout(const CfnHandle* h, int64_t M, int save) {
   L.v = take(M * (W / 2));
   L.ha = take(M * h->cfg.h_alpha);
   L.hr = take(M * h->cfg.h_rgb);
-  L.P = L.GP = L.G1 = L.G2 = L.gv = L.gh = L.dAm = 0;
+  L.P = L.GP = L.G1 = L.G2 = L.gv = L.gh = L.dAm = L.dWp = 0;
   if (save) {
     L.P = take(M * h->PP);
     L.GP = take(M * h->PP);
@@ -43,6 +45,7 @@ static Fp32Layout make_layout(const CfnHandle* h, int64_t M, int save) {
     int hm = h->cfg.h_alpha > h->cfg.h_rgb ? h->cfg.h_alpha : h->cfg.h_rgb;
     L.gh = take(M * hm);
     L.dAm = take((int64_t)h->PP * (hm + 1));
+    L.dWp = take((int64_t)W * (h->gp + W + 4));   // padded weight gradient of the odd-width layers
   }
   L.total = o;
   return L;
@@ -67,9 +70,15 @@ __device__ __forceinline__ void embed3(float x, float y, float z, int L, float* 
   }
 }
 
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
+}
+
+// n_pos / n_dir: padded widths (pad columns are written as zeros); round: store tf32-rounded values
 __global__ void encode_kernel(const float* __restrict__ rays, const float* __restrict__ z_vals,
                               const float* __restrict__ pts, const float* __restrict__ viewdirs, int64_t M, int N,
-                              int L_pos, int L_dir, float* __restrict__ X5, int ld5, float* __restrict__ Vd, int ldv) {
+                              int L_pos, int L_dir, float* __restrict__ X5, int ld5, float* __restrict__ Vd, int ldv,
+                              int n_pos, int n_dir, int round) {
   int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const int64_t b = m / N;
@@ -87,6 +96,32 @@ __global__ void encode_kernel(const float* __restrict__ rays, const float* __res
   embed3(px, py, pz, L_pos, X5 + m * ld5);
   const float* vd = viewdirs ? (viewdirs + b * 3) : (rays + b * 11 + 8);
   embed3(vd[0], vd[1], vd[2], L_dir, Vd + m * ldv);
+  for (int c = 3 + 6 * L_pos; c < n_pos; ++c) X5[m * ld5 + c] = 0.f;
+  for (int c = 3 + 6 * L_dir; c < n_dir; ++c) Vd[m * ldv + c] = 0.f;
+  if (round) {
+    for (int c = 0; c < 3 + 6 * L_pos; ++c) X5[m * ld5 + c] = round_tf32(X5[m * ld5 + c]);
+    for (int c = 0; c < 3 + 6 * L_dir; ++c) Vd[m * ldv + c] = round_tf32(Vd[m * ldv + c]);
+  }
+}
+
+// operand copy of every weight matrix: padded row stride, gap after gamma(p) in the skip layer, optional tf32 rounding
+struct RepackTable {
+  int64_t src[64], dst[64];
+  int rows[64], cols[64], ld[64], gap_at[64], gap[64];
+  int n;
+};
+__global__ void repack_weights_kernel(const float* __restrict__ w32, float* __restrict__ wg, RepackTable t, int round) {
+  const int s = blockIdx.y;
+  const int64_t n = (int64_t)t.rows[s] * t.cols[s];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / t.cols[s]), c = (int)(i % t.cols[s]);
+    const float v = w32[t.src[s] + i];
+    wg[t.dst[s] + (int64_t)r * t.ld[s] + c + (c >= t.gap_at[s] ? t.gap[s] : 0)] = round ? round_tf32(v) : v;
+  }
+}
+__global__ void round_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = round_tf32(src[i]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -125,8 +160,31 @@ int pack_fp32(CfnHandle* h, const float* const* params, cudaStream_t s) {
                                                  h->amA_b);
   gather_rows_kernel<<<15 * h->cfg.F, 64, 0, s>>>(h->w32, t, h->gatherC_dev, 15 * h->cfg.F, h->cfg.h_rgb, h->amC,
                                                   h->amC_b);
+  {
+    RepackTable rt;
+    rt.n = 0;
+    for (size_t i = 0; i < h->slots.size(); ++i) {
+      if (!h->wv[i].ld) continue;
+      const int k = rt.n++;
+      rt.src[k] = h->slots[i].offset; rt.dst[k] = h->wg_offset[i];
+      rt.rows[k] = h->slots[i].rows; rt.cols[k] = h->slots[i].cols;
+      rt.ld[k] = h->wv[i].ld; rt.gap_at[k] = h->wv[i].gap_at; rt.gap[k] = h->wv[i].gap;
+    }
+    repack_weights_kernel<<<dim3(64, rt.n), 256, 0, s>>>(h->w32, h->wg, rt, h->gemm_tc);
+    if (h->gemm_tc) {
+      const int na = 3 * h->cfg.F * h->cfg.h_alpha, nc = 15 * h->cfg.F * h->cfg.h_rgb;
+      round_copy_kernel<<<(na + 255) / 256, 256, 0, s>>>(h->amA, h->amA_g, na);
+      round_copy_kernel<<<(nc + 255) / 256, 256, 0, s>>>(h->amC, h->amC_g, nc);
+    }
+  }
   CFN_LAUNCH_CHECK();
   return CFN_OK;
+}
+
+// the contraction engine of this handle
+static int gemm(const CfnHandle* h, const GemmArgs& g, int round_out, cudaStream_t s) {
+  if (h->gemm_tc && tgemm_supported(g)) return launch_tgemm(g, round_out, s);
+  return launch_sgemm(g, s);   // fp32 mode, or a shape the TMA path cannot address (e.g. an odd flow-record width)
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -138,15 +196,16 @@ static inline const float* Wp(const CfnHandle* h, int slot) { return h->w32 + h-
 static int linear_fwd(const CfnHandle* h, int slot, const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t M,
                       int epi, const float* aux, cudaStream_t s) {
   const ParamSlot& w = h->slots[slot];
+  const WView& v = h->wv[slot];
   GemmArgs g{};
   g.A = X; g.a_rs = ldx; g.a_cs = 1;
-  g.B = Wp(h, slot); g.b_rs = 1; g.b_cs = w.cols;      // B(k,n) = W[n*in + k]
+  g.B = v.p; g.b_rs = 1; g.b_cs = v.ld;                // B(k,n) = W[n*ld + k]; pad columns meet zero activations
   g.C = Y; g.c_rs = ldy;
   g.bias = Wp(h, slot + 1);
   g.aux = aux; g.aux_rs = 0;
-  g.M = M; g.N = w.rows; g.K = w.cols;
+  g.M = M; g.N = w.rows; g.K = v.ld;
   g.epilogue = epi; g.accumulate = 0; g.split_k = 1;
-  return launch_sgemm(g, s);
+  return gemm(h, g, 1, s);
 }
 
 struct LayerIO {
@@ -161,7 +220,7 @@ static LayerIO trunk_io(const CfnHandle* h, const Fp32Layout& L, float* ws, int6
   if (i == 0) { io.in = ws + L.X5; io.ld_in = L.ld5; }
   else if (h->skip >= 0 && i == h->skip + 1) { io.in = ws + L.X5; io.ld_in = L.ld5; }
   else { io.in = Hbuf(i - 1); io.ld_in = W; }
-  if (h->skip >= 0 && i == h->skip) { io.out = ws + L.X5 + h->in_pos; io.ld_out = L.ld5; }
+  if (h->skip >= 0 && i == h->skip) { io.out = ws + L.X5 + h->gp; io.ld_out = L.ld5; }
   else { io.out = Hbuf(i); io.ld_out = W; }
   return io;
 }
@@ -172,7 +231,8 @@ int fp32_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const
   const int W = h->cfg.W, D = h->cfg.D, F = h->cfg.F;
   Fp32Layout L = make_layout(h, M, save);
   encode_kernel<<<(unsigned)((M + 127) / 128), 128, 0, s>>>(rays, z_vals, pts, viewdirs, M, N, h->cfg.L_pos,
-                                                            h->cfg.L_dir, ws + L.X5, L.ld5, ws + L.V + W, L.ldv);
+                                                            h->cfg.L_dir, ws + L.X5, L.ld5, ws + L.V + W, L.ldv, h->gp,
+                                                            h->gd, h->gemm_tc);
   CFN_LAUNCH_CHECK();
   int rc;
   LayerIO last{};
@@ -192,17 +252,17 @@ int fp32_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const
   {
     GemmArgs g{};
     g.A = ws + L.ha; g.a_rs = h->cfg.h_alpha; g.a_cs = 1;
-    g.B = h->amA; g.b_rs = 1; g.b_cs = h->cfg.h_alpha;
+    g.B = h->amA_g; g.b_rs = 1; g.b_cs = h->cfg.h_alpha;
     g.C = flow_params; g.c_rs = h->PP;
     g.bias = h->amA_b; g.aux = h->tanh_flags; g.aux_rs = 0;
     g.M = M; g.N = 3 * F; g.K = h->cfg.h_alpha; g.epilogue = EPI_TANH_MASK; g.split_k = 1;
-    if ((rc = launch_sgemm(g, s))) return rc;
+    if ((rc = gemm(h, g, 0, s))) return rc;
     g.A = ws + L.hr; g.a_rs = h->cfg.h_rgb;
-    g.B = h->amC; g.b_cs = h->cfg.h_rgb;
+    g.B = h->amC_g; g.b_cs = h->cfg.h_rgb;
     g.C = flow_params + 3 * F;
     g.bias = h->amC_b; g.aux = h->tanh_flags + 3 * F;
     g.N = 15 * F; g.K = h->cfg.h_rgb;
-    if ((rc = launch_sgemm(g, s))) return rc;
+    if ((rc = gemm(h, g, 0, s))) return rc;
   }
   if (save) CFN_CUDA(cudaMemcpyAsync(ws + L.P, flow_params, (size_t)M * h->PP * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return CFN_OK;
@@ -212,11 +272,12 @@ int fp32_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const
 // backward
 // ---------------------------------------------------------------------------------------------------
 __global__ void tanh_bwd_kernel(const float* __restrict__ g, const float* __restrict__ p, const float* __restrict__ flags,
-                                float* __restrict__ out, int64_t total, int PP) {
+                                float* __restrict__ out, int64_t total, int PP, int round) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const float pv = p[i];
-  out[i] = flags[i % PP] != 0.f ? g[i] * (1.0f - pv * pv) : g[i];
+  const float v = flags[i % PP] != 0.f ? g[i] * (1.0f - pv * pv) : g[i];
+  out[i] = round ? round_tf32(v) : v;
 }
 
 // out[n] += sum over a slab of rows of g[m*ld + n]   (out pre-zeroed)
@@ -240,36 +301,66 @@ static int colsum(const float* g, int64_t ld, int64_t M, int N, float* out, cuda
 }
 
 // dW(out x in) = G(M x out)^T X(M x in), split over the point dimension, atomically accumulated into zeroed dW
-static int wgrad(const float* G, int64_t ldg, int out_f, const float* X, int64_t ldx, int in_f, int64_t M, float* dW,
-                 cudaStream_t s) {
+static int wgrad(const CfnHandle* h, const float* G, int64_t ldg, int out_f, const float* X, int64_t ldx, int in_f, int64_t M,
+                 float* dW, cudaStream_t s) {
   CFN_CUDA(cudaMemsetAsync(dW, 0, (size_t)out_f * in_f * sizeof(float), s));
   GemmArgs g{};
   g.A = G; g.a_rs = 1; g.a_cs = ldg;        // A(m=o, k=pt) = G[pt*ldg + o]
   g.B = X; g.b_rs = ldx; g.b_cs = 1;        // B(k=pt, n=i) = X[pt*ldx + i]
   g.C = dW; g.c_rs = in_f;
   g.M = out_f; g.N = in_f; g.K = M;
-  int tiles = ((out_f + 127) / 128) * ((in_f + 127) / 128);
-  int64_t split = (M + 1023) / 1024;
-  int64_t cap = (148 * 8 + tiles - 1) / tiles;
-  if (split > cap) split = cap;
+  int64_t split;
+  if (h->gemm_tc && tgemm_supported(g)) {
+    // one K slice per CTA (pair): (m tiles x n tiles x splits) ~ number of SMs (pairs)
+    const int cg = out_f <= 128 ? 1 : 2;
+    const int bn = in_f >= 256 ? 256 : ((in_f + 15) / 16) * 16;
+    const int tiles = ((out_f + 128 * cg - 1) / (128 * cg)) * ((in_f + bn - 1) / bn);
+    split = (148 / cg) / tiles;
+    const int64_t cap = (M + 255) / 256;
+    if (split > cap) split = cap;
+  } else {
+    const int tiles = ((out_f + 127) / 128) * ((in_f + 127) / 128);
+    split = (M + 1023) / 1024;
+    const int64_t cap = (148 * 8 + tiles - 1) / tiles;
+    if (split > cap) split = cap;
+  }
   if (split < 2) split = 2;                 // split_k > 1 selects the atomic accumulate path
   g.split_k = (int)split;
-  return launch_sgemm(g, s);
+  return gemm(h, g, 0, s);
+}
+
+// weight gradient of parameter slot `slot` (an nn.Linear whose input rows are X): straight into grads[slot] when the
+// operand view is unpadded, otherwise through the padded scratch and two strided copies that drop the pad columns
+static int wgrad_slot(const CfnHandle* h, int slot, const float* G, int64_t ldg, const float* X, int64_t ldx, int64_t M,
+                      float* dW, float* scratch, cudaStream_t s) {
+  const ParamSlot& w = h->slots[slot];
+  const WView& v = h->wv[slot];
+  if (v.ld == w.cols) return wgrad(h, G, ldg, w.rows, X, ldx, w.cols, M, dW, s);
+  int rc = wgrad(h, G, ldg, w.rows, X, ldx, v.ld, M, scratch, s);
+  if (rc) return rc;
+  const int first = v.gap_at < w.cols ? v.gap_at : w.cols;
+  if (first > 0)
+    CFN_CUDA(cudaMemcpy2DAsync(dW, (size_t)w.cols * 4, scratch, (size_t)v.ld * 4, (size_t)first * 4, w.rows, cudaMemcpyDeviceToDevice, s));
+  if (w.cols > first)
+    CFN_CUDA(cudaMemcpy2DAsync(dW + first, (size_t)w.cols * 4, scratch + first + v.gap, (size_t)v.ld * 4,
+                               (size_t)(w.cols - first) * 4, w.rows, cudaMemcpyDeviceToDevice, s));
+  return CFN_OK;
 }
 
 // Gin(M x n_cols) = [accumulate +] Gout(M x out) W[:, col0:col0+n_cols], optional ReLU mask
 static int dgrad(const CfnHandle* h, int slot, const float* Gout, int64_t ldgo, int col0, int n_cols, float* Gin,
                  int64_t ldgi, int64_t M, const float* mask, int64_t ld_mask, int accumulate, cudaStream_t s) {
   const ParamSlot& w = h->slots[slot];
+  const WView& v = h->wv[slot];
   GemmArgs g{};
   g.A = Gout; g.a_rs = ldgo; g.a_cs = 1;
-  g.B = Wp(h, slot) + col0; g.b_rs = w.cols; g.b_cs = 1;   // B(k=o, n=i) = W[o*in + col0 + i]
+  g.B = v.p + col0 + (col0 >= v.gap_at ? v.gap : 0); g.b_rs = v.ld; g.b_cs = 1;   // B(k=o, n=i) = W[o*ld + col0' + i]
   g.C = Gin; g.c_rs = ldgi;
   g.aux = mask; g.aux_rs = ld_mask;
   g.M = M; g.N = n_cols; g.K = w.rows;
   g.epilogue = mask ? EPI_RELU_MASK_MUL : EPI_NONE;
   g.accumulate = accumulate; g.split_k = 1;
-  return launch_sgemm(g, s);
+  return gemm(h, g, 1, s);
 }
 
 __global__ void scatter_rows_kernel(const float* __restrict__ dAm, const float* __restrict__ dAb, int cols,
@@ -299,7 +390,7 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
   {
     int64_t total = M * PP;
     tanh_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g_flow_params, ws + L.P, h->tanh_flags, ws + L.GP,
-                                                                    total, PP);
+                                                                    total, PP, h->gemm_tc);
     CFN_LAUNCH_CHECK();
   }
   const float* GP = ws + L.GP;
@@ -310,6 +401,7 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
   float* G2 = ws + L.G2;
   float* gh = ws + L.gh;
   float* gv = ws + L.gv;
+  float* dWp = ws + L.dWp;
 
   // zero every flow-conditioning gradient: rows the path never reads keep an exact 0
   for (int base : {h->s_frgb, h->s_falpha})
@@ -323,41 +415,41 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
   // 2. alpha conditioning branch
   {
     // gathered dAmA = GP[:, :3F]^T ha ; bias = colsum
-    if ((rc = wgrad(GP, PP, 3 * F, ws + L.ha, ha_n, ha_n, M, dAm, s))) return rc;
+    if ((rc = wgrad(h, GP, PP, 3 * F, ws + L.ha, ha_n, ha_n, M, dAm, s))) return rc;
     if ((rc = colsum(GP, PP, M, 3 * F, dAb, s))) return rc;
     scatter_rows_kernel<<<3 * F, 64, 0, s>>>(dAm, dAb, ha_n, h->gatherA_dev, 3 * F, table);
     CFN_LAUNCH_CHECK();
     // g_ha = GP[:, :3F] amA
     GemmArgs g{};
     g.A = GP; g.a_rs = PP; g.a_cs = 1;
-    g.B = h->amA; g.b_rs = ha_n; g.b_cs = 1;
+    g.B = h->amA_g; g.b_rs = ha_n; g.b_cs = 1;
     g.C = gh; g.c_rs = ha_n; g.M = M; g.N = ha_n; g.K = 3 * F; g.split_k = 1;
-    if ((rc = launch_sgemm(g, s))) return rc;
-    if ((rc = wgrad(gh, ha_n, ha_n, h7, ld7, W, M, grads[h->s_halpha], s))) return rc;
+    if ((rc = gemm(h, g, 1, s))) return rc;
+    if ((rc = wgrad_slot(h, h->s_halpha, gh, ha_n, h7, ld7, M, grads[h->s_halpha], dWp, s))) return rc;
     if ((rc = colsum(gh, ha_n, M, ha_n, grads[h->s_halpha + 1], s))) return rc;
     // g_h7 (unmasked, first contribution) = g_ha W_halpha
     if ((rc = dgrad(h, h->s_halpha, gh, ha_n, 0, W, G1, W, M, nullptr, 0, 0, s))) return rc;
   }
   // 3. rgb conditioning branch
   {
-    if ((rc = wgrad(GP + 3 * F, PP, 15 * F, ws + L.hr, hr_n, hr_n, M, dAm, s))) return rc;
+    if ((rc = wgrad(h, GP + 3 * F, PP, 15 * F, ws + L.hr, hr_n, hr_n, M, dAm, s))) return rc;
     if ((rc = colsum(GP + 3 * F, PP, M, 15 * F, dAb, s))) return rc;
     scatter_rows_kernel<<<15 * F, 64, 0, s>>>(dAm, dAb, hr_n, h->gatherC_dev, 15 * F, table);
     CFN_LAUNCH_CHECK();
     GemmArgs g{};
     g.A = GP + 3 * F; g.a_rs = PP; g.a_cs = 1;
-    g.B = h->amC; g.b_rs = hr_n; g.b_cs = 1;
+    g.B = h->amC_g; g.b_rs = hr_n; g.b_cs = 1;
     g.C = gh; g.c_rs = hr_n; g.M = M; g.N = hr_n; g.K = 15 * F; g.split_k = 1;
-    if ((rc = launch_sgemm(g, s))) return rc;
-    if ((rc = wgrad(gh, hr_n, hr_n, ws + L.v, W / 2, W / 2, M, grads[h->s_hrgb], s))) return rc;
+    if ((rc = gemm(h, g, 1, s))) return rc;
+    if ((rc = wgrad_slot(h, h->s_hrgb, gh, hr_n, ws + L.v, W / 2, M, grads[h->s_hrgb], dWp, s))) return rc;
     if ((rc = colsum(gh, hr_n, M, hr_n, grads[h->s_hrgb + 1], s))) return rc;
     // g_v = (g_hr W_hrgb) * relu'(v)
     if ((rc = dgrad(h, h->s_hrgb, gh, hr_n, 0, W / 2, gv, W / 2, M, ws + L.v, W / 2, 0, s))) return rc;
-    if ((rc = wgrad(gv, W / 2, W / 2, ws + L.V, L.ldv, L.ldv, M, grads[h->s_views], s))) return rc;
+    if ((rc = wgrad_slot(h, h->s_views, gv, W / 2, ws + L.V, L.ldv, M, grads[h->s_views], dWp, s))) return rc;
     if ((rc = colsum(gv, W / 2, M, W / 2, grads[h->s_views + 1], s))) return rc;
     // g_feat = g_v W_view[:, :W]   (gamma(d) columns need no gradient)
     if ((rc = dgrad(h, h->s_views, gv, W / 2, 0, W, G2, W, M, nullptr, 0, 0, s))) return rc;
-    if ((rc = wgrad(G2, W, W, h7, ld7, W, M, grads[h->s_feat], s))) return rc;
+    if ((rc = wgrad_slot(h, h->s_feat, G2, W, h7, ld7, M, grads[h->s_feat], dWp, s))) return rc;
     if ((rc = colsum(G2, W, M, W, grads[h->s_feat + 1], s))) return rc;
     // g_h7 = (g_h7 + g_feat W_feat) * relu'(h7)
     if ((rc = dgrad(h, h->s_feat, G2, W, 0, W, G1, W, M, h7, ld7, 1, s))) return rc;
@@ -368,8 +460,7 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
   for (int i = D - 1; i >= 0; --i) {
     LayerIO io = trunk_io(h, L, ws, M, i, 1);
     const int slot = h->s_pts(i, 0);
-    const int fin = h->slots[slot].cols;
-    if ((rc = wgrad(gout, W, W, io.in, io.ld_in, fin, M, grads[slot], s))) return rc;
+    if ((rc = wgrad_slot(h, slot, gout, W, io.in, io.ld_in, M, grads[slot], dWp, s))) return rc;
     if ((rc = colsum(gout, W, M, W, grads[slot + 1], s))) return rc;
     if (i == 0) break;
     // gradient w.r.t. the previous layer's (post-ReLU) output, masked by its ReLU

@@ -37,6 +37,9 @@ extern "C" {
 #define CFN_PREC_FP32 0 /* CUDA-core fp32 FMA GEMMs: the 1e-5 "check" mode and the round-1 training path   */
 #define CFN_PREC_BF16 1 /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulation in TMEM                  */
 #define CFN_PREC_FP16 2 /* tcgen05.mma kind::f16, fp16 operands (11-bit significand, TF32-class), fp32 acc  */
+#define CFN_PREC_TF32 3 /* tcgen05.mma kind::tf32 layer by layer, fp32 storage (operands rounded to tf32)       */
+/* Training (cfn_network_fwd with save_for_backward + cfn_network_bwd) runs the layer-by-layer chain with saved
+ * activations in every mode: fp32 FMA GEMMs in CFN_PREC_FP32, tf32 tensor-core GEMMs in the other three. */
 
 /* Architecture of one NeRF_Flows network (model/models.py:20-36; run_nerf_uncertainty_NF.py:317-336). */
 typedef struct CfnConfig {
@@ -165,6 +168,17 @@ int cfn_adam_step_f32(int n_tensors, float* const* params, const float* const* g
  * clock64() stamps of CTA 0 (3 roles x 4096: epilogue warp, MMA thread, TMA producer); this copies them to HOST
  * memory after a device synchronise.  Used by scripts/k1_timeline.py only; not part of the data path. */
 int cfn_debug_profile(CfnHandle* h, uint64_t* out_host, int n);
+
+/* The dense contraction primitive of the network stage, exposed for unit tests and micro-benchmarks:
+ *   C(m,n) = epi( [C(m,n) +] sum_k A[m*a_rs + k*a_cs] * B[k*b_rs + n*b_cs] + bias[n] )      (fp32 storage)
+ * engine 0: CUDA-core fp32 FMA (sgemm.cu); engine 1: tcgen05.mma kind::tf32 fed by TMA (gemm_tf32.cu; needs unit stride
+ * along one axis of each operand and 16-byte aligned bases / strides, else CFN_EINVAL).
+ * epilogue: 0 none, 1 ReLU, 2 tanh where aux[n] != 0, 3 zero where aux[m*aux_rs + n] <= 0.  split_k > 1: partial sums
+ * are added atomically into a pre-zeroed C (no bias / epilogue).  round_out (engine 1): round outputs to tf32.
+ * Replaces the torch.nn.Linear / autograd matmuls of model/models.py:165-186 inside cfn_network_fwd / _bwd. */
+int cfn_gemm_f32(int engine, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,
+                 float* C, int64_t c_rs, const float* bias, const float* aux, int64_t aux_rs, int64_t M, int N, int64_t K,
+                 int epilogue, int accumulate, int split_k, int round_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,6 @@
 """BASELINE.json configs[2]: one training step (render -> K-mean -> KDE-NLL + 0.01*entropy -> backward ->
 gradient all-reduce -> Adam) on a 4096-ray global batch, data-parallel over the ranks of torchrun.
-Round 1 runs this path on the fp32 CUDA-core GEMMs (the tcgen05 backward is round-2 work); reported for coverage."""
+CFN_TRAIN_PRECISION selects the GEMM engine of the step: fp32 (CUDA-core FMA) or tf32 (tcgen05 kind::tf32, default)."""
 import json
 import os
 import sys
@@ -22,6 +22,7 @@ dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 GLOBAL = int(os.environ.get("CFN_TRAIN_RAYS", "4096"))
+PREC = os.environ.get("CFN_TRAIN_PRECISION", "tf32")
 steps, warm = 5, 2
 cfg = O.CfnConfig()
 net = cf.NeRFFlowsParams.from_oracle_params(cfg, O.make_params(cfg, 0), *O.make_latents(cfg, 0)).to(dev)
@@ -33,14 +34,14 @@ g = torch.Generator().manual_seed(2)
 target = D.shard_rays(torch.rand(GLOBAL, 3, generator=g), rank, world).to(dev)
 torch.manual_seed(100 + rank)       # each rank draws its own latent noise, like each DataParallel replica (models.py:233-235)
 for _ in range(warm):
-    out = D.train_step(net, opt, rays, target, bucket)
+    out = D.train_step(net, opt, rays, target, bucket, precision=PREC)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(steps):
-    out = D.train_step(net, opt, rays, target, bucket)
+    out = D.train_step(net, opt, rays, target, bucket, precision=PREC)
 e1.record()
 torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -49,7 +50,7 @@ if world > 1:
 if rank == 0:
     t = float(ms) / steps * 1e-3
     print(json.dumps({"metric": "rays/sec (train step)", "value": GLOBAL / t, "unit": "rays/s", "n_gpus": world,
-                      "ms_per_step": t * 1e3, "global_batch_rays": GLOBAL, "dtype": "fp32 (CUDA-core GEMMs)",
+                      "ms_per_step": t * 1e3, "global_batch_rays": GLOBAL, "dtype": PREC,
                       "loss": float(out["loss"]), "psnr": float(out["psnr"]),
                       "gflops_per_step": GLOBAL * 128 * 4708864 * 3 / 1e9, "achieved_tflops": GLOBAL * 128 * 4708864 * 3 / t / 1e12}))
 if world > 1:
