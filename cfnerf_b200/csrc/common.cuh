@@ -95,11 +95,15 @@ struct GemmArgs {
   int epilogue;
   int accumulate;                       // C += result (applied before the epilogue)
   int split_k;                          // >1: atomicAdd partial sums into a pre-zeroed C (no bias/epilogue)
+  float* rowsum;                        // tensor-core engine, split_k > 1 only: rowsum[m] += sum_k A(m,k) (pre-zeroed; the bias
+                                        // gradient of a wgrad, produced by one extra N=16 MMA against a tile of ones)
 };
 int launch_sgemm(const GemmArgs& g, cudaStream_t s);
 // same contract on the tensor cores (tcgen05.mma kind::tf32, TMA-fed; gemm_tf32.cu).  round_out: round the stored
 // outputs to the tf32 grid (they are the next GEMM's operands).
 bool tgemm_supported(const GemmArgs& g);
 int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s);
+// true when launch_tgemm can also produce g.rowsum (every CTA (pair) owns exactly one K slice of one tile)
+bool tgemm_can_rowsum(const GemmArgs& g);
 
 }  // namespace cfn

@@ -45,6 +45,7 @@ struct TgParams {
   int64_t m_tiles; int n_tiles;
   int64_t n_work;      // m_tiles * n_tiles * split_k
   int stages; int stage_bytes;
+  float* rowsum;       // optional (atomic GEMMs): rowsum[m] += sum_k A(m,k)
 };
 
 // ---- PTX wrappers (same idioms as mlp_tc.cu) -----------------------------------------------------------
@@ -120,6 +121,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r; asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory"); return r;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // round-to-nearest (ties away) onto the 10-bit tf32 significand: the tensor core TRUNCATES fp32 operands, which is
 // a one-sided error that accumulates over the layers; operands written through this are read back exactly
@@ -166,6 +170,13 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < TG_MAX_STAGES; ++s) { mbar_init(bar_local(&bars->full[s]), CG); mbar_init(bar_local(&bars->empty[s]), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_local(&bars->acc_full[b]), 1); mbar_init(bar_local(&bars->acc_empty[b]), 8 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // 2 KB of ones right after the barriers: the B operand of the optional row-sum MMA (any layout of ones is ones)
+  const uint32_t ones_addr = smem_base + (uint32_t)p.stages * p.stage_bytes + 1024u;
+  if (p.rowsum) {
+    float* ones = reinterpret_cast<float*>(smem_raw + (size_t)p.stages * p.stage_bytes + 1024);
+    for (int i = threadIdx.x; i < 512; i += TG_THREADS) ones[i] = 1.0f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == TG_W_ALLOC) {
     if (CG == 1) {
@@ -237,6 +248,8 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint64_t b_hi = B_MN ? desc_hi_mnmajor(4096) : desc_hi_kmajor();
       const uint32_t a_step = A_MN ? (1024u >> 4) : (32u >> 4);     // one K = 8 slice: 8 k rows, or 32 bytes along the row
       const uint32_t b_step = B_MN ? (1024u >> 4) : (32u >> 4);
+      const uint32_t idesc16 = (idesc & ~(0x3Fu << 17)) | ((16u >> 3) << 17);
+      const uint64_t ones_desc = b_hi | (uint64_t)((ones_addr & 0x3FFFFu) >> 4);
       uint32_t it = 0;
       for (int64_t w = unit0; w < p.n_work; w += n_grid_units, ++it) {
         int64_t mt; int nt, z; decode(w, mt, nt, z);
@@ -256,6 +269,11 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               umma_tf32<CG>(d_tmem, adesc + (uint64_t)(a_step * ks), bdesc + (uint64_t)(b_step * ks), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            if (p.rowsum && nt == 0) {   // columns 256.. are free: a row-sum GEMM owns one work item per CTA (pair)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_tf32<CG>(tmem_base + 256u, adesc + (uint64_t)(a_step * ks), ones_desc, idesc16, (kb > 0 || ks > 0) ? 1u : 0u);
+            }
             umma_commit<CG>(bar_local(&bars->empty[stage]));
           }
           __syncwarp();
@@ -268,9 +286,10 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp < 8) {
     // ================================= epilogue warps =================================
     const int q = warp & 3, hh = warp >> 2;
-    float* stg = reinterpret_cast<float*>(smem_raw + (size_t)p.stages * p.stage_bytes + 1024) + warp * (32 * TG_STG_LD);
+    float* stg = reinterpret_cast<float*>(smem_raw + (size_t)p.stages * p.stage_bytes + 3072) + warp * (32 * TG_STG_LD);
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t it = 0;
+    const int sub_r = lane >> 3, c4 = (lane & 7) * 4;
     for (int64_t w = unit0; w < p.n_work; w += n_grid_units, ++it) {
       int64_t mt; int nt, z; decode(w, mt, nt, z);
       const uint32_t buf = it & 1u;
@@ -278,9 +297,23 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int n_tile0 = nt * p.bn;
       int n_cols = p.N - n_tile0; if (n_cols > p.bn) n_cols = p.bn;
       const int n_chunks = (n_cols + 31) / 32;
+      // dgrad reads one mask element per output element: the 8 row segments of a chunk are requested BEFORE the
+      // accumulator is waited for (and the next chunk's while the current one is processed), otherwise every one of
+      // the 32 row groups of a tile would pay a full HBM round trip in sequence
+      const bool pf = (p.epilogue == EPI_RELU_MASK_MUL) && p.vec_ok && !p.atomic;
+      float4 pre[8];
+      auto issue_pre = [&](int c) {
+        const int gnp = n_tile0 + c * 32 + c4;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int64_t gmp = tile_m0 + q * 32 + t * 4 + sub_r;
+          pre[t] = (gmp < p.M && gnp + 3 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.aux + gmp * p.aux_rs + gnp))
+                                                : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+      };
+      if (pf && hh < n_chunks) issue_pre(hh);
       mbar_wait(bar_local(&bars->acc_full[buf]), (it >> 1) & 1u);
       tc_fence_after();
-      const int sub_r = lane >> 3, c4 = (lane & 7) * 4;
       for (int c = hh; c < n_chunks; c += 2) {
         // phase 1: this warp's 32 x 32 accumulator block, TMEM -> registers (thread = row) -> padded shared-memory tile
         uint32_t v[32];
@@ -291,6 +324,10 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           *reinterpret_cast<float4*>(stg + lane * TG_STG_LD + 4 * u) =
               make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
         __syncwarp();
+        float4 cur[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) cur[t] = pre[t];
+        if (pf && c + 2 < n_chunks) issue_pre(c + 2);
         // phase 2: 8 lanes per row, 4 rows per instruction: every global access of the warp is 4 full 128-byte lines
         const int gn = n_tile0 + c * 32 + c4;
         const bool vec = p.vec_ok && (gn + 3 < p.N);
@@ -301,7 +338,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (p.bias) b4[i] = __ldg(p.bias + gn + i);
             if (p.epilogue == EPI_TANH_MASK) f4[i] = __ldg(p.aux + gn + i);
           }
-#pragma unroll 2
+#pragma unroll
         for (int t = 0; t < 8; ++t) {
           const int r = t * 4 + sub_r;
           const int64_t gm = tile_m0 + q * 32 + r;
@@ -319,9 +356,9 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           float cin[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {1.f, 1.f, 1.f, 1.f};
           const float* ap = (p.epilogue == EPI_RELU_MASK_MUL) ? (p.aux + gm * p.aux_rs + gn) : nullptr;
+          if (pf) { ax[0] = cur[t].x; ax[1] = cur[t].y; ax[2] = cur[t].z; ax[3] = cur[t].w; }
           if (vec) {
             if (p.accumulate) { const float4 t4 = *reinterpret_cast<const float4*>(cp); cin[0] = t4.x; cin[1] = t4.y; cin[2] = t4.z; cin[3] = t4.w; }
-            if (ap) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(ap)); ax[0] = t4.x; ax[1] = t4.y; ax[2] = t4.z; ax[3] = t4.w; }
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -346,6 +383,12 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
         __syncwarp();   // the staging tile is rewritten by the next chunk
+      }
+      if (p.rowsum && nt == 0 && hh == 0) {
+        const uint32_t sum = tmem_ld1(tmem_row + 256u);
+        tmem_ld_wait();
+        const int64_t gm = tile_m0 + q * 32 + lane;
+        if (gm < p.M) atomicAdd(p.rowsum + gm, __uint_as_float(sum));
       }
       tc_fence_before();
       __syncwarp();
@@ -446,20 +489,17 @@ bool tgemm_supported(const GemmArgs& g) {
   return true;
 }
 
-int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s) {
-  if (g.M == 0 || g.N == 0) return CFN_OK;
-  CFN_CHECK_ARG(tgemm_supported(g), "tgemm: operand layout not supported by the TMA path");
+// tile / split / stage geometry of one GEMM
+static void plan_tgemm(const GemmArgs& g, TgParams& p, int& CG, bool& a_mn, bool& b_mn, size_t& smem) {
   static int cg_env = -1;
   if (cg_env < 0) { const char* e = getenv("CFN_TG_CTA_GROUP"); cg_env = e ? atoi(e) : 2; if (cg_env != 1) cg_env = 2; }
-  const bool a_mn = (g.a_cs != 1);
-  const bool b_mn = (g.b_rs != 1);
-  const int CG = (g.M <= 128) ? 1 : cg_env;
-
-  TgParams p{};
+  a_mn = (g.a_cs != 1);
+  b_mn = (g.b_rs != 1);
+  CG = (g.M <= 128) ? 1 : cg_env;
+  p = TgParams{};
   p.C = g.C; p.c_rs = g.c_rs; p.bias = g.bias; p.aux = g.aux; p.aux_rs = g.aux_rs;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.epilogue = g.epilogue; p.accumulate = g.accumulate; p.split_k = g.split_k > 1 ? g.split_k : 1;
-  p.round_out = round_out;
   p.vec_ok = (g.c_rs % 4 == 0) && aligned16(g.C) &&
              (g.epilogue != EPI_RELU_MASK_MUL || (g.aux_rs % 4 == 0 && aligned16(g.aux)));
   int bn = (g.N + 15) / 16 * 16;
@@ -469,7 +509,7 @@ int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s) {
   p.b_blocks = (p.b_rows_cta + 31) / 32;
   const int b_bytes = b_mn ? p.b_blocks * 4096 : ((p.b_rows_cta * 128 + 1023) / 1024) * 1024;
   p.stage_bytes = TG_A_BYTES + b_bytes;
-  int stages = (int)((227 * 1024 - 1024 - TG_STG_BYTES) / p.stage_bytes);
+  int stages = (int)((227 * 1024 - 3072 - TG_STG_BYTES) / p.stage_bytes);
   if (stages > TG_MAX_STAGES) stages = TG_MAX_STAGES;
   p.stages = stages;
   // split-K (wgrad): the caller pre-zeroes C and every split adds its partial sum with fp32 atomics
@@ -481,8 +521,25 @@ int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s) {
   p.m_tiles = (g.M + 128 * CG - 1) / (128 * CG);
   p.n_tiles = (g.N + bn - 1) / bn;
   p.n_work = p.m_tiles * p.n_tiles * p.split_k;
-  size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + TG_STG_BYTES;   // ring | barriers (1 KB) | staging tiles
+  smem = (size_t)p.stages * p.stage_bytes + 3072 + TG_STG_BYTES;   // ring | barriers (1 KB) | ones (2 KB) | staging tiles
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each allocates all 512 TMEM columns
+}
+
+bool tgemm_can_rowsum(const GemmArgs& g) {
+  if (!tgemm_supported(g) || g.split_k <= 1) return false;
+  TgParams p; int CG; bool a_mn, b_mn; size_t smem;
+  plan_tgemm(g, p, CG, a_mn, b_mn, smem);
+  return p.n_work <= num_sms() / CG;
+}
+
+int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s) {
+  if (g.M == 0 || g.N == 0) return CFN_OK;
+  CFN_CHECK_ARG(tgemm_supported(g), "tgemm: operand layout not supported by the TMA path");
+  TgParams p; int CG; bool a_mn, b_mn; size_t smem;
+  plan_tgemm(g, p, CG, a_mn, b_mn, smem);
+  p.round_out = round_out;
+  p.rowsum = g.rowsum;
+  CFN_CHECK_ARG(!g.rowsum || (p.atomic && p.n_work <= num_sms() / CG), "tgemm: rowsum needs one work item per CTA (see tgemm_can_rowsum)");
 
   CUtensorMap tmA, tmB;
   int rc;

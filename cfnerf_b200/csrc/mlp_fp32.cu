@@ -301,8 +301,9 @@ static int colsum(const float* g, int64_t ld, int64_t M, int N, float* out, cuda
 }
 
 // dW(out x in) = G(M x out)^T X(M x in), split over the point dimension, atomically accumulated into zeroed dW
+// db (optional): the bias gradient = column sums of G, fused into the tensor-core GEMM when possible
 static int wgrad(const CfnHandle* h, const float* G, int64_t ldg, int out_f, const float* X, int64_t ldx, int in_f, int64_t M,
-                 float* dW, cudaStream_t s) {
+                 float* dW, float* db, cudaStream_t s) {
   CFN_CUDA(cudaMemsetAsync(dW, 0, (size_t)out_f * in_f * sizeof(float), s));
   GemmArgs g{};
   g.A = G; g.a_rs = 1; g.a_cs = ldg;        // A(m=o, k=pt) = G[pt*ldg + o]
@@ -326,17 +327,26 @@ static int wgrad(const CfnHandle* h, const float* G, int64_t ldg, int out_f, con
   }
   if (split < 2) split = 2;                 // split_k > 1 selects the atomic accumulate path
   g.split_k = (int)split;
+  if (db) {
+    if (h->gemm_tc && tgemm_can_rowsum(g)) {
+      CFN_CUDA(cudaMemsetAsync(db, 0, (size_t)out_f * sizeof(float), s));
+      g.rowsum = db;
+    } else {
+      int rc = colsum(G, ldg, M, out_f, db, s);
+      if (rc) return rc;
+    }
+  }
   return gemm(h, g, 0, s);
 }
 
 // weight gradient of parameter slot `slot` (an nn.Linear whose input rows are X): straight into grads[slot] when the
 // operand view is unpadded, otherwise through the padded scratch and two strided copies that drop the pad columns
 static int wgrad_slot(const CfnHandle* h, int slot, const float* G, int64_t ldg, const float* X, int64_t ldx, int64_t M,
-                      float* dW, float* scratch, cudaStream_t s) {
+                      float* dW, float* db, float* scratch, cudaStream_t s) {
   const ParamSlot& w = h->slots[slot];
   const WView& v = h->wv[slot];
-  if (v.ld == w.cols) return wgrad(h, G, ldg, w.rows, X, ldx, w.cols, M, dW, s);
-  int rc = wgrad(h, G, ldg, w.rows, X, ldx, v.ld, M, scratch, s);
+  if (v.ld == w.cols) return wgrad(h, G, ldg, w.rows, X, ldx, w.cols, M, dW, db, s);
+  int rc = wgrad(h, G, ldg, w.rows, X, ldx, v.ld, M, scratch, db, s);
   if (rc) return rc;
   const int first = v.gap_at < w.cols ? v.gap_at : w.cols;
   if (first > 0)
@@ -415,8 +425,7 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
   // 2. alpha conditioning branch
   {
     // gathered dAmA = GP[:, :3F]^T ha ; bias = colsum
-    if ((rc = wgrad(h, GP, PP, 3 * F, ws + L.ha, ha_n, ha_n, M, dAm, s))) return rc;
-    if ((rc = colsum(GP, PP, M, 3 * F, dAb, s))) return rc;
+    if ((rc = wgrad(h, GP, PP, 3 * F, ws + L.ha, ha_n, ha_n, M, dAm, dAb, s))) return rc;
     scatter_rows_kernel<<<3 * F, 64, 0, s>>>(dAm, dAb, ha_n, h->gatherA_dev, 3 * F, table);
     CFN_LAUNCH_CHECK();
     // g_ha = GP[:, :3F] amA
@@ -425,15 +434,13 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
     g.B = h->amA_g; g.b_rs = ha_n; g.b_cs = 1;
     g.C = gh; g.c_rs = ha_n; g.M = M; g.N = ha_n; g.K = 3 * F; g.split_k = 1;
     if ((rc = gemm(h, g, 1, s))) return rc;
-    if ((rc = wgrad_slot(h, h->s_halpha, gh, ha_n, h7, ld7, M, grads[h->s_halpha], dWp, s))) return rc;
-    if ((rc = colsum(gh, ha_n, M, ha_n, grads[h->s_halpha + 1], s))) return rc;
+    if ((rc = wgrad_slot(h, h->s_halpha, gh, ha_n, h7, ld7, M, grads[h->s_halpha], grads[h->s_halpha + 1], dWp, s))) return rc;
     // g_h7 (unmasked, first contribution) = g_ha W_halpha
     if ((rc = dgrad(h, h->s_halpha, gh, ha_n, 0, W, G1, W, M, nullptr, 0, 0, s))) return rc;
   }
   // 3. rgb conditioning branch
   {
-    if ((rc = wgrad(h, GP + 3 * F, PP, 15 * F, ws + L.hr, hr_n, hr_n, M, dAm, s))) return rc;
-    if ((rc = colsum(GP + 3 * F, PP, M, 15 * F, dAb, s))) return rc;
+    if ((rc = wgrad(h, GP + 3 * F, PP, 15 * F, ws + L.hr, hr_n, hr_n, M, dAm, dAb, s))) return rc;
     scatter_rows_kernel<<<15 * F, 64, 0, s>>>(dAm, dAb, hr_n, h->gatherC_dev, 15 * F, table);
     CFN_LAUNCH_CHECK();
     GemmArgs g{};
@@ -441,16 +448,13 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
     g.B = h->amC_g; g.b_rs = hr_n; g.b_cs = 1;
     g.C = gh; g.c_rs = hr_n; g.M = M; g.N = hr_n; g.K = 15 * F; g.split_k = 1;
     if ((rc = gemm(h, g, 1, s))) return rc;
-    if ((rc = wgrad_slot(h, h->s_hrgb, gh, hr_n, ws + L.v, W / 2, M, grads[h->s_hrgb], dWp, s))) return rc;
-    if ((rc = colsum(gh, hr_n, M, hr_n, grads[h->s_hrgb + 1], s))) return rc;
+    if ((rc = wgrad_slot(h, h->s_hrgb, gh, hr_n, ws + L.v, W / 2, M, grads[h->s_hrgb], grads[h->s_hrgb + 1], dWp, s))) return rc;
     // g_v = (g_hr W_hrgb) * relu'(v)
     if ((rc = dgrad(h, h->s_hrgb, gh, hr_n, 0, W / 2, gv, W / 2, M, ws + L.v, W / 2, 0, s))) return rc;
-    if ((rc = wgrad_slot(h, h->s_views, gv, W / 2, ws + L.V, L.ldv, M, grads[h->s_views], dWp, s))) return rc;
-    if ((rc = colsum(gv, W / 2, M, W / 2, grads[h->s_views + 1], s))) return rc;
+    if ((rc = wgrad_slot(h, h->s_views, gv, W / 2, ws + L.V, L.ldv, M, grads[h->s_views], grads[h->s_views + 1], dWp, s))) return rc;
     // g_feat = g_v W_view[:, :W]   (gamma(d) columns need no gradient)
     if ((rc = dgrad(h, h->s_views, gv, W / 2, 0, W, G2, W, M, nullptr, 0, 0, s))) return rc;
-    if ((rc = wgrad_slot(h, h->s_feat, G2, W, h7, ld7, M, grads[h->s_feat], dWp, s))) return rc;
-    if ((rc = colsum(G2, W, M, W, grads[h->s_feat + 1], s))) return rc;
+    if ((rc = wgrad_slot(h, h->s_feat, G2, W, h7, ld7, M, grads[h->s_feat], grads[h->s_feat + 1], dWp, s))) return rc;
     // g_h7 = (g_h7 + g_feat W_feat) * relu'(h7)
     if ((rc = dgrad(h, h->s_feat, G2, W, 0, W, G1, W, M, h7, ld7, 1, s))) return rc;
   }
@@ -460,8 +464,7 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
   for (int i = D - 1; i >= 0; --i) {
     LayerIO io = trunk_io(h, L, ws, M, i, 1);
     const int slot = h->s_pts(i, 0);
-    if ((rc = wgrad_slot(h, slot, gout, W, io.in, io.ld_in, M, grads[slot], dWp, s))) return rc;
-    if ((rc = colsum(gout, W, M, W, grads[slot + 1], s))) return rc;
+    if ((rc = wgrad_slot(h, slot, gout, W, io.in, io.ld_in, M, grads[slot], grads[slot + 1], dWp, s))) return rc;
     if (i == 0) break;
     // gradient w.r.t. the previous layer's (post-ReLU) output, masked by its ReLU
     LayerIO prev = trunk_io(h, L, ws, M, i - 1, 1);

@@ -311,13 +311,13 @@ def test_render_rays_hierarchical_fp32(cf, dev):
 # ------------------------------------------------------------------------------------------------
 # tensor-core modes (bf16 / fp16 operands, fp32 accumulation)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
 @pytest.mark.parametrize("name", ["render_test_canonical", "render_test_default_init", "render_test_small_wb_lindisp"])
 def test_render_rays_test_mode_tensor_core(cf, dev, name, precision):
     _render_test_case(cf, dev, name, precision, TOL_TC)
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
 def test_network_tensor_core_vs_golden(cf, dev, precision):
     _network_case(cf, dev, "network_canonical", precision, 3e-2, 3e-2)
 
@@ -378,7 +378,8 @@ def test_install_behind_reference_render(cf, dev):
         np.testing.assert_allclose(x.cpu().numpy(), y.numpy(), rtol=2e-6, atol=4e-6)
 
 
-def test_training_steps_track_the_oracle(cf, dev):
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_training_steps_track_the_oracle(cf, dev, precision):
     """PSNR after a fixed number of optimisation steps (north star: within 0.1 dB of the reference path).  Same
     weights, rays, targets, noise draws and Adam on both sides; the CUDA path on the GPU, the oracle (autograd on the
     CPU restatement that is pinned to the reference's own gradients) on the host."""
@@ -406,7 +407,7 @@ def test_training_steps_track_the_oracle(cf, dev):
         lr_["loss"].backward()
         opt_ref.step()
         o2 = cf.render_rays(rays.to(dev), net, None, 128, True, False, K_samples=cfg.K, perturb=1., raw_noise_std=1.,
-                            t_rand=t_rand.to(dev), eps_alpha=ea.to(dev), eps_rgb=er.to(dev))
+                            t_rand=t_rand.to(dev), eps_alpha=ea.to(dev), eps_rgb=er.to(dev), precision=precision)
         l2 = cf.kde_nll_loss(o2["rgb_map"], target.to(dev), o2["loss_entropy"], cfg.K, 0.01)
         opt.zero_grad()
         l2["loss"].backward()
@@ -417,7 +418,9 @@ def test_training_steps_track_the_oracle(cf, dev):
     # the weights themselves stayed together
     sd = net.state_dict()
     worst = max((sd[k].cpu() - p_ref[k].detach()).abs().max().item() for k in live)
-    assert worst <= 5e-4, worst
+    # Adam's first steps move every weight by ~lr * sign(grad): where a tf32-rounded gradient changes sign the weights
+    # part by up to 2 * lr per step, which the fp32 mode never does
+    assert worst <= (5e-4 if precision == "fp32" else 2 * 5e-4 * steps + 5e-4), worst
 
 
 # ------------------------------------------------------------------------------------------------
@@ -628,3 +631,102 @@ def test_large_ragged_batch_tensor_core_vs_fp32(cf, dev):
     for k in ("rgb_map", "depth_map"):
         assert (a[k] - b[k]).abs().max().item() <= TOL_TC, k
     assert torch.isfinite(a["disp_map"]).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# the TF32 tensor-core GEMM (gemm_tf32.cu) and the training path built on it
+# ------------------------------------------------------------------------------------------------
+def _tf32_round(x):
+    i = x.view(torch.int32)
+    return ((i + 0xFFF + ((i >> 13) & 1)) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,kw", [
+    (128, 16, 32, False, False, {}), (300, 100, 72, False, False, {}), (5000, 512, 576, False, False, {}),
+    (3000, 512, 512, False, False, dict(epi="relu", bias=True)), (3000, 72, 64, False, False, dict(epi="tanh_mask", bias=True)),
+    (700, 64, 12, False, True, {}), (3000, 512, 512, False, True, dict(epi="relu_mask_mul")),
+    (3000, 512, 512, False, True, dict(epi="relu_mask_mul", acc=True)), (1001, 540, 256, False, True, {}),
+    (512, 512, 40000, True, True, dict(split=37)), (512, 576, 40000, True, True, dict(split=24)),
+    (64, 512, 40000, True, True, dict(split=148)), (12, 64, 3000, True, True, dict(split=5)), (256, 540, 1000, True, True, {}),
+    (256, 128, 64, True, False, {}),
+])
+def test_tf32_tensor_core_gemm_vs_torch(cf, dev, M, N, K, a_mn, b_mn, kw):
+    """Every operand-major combination the network stage issues (forward K/K, dgrad K/N, wgrad M/N), ragged edges, K
+    tails, fused epilogues and split-K.  Operands are pre-rounded to tf32, so the products are exact and the only
+    error left is the fp32 accumulation order."""
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    rnd = lambda *sh: _tf32_round(torch.randn(*sh, generator=g)).to(dev)
+    A = rnd(K, M).t() if a_mn else rnd(M, K)
+    B = rnd(K, N) if b_mn else rnd(N, K).t()
+    epi = kw.get("epi", "none")
+    bias = torch.randn(N, generator=g).to(dev) if kw.get("bias") else None
+    aux = None
+    if epi == "relu_mask_mul":
+        aux = torch.randn(M, N, generator=g).to(dev)
+    if epi == "tanh_mask":
+        aux = (torch.rand(N, generator=g) > 0.5).float().to(dev)
+    ref = A.double() @ B.double()
+    out = None
+    if bias is not None:
+        ref = ref + bias.double()
+    if kw.get("acc"):
+        out = torch.randn(M, N, generator=g).to(dev)
+        ref = ref + out.double()
+    if epi == "relu":
+        ref = ref.clamp_min(0)
+    if epi == "tanh_mask":
+        ref = torch.where(aux.bool()[None, :], torch.tanh(ref), ref)
+    if epi == "relu_mask_mul":
+        ref = torch.where(aux > 0, ref, torch.zeros_like(ref))
+    out0 = None if out is None else out.clone()
+    C = cf.gemm(A, B, engine="tf32", bias=bias, epilogue=epi, aux=aux, out=out, accumulate=bool(kw.get("acc")),
+                split_k=kw.get("split", 1))
+    scale = max(1.0, ref.abs().max().item())
+    assert torch.isfinite(C).all()
+    assert (C.double() - ref).abs().max().item() <= 2e-5 * scale     # fp32 accumulation of K exact products
+    # and the CUDA-core engine agrees on the same inputs
+    C0 = cf.gemm(A, B, engine="fp32", bias=bias, epilogue=epi, aux=aux, out=out0, accumulate=bool(kw.get("acc")),
+                 split_k=kw.get("split", 1))
+    assert (C0.double() - ref).abs().max().item() <= 2e-5 * scale
+
+
+def test_tf32_gemm_rejects_unaligned_operands(cf, dev):
+    A = torch.randn(64, 63, device=dev)          # row stride 63 floats: not a multiple of 16 bytes
+    B = torch.randn(63, 32, device=dev)
+    with pytest.raises(Exception, match="not supported"):
+        cf.gemm(A, B, engine="tf32")
+    assert torch.allclose(cf.gemm(A, B, engine="fp32"), A @ B, atol=1e-4)
+
+
+@pytest.mark.parametrize("kw,B", [(dict(), 48), (dict(W=256, K=64, h_alpha=32), 33), (dict(D=7, W=128, F=3), 17)])
+def test_training_step_tensor_core_vs_fp32_path(cf, dev, kw, B):
+    """The tf32 tensor-core training path against the fp32 check path of the same library on the same inputs: forward
+    maps at the 2e-3 bar, loss, and every parameter gradient (relative L2; the early trunk layers see the rounding of
+    the whole dgrad chain).  F=3 makes the flow-record width (54) unaligned: those GEMMs fall back to the CUDA cores."""
+    cfg = O.CfnConfig(**kw)
+    p = O.make_params(cfg, 3, "lively")
+    sa, sr = O.make_latents(cfg, 3)
+    rays = O.synthetic_rays(B, 4).to(dev)
+    g = torch.Generator().manual_seed(7)
+    target = torch.rand(B, 3, generator=g).to(dev)
+    t_rand = torch.rand(B, 128, generator=g).to(dev)
+    ea, er = torch.randn(cfg.K, 1, generator=g).to(dev), torch.randn(cfg.K, 3, generator=g).to(dev)
+    res = {}
+    for prec in ("fp32", "tf32"):
+        net = make_net(cf, cfg, p, sa, sr, dev)
+        out = cf.render_rays(rays, net, None, 128, True, False, perturb=1., raw_noise_std=1., t_rand=t_rand, eps_alpha=ea,
+                             eps_rgb=er, precision=prec)
+        l = cf.kde_nll_loss(out["rgb_map"], target, out["loss_entropy"], cfg.K, 0.01)
+        net.zero_grad()
+        l["loss"].backward()
+        res[prec] = (out, float(l["loss"]), {n: q.grad.clone() for n, q in net.named_parameters() if q.grad is not None})
+    (oa, la, ga), (ob, lb, gb) = res["fp32"], res["tf32"]
+    for k in ("rgb_map", "depth_map"):
+        assert (oa[k] - ob[k]).abs().max().item() <= TOL_TC, k
+    assert abs(la - lb) <= 2e-3 * max(1.0, abs(la))
+    assert set(ga) == set(gb)
+    for n in ga:
+        na = ga[n].double().norm().item()
+        err = (ga[n].double() - gb[n].double()).norm().item()
+        assert torch.isfinite(gb[n]).all(), n
+        assert err <= 8e-2 * na + 1e-9, f"grad {n}: |g| {na:.3e}, |diff| {err:.3e}"
