@@ -177,6 +177,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=32768, help="rays per render_rays call (bounds the flow-parameter buffer)")
     ap.add_argument("--cpu-rays", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[2])")
+    ap.add_argument("--train-rays", type=int, default=4096, help="rays per GPU per optimisation step")
+    ap.add_argument("--train-precision", default="tf32", choices=["tf32", "fp32"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -283,10 +286,36 @@ def main():
     h2d = rays_host.numel() * 4
     d2h = sum(v.numel() * 4 for v in cat.values())
 
-    t = torch.tensor([ms, e2e_ms, k1_ms], dtype=torch.float64, device=dev)
+    # ---- the other half of the metric: one optimisation step (BASELINE.json configs[2]) ----
+    # render (train mode, saved activations) -> K-mean + KDE-NLL + 0.01 * entropy -> backward (flow/composite backward,
+    # dgrad chain, split-K wgrad) -> one all-reduce of the flat gradient bucket (N > 1) -> Adam.  Weak scaling like the
+    # render leg: --train-rays rays per GPU.  Runs last (it moves the weights).
+    train_ms = 0.0
+    if not args.no_train:
+        from cfnerf_b200 import dist as D
+        tparams = [q for n, q in net.named_parameters()
+                   if not n.startswith("alpha_linear") and not n.startswith("alpha_std_linear")]
+        opt = torch.optim.Adam(tparams, lr=5e-4, betas=(0.9, 0.999))
+        bucket = D.GradBucket(tparams) if world > 1 else None
+        gt = torch.Generator().manual_seed(100 + rank)
+        t_rays = rays_dev[torch.randperm(B, generator=gt)[:args.train_rays].to(dev)].contiguous()
+        t_target = torch.rand(t_rays.shape[0], 3, generator=gt).to(dev)
+        torch.manual_seed(100 + rank)
+        for _ in range(3):
+            D.train_step(net, opt, t_rays, t_target, bucket, precision=args.train_precision)
+        barrier()
+        te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        te0.record()
+        for _ in range(args.steps):
+            t_out = D.train_step(net, opt, t_rays, t_target, bucket, precision=args.train_precision)
+        te1.record()
+        barrier()
+        train_ms = te0.elapsed_time(te1)
+
+    t = torch.tensor([ms, e2e_ms, k1_ms, train_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, k1_ms = [float(x) for x in t.cpu()]
+    ms, e2e_ms, k1_ms, train_ms = [float(x) for x in t.cpu()]
 
     if rank == 0:
         peaks, which = measured_peaks()
@@ -316,6 +345,15 @@ def main():
                          "k1_share_of_step": k1_ms / ms, "points_per_launch": pts_per_launch},
             "clocks": sampler.summary(),
         }
+        if not args.no_train:
+            n_t = t_rays.shape[0]
+            step_s = train_ms * 1e-3 / args.steps
+            line["train_step"] = {
+                "value": n_t * world / step_s, "unit": "rays/s", "ms_per_step": step_s * 1e3, "rays_per_gpu": n_t,
+                "precision": args.train_precision, "loss": float(t_out["loss"]),
+                "achieved_tflops_per_gpu": n_t * N_SAMPLES * FLOP_PER_POINT * 3 / step_s / 1e12,
+                "note": "forward + backward + Adam through cfnerf_b200.dist.train_step; GEMMs = TMA-fed tcgen05 kind::tf32 "
+                        "(fp32 storage) when precision is tf32, CUDA-core fp32 FMA when fp32; flops = 3 x forward GEMM flops"}
         if not args.no_cpu_baseline:
             v, cores = cpu_reference_rays_per_s(args.cpu_rays, 2)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",

@@ -28,7 +28,7 @@ from .engine import Engine, _f32c, _ptr, _stream, _unwrap, engine_for
 DEFAULT_PRECISION = "fp16"
 # Training (forward with saved activations + backward) runs layer by layer: "fp32" = CUDA-core FMA GEMMs (the exact
 # check mode), "tf32" / "bf16" / "fp16" = tcgen05 kind::tf32 GEMMs over fp32 storage with tf32-rounded operands.
-DEFAULT_TRAIN_PRECISION = "fp32"
+DEFAULT_TRAIN_PRECISION = "tf32"
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -343,12 +343,15 @@ def render_image(H, W, focal, c2w, network_fn, near=0., far=1., ndc=False, chunk
     return [allr[k] for k in ex] + [{k: v for k, v in allr.items() if k not in ex}]
 
 
-def install(ref_module, precision: str | None = None):
+def install(ref_module, precision: str | None = None, train_precision: str | None = None):
     """Rebind the reference's module-global names: `batchify_rays` looks `render_rays` up by global
-    name (main:93) and `render_rays` looks `raw2outputs` up the same way (main:540)."""
-    global DEFAULT_PRECISION
+    name (main:93) and `render_rays` looks `raw2outputs` up the same way (main:540).  `precision` selects the render
+    mode ("fp16" default, "bf16", "tf32", "fp32"), `train_precision` the training mode ("tf32" default, "fp32")."""
+    global DEFAULT_PRECISION, DEFAULT_TRAIN_PRECISION
     if precision is not None:
         DEFAULT_PRECISION = precision
+    if train_precision is not None:
+        DEFAULT_TRAIN_PRECISION = train_precision
     ref_module.render_rays = render_rays
     ref_module.raw2outputs = raw2outputs
     return ref_module

@@ -251,7 +251,7 @@ def test_render_rays_train_mode_and_gradients(cf, dev, name):
     rays = T(g["in_rays"]).to(dev)
     out = cf.render_rays(rays, net, None, 128, True, False, K_samples=cfg.K, perturb=1., raw_noise_std=1.,
                          t_rand=T(g["in_t_rand"]).to(dev), eps_alpha=T(g["in_eps_alpha"]).to(dev),
-                         eps_rgb=T(g["in_eps_rgb"]).to(dev))
+                         eps_rgb=T(g["in_eps_rgb"]).to(dev), precision="fp32")
     B = rays.shape[0]
     assert out["loss_entropy"].shape == (B * 128, cfg.K, 1) and out["pts"].shape == (B, 128, 3)
     for k in ("rgb_map", "depth_map"):
