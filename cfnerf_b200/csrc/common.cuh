@@ -97,6 +97,11 @@ struct GemmArgs {
   int split_k;                          // >1: atomicAdd partial sums into a pre-zeroed C (no bias/epilogue)
   float* rowsum;                        // tensor-core engine, split_k > 1 only: rowsum[m] += sum_k A(m,k) (pre-zeroed; the bias
                                         // gradient of a wgrad, produced by one extra N=16 MMA against a tile of ones)
+  // tensor-core engine only: ReLU derivative as a bit mask, one word per row and 32 output columns (bits_ld words/row).
+  // EPI_RELU writes it (mask_out); EPI_RELU_MASK_MUL reads it (aux_bits) instead of the fp32 aux, 32x fewer bytes.
+  uint32_t* mask_out;
+  const uint32_t* aux_bits;
+  int64_t bits_ld;
 };
 int launch_sgemm(const GemmArgs& g, cudaStream_t s);
 // same contract on the tensor cores (tcgen05.mma kind::tf32, TMA-fed; gemm_tf32.cu).  round_out: round the stored

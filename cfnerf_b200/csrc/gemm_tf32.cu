@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <math.h>
 
 #include "common.cuh"
 
@@ -46,6 +47,9 @@ struct TgParams {
   int64_t n_work;      // m_tiles * n_tiles * split_k
   int stages; int stage_bytes;
   float* rowsum;       // optional (atomic GEMMs): rowsum[m] += sum_k A(m,k)
+  uint32_t* mask_out;  // optional (EPI_RELU): bit n of word [m][n / 32] = output (m, n) > 0
+  const uint32_t* aux_bits;   // optional (EPI_RELU_MASK_MUL): the same words, read instead of the fp32 aux
+  int64_t bits_ld;     // words per row of either
 };
 
 // ---- PTX wrappers (same idioms as mlp_tc.cu) -----------------------------------------------------------
@@ -297,89 +301,117 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int n_tile0 = nt * p.bn;
       int n_cols = p.N - n_tile0; if (n_cols > p.bn) n_cols = p.bn;
       const int n_chunks = (n_cols + 31) / 32;
-      // dgrad reads one mask element per output element: the 8 row segments of a chunk are requested BEFORE the
-      // accumulator is waited for (and the next chunk's while the current one is processed), otherwise every one of
-      // the 32 row groups of a tile would pay a full HBM round trip in sequence
-      const bool pf = (p.epilogue == EPI_RELU_MASK_MUL) && p.vec_ok && !p.atomic;
-      float4 pre[8];
-      auto issue_pre = [&](int c) {
-        const int gnp = n_tile0 + c * 32 + c4;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int64_t gmp = tile_m0 + q * 32 + t * 4 + sub_r;
-          pre[t] = (gmp < p.M && gnp + 3 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.aux + gmp * p.aux_rs + gnp))
-                                                : make_float4(1.f, 1.f, 1.f, 1.f);
-        }
+      // dgrad needs relu'(h) per output element.  The fast form is the BIT mask the forward GEMM wrote (one 32-bit word
+      // per row and 32-column chunk): lane j holds the word of row j of this warp's 32 rows, the words of the next two
+      // chunks are requested before they are needed (the first two before the accumulator is even waited for), so no
+      // HBM round trip is exposed.  The fp32 form (aux = the saved activations) is kept for callers without bit masks.
+      // The loops below are deliberately NOT unrolled: with every epilogue flavour inlined, an unrolled body ran out of
+      // the instruction cache (a quarter of all stall samples were instruction fetches) and became the critical path.
+      const bool use_bits = (p.epilogue == EPI_RELU_MASK_MUL) && p.aux_bits != nullptr;
+      uint32_t pb1 = 0, pb2 = 0;
+      auto load_bits = [&](int c) -> uint32_t {
+        const int64_t gmp = tile_m0 + q * 32 + lane;
+        return (gmp < p.M) ? __ldg(p.aux_bits + gmp * p.bits_ld + ((n_tile0 + c * 32) >> 5)) : 0u;
       };
-      if (pf && hh < n_chunks) issue_pre(hh);
+      if (use_bits) {
+        if (hh < n_chunks) pb1 = load_bits(hh);
+        if (hh + 2 < n_chunks) pb2 = load_bits(hh + 2);
+      }
       mbar_wait(bar_local(&bars->acc_full[buf]), (it >> 1) & 1u);
       tc_fence_after();
+      const float relu_lo = (p.epilogue == EPI_RELU) ? 0.f : -INFINITY;
+#pragma unroll 1
       for (int c = hh; c < n_chunks; c += 2) {
         // phase 1: this warp's 32 x 32 accumulator block, TMEM -> registers (thread = row) -> padded shared-memory tile
-        uint32_t v[32];
-        tmem_ld32(tmem_row + buf * 256u + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
+        {
+          uint32_t v[32];
+          tmem_ld32(tmem_row + buf * 256u + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          *reinterpret_cast<float4*>(stg + lane * TG_STG_LD + 4 * u) =
-              make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<float4*>(stg + lane * TG_STG_LD + 4 * u) =
+                make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
+        }
         __syncwarp();
-        float4 cur[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) cur[t] = pre[t];
-        if (pf && c + 2 < n_chunks) issue_pre(c + 2);
+        const uint32_t curb = pb1;
+        if (use_bits) {
+          pb1 = pb2;
+          if (c + 4 < n_chunks) pb2 = load_bits(c + 4);
+        }
         // phase 2: 8 lanes per row, 4 rows per instruction: every global access of the warp is 4 full 128-byte lines
         const int gn = n_tile0 + c * 32 + c4;
         const bool vec = p.vec_ok && (gn + 3 < p.N);
-        float b4[4] = {0.f, 0.f, 0.f, 0.f}, f4[4] = {0.f, 0.f, 0.f, 0.f};
+        float b4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t tanh_nib = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (gn + i < p.N) {
             if (p.bias) b4[i] = __ldg(p.bias + gn + i);
-            if (p.epilogue == EPI_TANH_MASK) f4[i] = __ldg(p.aux + gn + i);
+            if (p.epilogue == EPI_TANH_MASK && __ldg(p.aux + gn + i) != 0.f) tanh_nib |= 1u << i;
           }
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < 8; ++t) {
           const int r = t * 4 + sub_r;
           const int64_t gm = tile_m0 + q * 32 + r;
           const float4 a4 = *reinterpret_cast<const float4*>(stg + r * TG_STG_LD + c4);
-          if (gm >= p.M || gn >= p.N) continue;
+          const uint32_t rowbits = __shfl_sync(0xffffffffu, curb, r);   // every lane takes part
+          const bool ok = gm < p.M && gn < p.N;
           float x[4] = {a4.x, a4.y, a4.z, a4.w};
           float* cp = p.C + gm * p.c_rs + gn;
           if (p.atomic) {
-            if (vec) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(cp), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
-            else {
+            if (ok) {
+              if (vec) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(cp), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+              else {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) if (gn + i < p.N) atomicAdd(cp + i, x[i]);
+                for (int i = 0; i < 4; ++i) if (gn + i < p.N) atomicAdd(cp + i, x[i]);
+              }
             }
             continue;
           }
-          float cin[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {1.f, 1.f, 1.f, 1.f};
-          const float* ap = (p.epilogue == EPI_RELU_MASK_MUL) ? (p.aux + gm * p.aux_rs + gn) : nullptr;
-          if (pf) { ax[0] = cur[t].x; ax[1] = cur[t].y; ax[2] = cur[t].z; ax[3] = cur[t].w; }
-          if (vec) {
-            if (p.accumulate) { const float4 t4 = *reinterpret_cast<const float4*>(cp); cin[0] = t4.x; cin[1] = t4.y; cin[2] = t4.z; cin[3] = t4.w; }
-          } else {
+          uint32_t keep = 0xFu;                       // relu'(h) of the four columns
+          if (use_bits) keep = rowbits >> (4 * (lane & 7));
+          else if (p.epilogue == EPI_RELU_MASK_MUL && ok) {
+            const float* ap = p.aux + gm * p.aux_rs + gn;
+            keep = 0;
+            if (vec) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(ap));
+              keep = (t4.x > 0.f ? 1u : 0u) | (t4.y > 0.f ? 2u : 0u) | (t4.z > 0.f ? 4u : 0u) | (t4.w > 0.f ? 8u : 0u);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (gn + i < p.N) {
-                if (p.accumulate) cin[i] = cp[i];
-                if (ap) ax[i] = __ldg(ap + i);
-              }
+              for (int i = 0; i < 4; ++i) if (gn + i < p.N && __ldg(ap + i) > 0.f) keep |= 1u << i;
+            }
           }
+          if (p.accumulate && ok) {
+            if (vec) { const float4 t4 = *reinterpret_cast<const float4*>(cp); x[0] += t4.x; x[1] += t4.y; x[2] += t4.z; x[3] += t4.w; }
+            else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) if (gn + i < p.N) x[i] += cp[i];
+            }
+          }
+          uint32_t pos = 0;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            float y = x[i] + b4[i] + cin[i];
-            if (p.epilogue == EPI_RELU) y = fmaxf(y, 0.f);
-            else if (p.epilogue == EPI_TANH_MASK) { if (f4[i] != 0.f) y = tanhf(y); }
-            else if (p.epilogue == EPI_RELU_MASK_MUL) { if (!(ax[i] > 0.f)) y = 0.f; }
+            float y = fmaxf(x[i] + b4[i], relu_lo);
+            if (tanh_nib & (1u << i)) y = tanhf(y);
+            if (!(keep & (1u << i))) y = 0.f;
             if (p.round_out) y = round_tf32(y);
+            if (y > 0.f && gn + i < p.N) pos |= 1u << i;
             x[i] = y;
           }
-          if (vec) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
-          else {
+          if (ok) {
+            if (vec) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+            else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) if (gn + i < p.N) cp[i] = x[i];
+              for (int i = 0; i < 4; ++i) if (gn + i < p.N) cp[i] = x[i];
+            }
+          }
+          if (p.mask_out) {
+            // relu'(y) of this row's 32 columns packed into one word by the 8 lanes that hold them (all lanes shuffle)
+            uint32_t word = (ok ? pos : 0u) << (4 * (lane & 7));
+            word |= __shfl_xor_sync(0xffffffffu, word, 1);
+            word |= __shfl_xor_sync(0xffffffffu, word, 2);
+            word |= __shfl_xor_sync(0xffffffffu, word, 4);
+            if ((lane & 7) == 0 && gm < p.M) p.mask_out[gm * p.bits_ld + ((n_tile0 + c * 32) >> 5)] = word;
           }
         }
         __syncwarp();   // the staging tile is rewritten by the next chunk
@@ -539,6 +571,9 @@ int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s) {
   plan_tgemm(g, p, CG, a_mn, b_mn, smem);
   p.round_out = round_out;
   p.rowsum = g.rowsum;
+  p.mask_out = (g.epilogue == EPI_RELU && !p.atomic) ? g.mask_out : nullptr;
+  p.aux_bits = (g.epilogue == EPI_RELU_MASK_MUL) ? g.aux_bits : nullptr;
+  p.bits_ld = g.bits_ld;
   CFN_CHECK_ARG(!g.rowsum || (p.atomic && p.n_work <= num_sms() / CG), "tgemm: rowsum needs one work item per CTA (see tgemm_can_rowsum)");
 
   CUtensorMap tmA, tmB;

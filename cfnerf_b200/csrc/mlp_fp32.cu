@@ -16,9 +16,13 @@ struct Fp32Layout {
   int ld5, ldv, ldg;
   int64_t X5, V, H, v, ha, hr;            // forward
   int64_t P, GP, G1, G2, gv, gh, dAm, dWp;  // saved outputs / backward scratch
+  int64_t MB, mbv; int bw, bwv;             // ReLU bit masks of the trunk layers / the view layer (words per row)
   int nH;
   int64_t total;
 };
+
+// the tensor-core engine carries relu'(h) from the forward to the dgrad GEMMs as bit masks (needs every ReLU layer on it)
+static bool use_bits(const CfnHandle* h) { return h->gemm_tc && h->cfg.W % 8 == 0; }
 
 static Fp32Layout make_layout(const CfnHandle* h, int64_t M, int save) {
   Fp32Layout L;
@@ -35,7 +39,8 @@ static Fp32Layout make_layout(const CfnHandle* h, int64_t M, int save) {
   L.v = take(M * (W / 2));
   L.ha = take(M * h->cfg.h_alpha);
   L.hr = take(M * h->cfg.h_rgb);
-  L.P = L.GP = L.G1 = L.G2 = L.gv = L.gh = L.dAm = L.dWp = 0;
+  L.P = L.GP = L.G1 = L.G2 = L.gv = L.gh = L.dAm = L.dWp = L.MB = L.mbv = 0;
+  L.bw = (W + 31) / 32; L.bwv = (W / 2 + 31) / 32;
   if (save) {
     L.P = take(M * h->PP);
     L.GP = take(M * h->PP);
@@ -46,6 +51,10 @@ static Fp32Layout make_layout(const CfnHandle* h, int64_t M, int save) {
     L.gh = take(M * hm);
     L.dAm = take((int64_t)h->PP * (hm + 1));
     L.dWp = take((int64_t)W * (h->gp + W + 4));   // padded weight gradient of the odd-width layers
+    if (use_bits(h)) {
+      L.MB = take((int64_t)h->cfg.D * M * L.bw);
+      L.mbv = take(M * L.bwv);
+    }
   }
   L.total = o;
   return L;
@@ -74,33 +83,52 @@ __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
 }
 
-// n_pos / n_dir: padded widths (pad columns are written as zeros); round: store tf32-rounded values
-__global__ void encode_kernel(const float* __restrict__ rays, const float* __restrict__ z_vals,
-                              const float* __restrict__ pts, const float* __restrict__ viewdirs, int64_t M, int N,
-                              int L_pos, int L_dir, float* __restrict__ X5, int ld5, float* __restrict__ Vd, int ldv,
-                              int n_pos, int n_dir, int round) {
-  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  const int64_t b = m / N;
-  float px, py, pz;
-  if (pts) {
-    px = pts[m * 3 + 0]; py = pts[m * 3 + 1]; pz = pts[m * 3 + 2];
-  } else {
-    const float* r = rays + b * 11;
-    const float z = z_vals[m];
-    // pts = rays_o + rays_d * z (main:534): separate multiply and add, as torch evaluates it
-    px = __fadd_rn(r[0], __fmul_rn(r[3], z));
-    py = __fadd_rn(r[1], __fmul_rn(r[4], z));
-    pz = __fadd_rn(r[2], __fmul_rn(r[5], z));
+// n_pos / n_dir: padded widths (pad columns are written as zeros); round: store tf32-rounded values.
+// One thread encodes one point into shared memory; the block then writes the rows out with consecutive lanes on
+// consecutive columns (the rows are 2304 bytes apart in X5: per-thread row stores would touch 32 lines per instruction).
+constexpr int ENC_PTS = 128, ENC_MAXW = 104;   // up to multires 16: 3 + 6*16 = 99 (+ pad)
+__global__ void __launch_bounds__(ENC_PTS)
+encode_kernel(const float* __restrict__ rays, const float* __restrict__ z_vals, const float* __restrict__ pts,
+              const float* __restrict__ viewdirs, int64_t M, int N, int L_pos, int L_dir, float* __restrict__ X5, int ld5,
+              float* __restrict__ Vd, int ldv, int n_pos, int n_dir, int round) {
+  extern __shared__ float enc_smem[];
+  const int lp = n_pos | 1, ldd = n_dir | 1;            // odd row strides: conflict-free per-thread rows
+  float* sp = enc_smem;
+  float* sd = enc_smem + ENC_PTS * lp;
+  const int64_t m0 = (int64_t)blockIdx.x * ENC_PTS;
+  const int64_t m = m0 + threadIdx.x;
+  if (m < M) {
+    const int64_t b = m / N;
+    float px, py, pz;
+    if (pts) {
+      px = pts[m * 3 + 0]; py = pts[m * 3 + 1]; pz = pts[m * 3 + 2];
+    } else {
+      const float* r = rays + b * 11;
+      const float z = z_vals[m];
+      // pts = rays_o + rays_d * z (main:534): separate multiply and add, as torch evaluates it
+      px = __fadd_rn(r[0], __fmul_rn(r[3], z));
+      py = __fadd_rn(r[1], __fmul_rn(r[4], z));
+      pz = __fadd_rn(r[2], __fmul_rn(r[5], z));
+    }
+    float* rp = sp + threadIdx.x * lp;
+    float* rd = sd + threadIdx.x * ldd;
+    embed3(px, py, pz, L_pos, rp);
+    const float* vd = viewdirs ? (viewdirs + b * 3) : (rays + b * 11 + 8);
+    embed3(vd[0], vd[1], vd[2], L_dir, rd);
+    for (int c = 3 + 6 * L_pos; c < n_pos; ++c) rp[c] = 0.f;
+    for (int c = 3 + 6 * L_dir; c < n_dir; ++c) rd[c] = 0.f;
   }
-  embed3(px, py, pz, L_pos, X5 + m * ld5);
-  const float* vd = viewdirs ? (viewdirs + b * 3) : (rays + b * 11 + 8);
-  embed3(vd[0], vd[1], vd[2], L_dir, Vd + m * ldv);
-  for (int c = 3 + 6 * L_pos; c < n_pos; ++c) X5[m * ld5 + c] = 0.f;
-  for (int c = 3 + 6 * L_dir; c < n_dir; ++c) Vd[m * ldv + c] = 0.f;
-  if (round) {
-    for (int c = 0; c < 3 + 6 * L_pos; ++c) X5[m * ld5 + c] = round_tf32(X5[m * ld5 + c]);
-    for (int c = 0; c < 3 + 6 * L_dir; ++c) Vd[m * ldv + c] = round_tf32(Vd[m * ldv + c]);
+  __syncthreads();
+  const int rows = (int)min((int64_t)ENC_PTS, M - m0);
+  for (int i = threadIdx.x; i < rows * n_pos; i += ENC_PTS) {
+    const int r = i / n_pos, c = i - r * n_pos;
+    const float v = sp[r * lp + c];
+    X5[(m0 + r) * ld5 + c] = round ? round_tf32(v) : v;
+  }
+  for (int i = threadIdx.x; i < rows * n_dir; i += ENC_PTS) {
+    const int r = i / n_dir, c = i - r * n_dir;
+    const float v = sd[r * ldd + c];
+    Vd[(m0 + r) * ldv + c] = round ? round_tf32(v) : v;
   }
 }
 
@@ -194,7 +222,7 @@ static inline const float* Wp(const CfnHandle* h, int slot) { return h->w32 + h-
 
 // Y(M x out) = epi(X(M x in) W^T + b) for an nn.Linear stored (out, in) row-major
 static int linear_fwd(const CfnHandle* h, int slot, const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t M,
-                      int epi, const float* aux, cudaStream_t s) {
+                      int epi, const float* aux, cudaStream_t s, uint32_t* mask_out = nullptr, int bits_ld = 0) {
   const ParamSlot& w = h->slots[slot];
   const WView& v = h->wv[slot];
   GemmArgs g{};
@@ -205,6 +233,8 @@ static int linear_fwd(const CfnHandle* h, int slot, const float* X, int64_t ldx,
   g.aux = aux; g.aux_rs = 0;
   g.M = M; g.N = w.rows; g.K = v.ld;
   g.epilogue = epi; g.accumulate = 0; g.split_k = 1;
+  g.mask_out = mask_out; g.bits_ld = bits_ld;
+  if (mask_out) CFN_CHECK_ARG(tgemm_supported(g), "linear_fwd: ReLU bit masks need the tensor-core engine");
   return gemm(h, g, 1, s);
 }
 
@@ -230,15 +260,22 @@ int fp32_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const
   const int64_t M = B * N;
   const int W = h->cfg.W, D = h->cfg.D, F = h->cfg.F;
   Fp32Layout L = make_layout(h, M, save);
-  encode_kernel<<<(unsigned)((M + 127) / 128), 128, 0, s>>>(rays, z_vals, pts, viewdirs, M, N, h->cfg.L_pos,
-                                                            h->cfg.L_dir, ws + L.X5, L.ld5, ws + L.V + W, L.ldv, h->gp,
-                                                            h->gd, h->gemm_tc);
+  const size_t enc_smem = (size_t)ENC_PTS * ((h->gp | 1) + (h->gd | 1)) * sizeof(float);
+  static bool enc_attr = false;
+  if (!enc_attr) {
+    CFN_CUDA(cudaFuncSetAttribute((const void*)encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ENC_PTS * ENC_MAXW * 4));
+    enc_attr = true;
+  }
+  encode_kernel<<<(unsigned)((M + ENC_PTS - 1) / ENC_PTS), ENC_PTS, enc_smem, s>>>(
+      rays, z_vals, pts, viewdirs, M, N, h->cfg.L_pos, h->cfg.L_dir, ws + L.X5, L.ld5, ws + L.V + W, L.ldv, h->gp, h->gd,
+      h->gemm_tc);
   CFN_LAUNCH_CHECK();
   int rc;
   LayerIO last{};
   for (int i = 0; i < D; ++i) {
     LayerIO io = trunk_io(h, L, ws, M, i, save);
-    if ((rc = linear_fwd(h, h->s_pts(i, 0), io.in, io.ld_in, io.out, io.ld_out, M, EPI_RELU, nullptr, s))) return rc;
+    uint32_t* mb = (save && use_bits(h)) ? reinterpret_cast<uint32_t*>(ws + L.MB) + (int64_t)i * M * L.bw : nullptr;
+    if ((rc = linear_fwd(h, h->s_pts(i, 0), io.in, io.ld_in, io.out, io.ld_out, M, EPI_RELU, nullptr, s, mb, L.bw))) return rc;
     last = io;
   }
   const float* h7 = last.out;
@@ -246,7 +283,8 @@ int fp32_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const
   // heads (models.py:175-182)
   if ((rc = linear_fwd(h, h->s_halpha, h7, ld7, ws + L.ha, h->cfg.h_alpha, M, EPI_NONE, nullptr, s))) return rc;
   if ((rc = linear_fwd(h, h->s_feat, h7, ld7, ws + L.V, L.ldv, M, EPI_NONE, nullptr, s))) return rc;
-  if ((rc = linear_fwd(h, h->s_views, ws + L.V, L.ldv, ws + L.v, W / 2, M, EPI_RELU, nullptr, s))) return rc;
+  if ((rc = linear_fwd(h, h->s_views, ws + L.V, L.ldv, ws + L.v, W / 2, M, EPI_RELU, nullptr, s,
+                       (save && use_bits(h)) ? reinterpret_cast<uint32_t*>(ws + L.mbv) : nullptr, L.bwv))) return rc;
   if ((rc = linear_fwd(h, h->s_hrgb, ws + L.v, W / 2, ws + L.hr, h->cfg.h_rgb, M, EPI_NONE, nullptr, s))) return rc;
   // amortised flow parameters, once per point (models.py:358-385)
   {
@@ -359,7 +397,8 @@ static int wgrad_slot(const CfnHandle* h, int slot, const float* G, int64_t ldg,
 
 // Gin(M x n_cols) = [accumulate +] Gout(M x out) W[:, col0:col0+n_cols], optional ReLU mask
 static int dgrad(const CfnHandle* h, int slot, const float* Gout, int64_t ldgo, int col0, int n_cols, float* Gin,
-                 int64_t ldgi, int64_t M, const float* mask, int64_t ld_mask, int accumulate, cudaStream_t s) {
+                 int64_t ldgi, int64_t M, const float* mask, int64_t ld_mask, int accumulate, cudaStream_t s,
+                 const uint32_t* mask_bits = nullptr, int bits_ld = 0) {
   const ParamSlot& w = h->slots[slot];
   const WView& v = h->wv[slot];
   GemmArgs g{};
@@ -367,6 +406,7 @@ static int dgrad(const CfnHandle* h, int slot, const float* Gout, int64_t ldgo, 
   g.B = v.p + col0 + (col0 >= v.gap_at ? v.gap : 0); g.b_rs = v.ld; g.b_cs = 1;   // B(k=o, n=i) = W[o*ld + col0' + i]
   g.C = Gin; g.c_rs = ldgi;
   g.aux = mask; g.aux_rs = ld_mask;
+  g.aux_bits = mask ? mask_bits : nullptr; g.bits_ld = bits_ld;
   g.M = M; g.N = n_cols; g.K = w.rows;
   g.epilogue = mask ? EPI_RELU_MASK_MUL : EPI_NONE;
   g.accumulate = accumulate; g.split_k = 1;
@@ -412,6 +452,11 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
   float* gh = ws + L.gh;
   float* gv = ws + L.gv;
   float* dWp = ws + L.dWp;
+  const bool bits = use_bits(h);
+  const uint32_t* mbv = bits ? reinterpret_cast<const uint32_t*>(ws + L.mbv) : nullptr;
+  auto MBl = [&](int layer) -> const uint32_t* {
+    return bits ? reinterpret_cast<const uint32_t*>(ws + L.MB) + (int64_t)layer * M * L.bw : nullptr;
+  };
 
   // zero every flow-conditioning gradient: rows the path never reads keep an exact 0
   for (int base : {h->s_frgb, h->s_falpha})
@@ -450,13 +495,13 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
     if ((rc = gemm(h, g, 1, s))) return rc;
     if ((rc = wgrad_slot(h, h->s_hrgb, gh, hr_n, ws + L.v, W / 2, M, grads[h->s_hrgb], grads[h->s_hrgb + 1], dWp, s))) return rc;
     // g_v = (g_hr W_hrgb) * relu'(v)
-    if ((rc = dgrad(h, h->s_hrgb, gh, hr_n, 0, W / 2, gv, W / 2, M, ws + L.v, W / 2, 0, s))) return rc;
+    if ((rc = dgrad(h, h->s_hrgb, gh, hr_n, 0, W / 2, gv, W / 2, M, ws + L.v, W / 2, 0, s, mbv, L.bwv))) return rc;
     if ((rc = wgrad_slot(h, h->s_views, gv, W / 2, ws + L.V, L.ldv, M, grads[h->s_views], grads[h->s_views + 1], dWp, s))) return rc;
     // g_feat = g_v W_view[:, :W]   (gamma(d) columns need no gradient)
     if ((rc = dgrad(h, h->s_views, gv, W / 2, 0, W, G2, W, M, nullptr, 0, 0, s))) return rc;
     if ((rc = wgrad_slot(h, h->s_feat, G2, W, h7, ld7, M, grads[h->s_feat], grads[h->s_feat + 1], dWp, s))) return rc;
     // g_h7 = (g_h7 + g_feat W_feat) * relu'(h7)
-    if ((rc = dgrad(h, h->s_feat, G2, W, 0, W, G1, W, M, h7, ld7, 1, s))) return rc;
+    if ((rc = dgrad(h, h->s_feat, G2, W, 0, W, G1, W, M, h7, ld7, 1, s, MBl(D - 1), L.bw))) return rc;
   }
   // 4. trunk, last layer to first
   float* gout = G1;
@@ -469,7 +514,7 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
     // gradient w.r.t. the previous layer's (post-ReLU) output, masked by its ReLU
     LayerIO prev = trunk_io(h, L, ws, M, i - 1, 1);
     const int col0 = (h->skip >= 0 && i == h->skip + 1) ? h->in_pos : 0;   // skip input is cat[gamma(p), h]
-    if ((rc = dgrad(h, slot, gout, W, col0, W, gin, W, M, prev.out, prev.ld_out, 0, s))) return rc;
+    if ((rc = dgrad(h, slot, gout, W, col0, W, gin, W, M, prev.out, prev.ld_out, 0, s, MBl(i - 1), L.bw))) return rc;
     float* t = gout; gout = gin; gin = t;
   }
   return CFN_OK;
