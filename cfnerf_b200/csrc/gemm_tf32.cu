@@ -156,7 +156,10 @@ __device__ __forceinline__ uint64_t desc_hi_mnmajor(uint32_t lbo_bytes) {
   return ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 
-template <int CG, bool A_MN, bool B_MN>
+// EPI (compile-time epilogue flavour: one instruction stream per flavour keeps the epilogue loop short enough to unroll)
+enum { TG_PLAIN = 0, TG_RELU = 1, TG_TANH = 2, TG_MASK = 3, TG_ATOMIC = 4 };
+
+template <int CG, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -177,7 +180,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   // 2 KB of ones right after the barriers: the B operand of the optional row-sum MMA (any layout of ones is ones)
   const uint32_t ones_addr = smem_base + (uint32_t)p.stages * p.stage_bytes + 1024u;
-  if (p.rowsum) {
+  if (EPI == TG_ATOMIC && p.rowsum) {
     float* ones = reinterpret_cast<float*>(smem_raw + (size_t)p.stages * p.stage_bytes + 1024);
     for (int i = threadIdx.x; i < 512; i += TG_THREADS) ones[i] = 1.0f;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -273,7 +276,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               umma_tf32<CG>(d_tmem, adesc + (uint64_t)(a_step * ks), bdesc + (uint64_t)(b_step * ks), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-            if (p.rowsum && nt == 0) {   // columns 256.. are free: a row-sum GEMM owns one work item per CTA (pair)
+            if (EPI == TG_ATOMIC && p.rowsum && nt == 0) {   // columns 256.. are free: a row-sum GEMM owns one work item per CTA (pair)
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 umma_tf32<CG>(tmem_base + 256u, adesc + (uint64_t)(a_step * ks), ones_desc, idesc16, (kb > 0 || ks > 0) ? 1u : 0u);
@@ -307,7 +310,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // HBM round trip is exposed.  The fp32 form (aux = the saved activations) is kept for callers without bit masks.
       // The loops below are deliberately NOT unrolled: with every epilogue flavour inlined, an unrolled body ran out of
       // the instruction cache (a quarter of all stall samples were instruction fetches) and became the critical path.
-      const bool use_bits = (p.epilogue == EPI_RELU_MASK_MUL) && p.aux_bits != nullptr;
+      const bool use_bits = (EPI == TG_MASK) && p.aux_bits != nullptr;
       uint32_t pb1 = 0, pb2 = 0;
       auto load_bits = [&](int c) -> uint32_t {
         const int64_t gmp = tile_m0 + q * 32 + lane;
@@ -319,7 +322,6 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       mbar_wait(bar_local(&bars->acc_full[buf]), (it >> 1) & 1u);
       tc_fence_after();
-      const float relu_lo = (p.epilogue == EPI_RELU) ? 0.f : -INFINITY;
 #pragma unroll 1
       for (int c = hh; c < n_chunks; c += 2) {
         // phase 1: this warp's 32 x 32 accumulator block, TMEM -> registers (thread = row) -> padded shared-memory tile
@@ -343,80 +345,108 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const bool vec = p.vec_ok && (gn + 3 < p.N);
         float b4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t tanh_nib = 0;
+        if (EPI != TG_ATOMIC) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (gn + i < p.N) {
-            if (p.bias) b4[i] = __ldg(p.bias + gn + i);
-            if (p.epilogue == EPI_TANH_MASK && __ldg(p.aux + gn + i) != 0.f) tanh_nib |= 1u << i;
+          for (int i = 0; i < 4; ++i)
+            if (gn + i < p.N) {
+              if (p.bias) b4[i] = __ldg(p.bias + gn + i);
+              if (EPI == TG_TANH && __ldg(p.aux + gn + i) != 0.f) tanh_nib |= 1u << i;
+            }
+        }
+        const int64_t gm0 = tile_m0 + q * 32 + sub_r;
+        // WARP-UNIFORM choice (both paths contain full-mask shuffles): the whole 32 x 32 block inside the matrix
+        const bool block_inside = p.vec_ok && (tile_m0 + q * 32 + 31 < p.M) && (n_tile0 + c * 32 + 31 < p.N);
+        if (block_inside) {
+          // ---- fast path: the whole 32 x 32 block is inside the matrix and 16-byte addressable ----
+#pragma unroll 4
+          for (int t = 0; t < 8; ++t) {
+            const int r = t * 4 + sub_r;
+            const int64_t gm = gm0 + t * 4;
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + r * TG_STG_LD + c4);
+            float x[4] = {a4.x, a4.y, a4.z, a4.w};
+            float* cp = p.C + gm * p.c_rs + gn;
+            if (EPI == TG_ATOMIC) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(cp), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+              continue;
+            }
+            uint32_t keep = 0xFu;
+            if (EPI == TG_MASK) {
+              if (use_bits) keep = __shfl_sync(0xffffffffu, curb, r) >> (4 * (lane & 7));
+              else if (p.epilogue == EPI_RELU_MASK_MUL) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.aux + gm * p.aux_rs + gn));
+                keep = (t4.x > 0.f ? 1u : 0u) | (t4.y > 0.f ? 2u : 0u) | (t4.z > 0.f ? 4u : 0u) | (t4.w > 0.f ? 8u : 0u);
+              }
+              if (p.accumulate) { const float4 t4 = *reinterpret_cast<const float4*>(cp); x[0] += t4.x; x[1] += t4.y; x[2] += t4.z; x[3] += t4.w; }
+            }
+            uint32_t pos = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float y = x[i] + b4[i];
+              if (EPI == TG_RELU) y = fmaxf(y, 0.f);
+              if (EPI == TG_TANH) { if (tanh_nib & (1u << i)) y = tanhf(y); }
+              if (EPI == TG_MASK) y = (keep & (1u << i)) ? y : 0.f;
+              if (p.round_out) y = round_tf32(y);
+              if (EPI == TG_RELU) pos |= (y > 0.f ? 1u : 0u) << i;
+              x[i] = y;
+            }
+            *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+            if (EPI == TG_RELU && p.mask_out) {
+              // relu'(y) of this row's 32 columns packed into one word by the 8 lanes that hold them
+              uint32_t word = pos << (4 * (lane & 7));
+              word |= __shfl_xor_sync(0xffffffffu, word, 1);
+              word |= __shfl_xor_sync(0xffffffffu, word, 2);
+              word |= __shfl_xor_sync(0xffffffffu, word, 4);
+              if ((lane & 7) == 0) p.mask_out[gm * p.bits_ld + ((n_tile0 + c * 32) >> 5)] = word;
+            }
           }
+        } else {
+          // ---- edge path: ragged rows / columns or unaligned C: element-wise, every lane still joins the shuffles ----
 #pragma unroll 1
-        for (int t = 0; t < 8; ++t) {
-          const int r = t * 4 + sub_r;
-          const int64_t gm = tile_m0 + q * 32 + r;
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + r * TG_STG_LD + c4);
-          const uint32_t rowbits = __shfl_sync(0xffffffffu, curb, r);   // every lane takes part
-          const bool ok = gm < p.M && gn < p.N;
-          float x[4] = {a4.x, a4.y, a4.z, a4.w};
-          float* cp = p.C + gm * p.c_rs + gn;
-          if (p.atomic) {
+          for (int t = 0; t < 8; ++t) {
+            const int r = t * 4 + sub_r;
+            const int64_t gm = gm0 + t * 4;
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + r * TG_STG_LD + c4);
+            const uint32_t rowbits = __shfl_sync(0xffffffffu, curb, r);
+            const bool ok = gm < p.M && gn < p.N;
+            float x[4] = {a4.x, a4.y, a4.z, a4.w};
+            float* cp = p.C + gm * p.c_rs + gn;
+            uint32_t pos = 0;
             if (ok) {
-              if (vec) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(cp), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
-              else {
+              uint32_t keep = 0xFu;
+              if (EPI == TG_MASK) {
+                if (use_bits) keep = rowbits >> (4 * (lane & 7));
+                else if (p.epilogue == EPI_RELU_MASK_MUL) {
+                  keep = 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) if (gn + i < p.N) atomicAdd(cp + i, x[i]);
+                  for (int i = 0; i < 4; ++i) if (gn + i < p.N && __ldg(p.aux + gm * p.aux_rs + gn + i) > 0.f) keep |= 1u << i;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (gn + i >= p.N) continue;
+                if (EPI == TG_ATOMIC) { atomicAdd(cp + i, x[i]); continue; }
+                float y = x[i] + b4[i];
+                if (EPI == TG_MASK && p.accumulate) y += cp[i];
+                if (EPI == TG_RELU) y = fmaxf(y, 0.f);
+                if (EPI == TG_TANH) { if (tanh_nib & (1u << i)) y = tanhf(y); }
+                if (EPI == TG_MASK) y = (keep & (1u << i)) ? y : 0.f;
+                if (p.round_out) y = round_tf32(y);
+                if (y > 0.f) pos |= 1u << i;
+                cp[i] = y;
               }
             }
-            continue;
-          }
-          uint32_t keep = 0xFu;                       // relu'(h) of the four columns
-          if (use_bits) keep = rowbits >> (4 * (lane & 7));
-          else if (p.epilogue == EPI_RELU_MASK_MUL && ok) {
-            const float* ap = p.aux + gm * p.aux_rs + gn;
-            keep = 0;
-            if (vec) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(ap));
-              keep = (t4.x > 0.f ? 1u : 0u) | (t4.y > 0.f ? 2u : 0u) | (t4.z > 0.f ? 4u : 0u) | (t4.w > 0.f ? 8u : 0u);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) if (gn + i < p.N && __ldg(ap + i) > 0.f) keep |= 1u << i;
+            if (EPI == TG_RELU && p.mask_out) {
+              uint32_t word = pos << (4 * (lane & 7));
+              word |= __shfl_xor_sync(0xffffffffu, word, 1);
+              word |= __shfl_xor_sync(0xffffffffu, word, 2);
+              word |= __shfl_xor_sync(0xffffffffu, word, 4);
+              if ((lane & 7) == 0 && gm < p.M) p.mask_out[gm * p.bits_ld + ((n_tile0 + c * 32) >> 5)] = word;
             }
-          }
-          if (p.accumulate && ok) {
-            if (vec) { const float4 t4 = *reinterpret_cast<const float4*>(cp); x[0] += t4.x; x[1] += t4.y; x[2] += t4.z; x[3] += t4.w; }
-            else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) if (gn + i < p.N) x[i] += cp[i];
-            }
-          }
-          uint32_t pos = 0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float y = fmaxf(x[i] + b4[i], relu_lo);
-            if (tanh_nib & (1u << i)) y = tanhf(y);
-            if (!(keep & (1u << i))) y = 0.f;
-            if (p.round_out) y = round_tf32(y);
-            if (y > 0.f && gn + i < p.N) pos |= 1u << i;
-            x[i] = y;
-          }
-          if (ok) {
-            if (vec) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
-            else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) if (gn + i < p.N) cp[i] = x[i];
-            }
-          }
-          if (p.mask_out) {
-            // relu'(y) of this row's 32 columns packed into one word by the 8 lanes that hold them (all lanes shuffle)
-            uint32_t word = (ok ? pos : 0u) << (4 * (lane & 7));
-            word |= __shfl_xor_sync(0xffffffffu, word, 1);
-            word |= __shfl_xor_sync(0xffffffffu, word, 2);
-            word |= __shfl_xor_sync(0xffffffffu, word, 4);
-            if ((lane & 7) == 0 && gm < p.M) p.mask_out[gm * p.bits_ld + ((n_tile0 + c * 32) >> 5)] = word;
           }
         }
         __syncwarp();   // the staging tile is rewritten by the next chunk
       }
-      if (p.rowsum && nt == 0 && hh == 0) {
+      if (EPI == TG_ATOMIC && p.rowsum && nt == 0 && hh == 0) {
         const uint32_t sum = tmem_ld1(tmem_row + 256u);
         tmem_ld_wait();
         const int64_t gm = tile_m0 + q * 32 + lane;
@@ -481,10 +511,10 @@ int num_sms() {
   return n;
 }
 
-template <int CG, bool A_MN, bool B_MN>
+template <int CG, bool A_MN, bool B_MN, int EPI>
 int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const TgParams& p, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
-  auto kern = tgemm_kernel<CG, A_MN, B_MN>;
+  auto kern = tgemm_kernel<CG, A_MN, B_MN, EPI>;
   if (!attr_set) {
     CFN_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
@@ -518,7 +548,15 @@ bool tgemm_supported(const GemmArgs& g) {
   const int64_t a_ld = a_k ? g.a_rs : g.a_cs, b_ld = b_k ? g.b_cs : g.b_rs;
   if (a_ld % 4 || b_ld % 4 || a_ld <= 0 || b_ld <= 0) return false;
   if (!aligned16(g.A) || !aligned16(g.B)) return false;
-  return true;
+  // instantiated (operand majors x epilogue) combinations: what the network stage issues
+  const bool atomic = g.split_k > 1;
+  const bool a_mn_ = !a_k, b_mn_ = !b_k;
+  const bool plain = !atomic && g.epilogue == EPI_NONE && !g.accumulate;
+  const bool mask = !atomic && (g.epilogue == EPI_RELU_MASK_MUL || (g.epilogue == EPI_NONE && g.accumulate));
+  if (!a_mn_ && !b_mn_) return !atomic && (plain || mask || ((g.epilogue == EPI_RELU || g.epilogue == EPI_TANH_MASK) && !g.accumulate));
+  if (!a_mn_ && b_mn_) return plain || mask;
+  if (a_mn_ && b_mn_) return atomic || plain;
+  return plain;
 }
 
 // tile / split / stage geometry of one GEMM
@@ -585,16 +623,34 @@ int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s) {
   else rc = make_map(&tmB, g.B, g.K, g.N, g.b_rs, 32, true);
   if (rc) return rc;
 
-  if (CG == 1) {
-    if (!a_mn && !b_mn) return launch_variant<1, false, false>(tmA, tmB, p, smem, s);
-    if (!a_mn && b_mn) return launch_variant<1, false, true>(tmA, tmB, p, smem, s);
-    if (a_mn && !b_mn) return launch_variant<1, true, false>(tmA, tmB, p, smem, s);
-    return launch_variant<1, true, true>(tmA, tmB, p, smem, s);
+  // epilogue flavour (compile-time in the kernel); only the combinations the network stage issues are instantiated,
+  // anything else is reported as unsupported and the caller falls back to the CUDA-core engine
+  int epi = TG_PLAIN;
+  if (p.atomic) epi = TG_ATOMIC;
+  else if (g.epilogue == EPI_RELU) epi = TG_RELU;
+  else if (g.epilogue == EPI_TANH_MASK) epi = TG_TANH;
+  else if (g.epilogue == EPI_RELU_MASK_MUL || g.accumulate) epi = TG_MASK;
+#define TG_LAUNCH(cg, am, bm, e) return launch_variant<cg, am, bm, e>(tmA, tmB, p, smem, s)
+#define TG_BY_CG(am, bm, e) do { if (CG == 1) TG_LAUNCH(1, am, bm, e); else TG_LAUNCH(2, am, bm, e); } while (0)
+  if (!a_mn && !b_mn) {
+    if (epi == TG_PLAIN) TG_BY_CG(false, false, TG_PLAIN);
+    if (epi == TG_RELU) TG_BY_CG(false, false, TG_RELU);
+    if (epi == TG_TANH) TG_BY_CG(false, false, TG_TANH);
+    if (epi == TG_MASK) TG_BY_CG(false, false, TG_MASK);
+  } else if (!a_mn && b_mn) {
+    if (epi == TG_PLAIN) TG_BY_CG(false, true, TG_PLAIN);
+    if (epi == TG_MASK) TG_BY_CG(false, true, TG_MASK);
+  } else if (a_mn && b_mn) {
+    if (epi == TG_ATOMIC) TG_BY_CG(true, true, TG_ATOMIC);
+    if (epi == TG_PLAIN) TG_BY_CG(true, true, TG_PLAIN);
+  } else {
+    if (epi == TG_PLAIN) TG_BY_CG(true, false, TG_PLAIN);
   }
-  if (!a_mn && !b_mn) return launch_variant<2, false, false>(tmA, tmB, p, smem, s);
-  if (!a_mn && b_mn) return launch_variant<2, false, true>(tmA, tmB, p, smem, s);
-  if (a_mn && !b_mn) return launch_variant<2, true, false>(tmA, tmB, p, smem, s);
-  return launch_variant<2, true, true>(tmA, tmB, p, smem, s);
+#undef TG_BY_CG
+#undef TG_LAUNCH
+  set_error("tgemm: operand-major / epilogue combination not instantiated (a_mn %d, b_mn %d, epilogue %d, split %d)",
+            (int)a_mn, (int)b_mn, g.epilogue, g.split_k);
+  return CFN_EINVAL;
 }
 
 }  // namespace cfn
