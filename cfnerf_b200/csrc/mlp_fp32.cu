@@ -30,6 +30,8 @@ static Fp32Layout make_layout(const CfnHandle* h, int64_t M, int save) {
   L.ld5 = h->gp + W;          // [gamma(p) | pad to 4 | h]: the h columns start 16-byte aligned
   L.ldv = W + h->gd;          // [feature | gamma(d) | pad to 4]
   L.ldg = L.ld5 > L.ldv ? L.ld5 : L.ldv;
+  const int wc = W + ((h->cfg.h_alpha + 3) & ~3);   // [g_feat | g_h_alpha] rows of the fused head dgrad
+  if (wc > L.ldg) L.ldg = wc;
   L.nH = save ? h->cfg.D : 2;
   int64_t o = 0;
   auto take = [&](int64_t n) { int64_t r = o; o += (n + 3) & ~(int64_t)3; return r; };
@@ -453,6 +455,12 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
   float* gv = ws + L.gv;
   float* dWp = ws + L.dWp;
   const bool bits = use_bits(h);
+  // fused head dgrad: needs W_halpha stored right behind W_feat in the operand buffer with the same row stride
+  const bool fuse_heads = h->wv[h->s_feat].ld == W && h->wv[h->s_halpha].ld == W &&
+                          h->wv[h->s_halpha].p == h->wv[h->s_feat].p + (int64_t)W * W;
+  const int64_t ld_g2 = fuse_heads ? W + ((ha_n + 3) & ~3) : W;
+  float* gha = fuse_heads ? G2 + W : gh;                 // g_h_alpha lives in columns W.. of the g_feat rows when fused
+  const int64_t ld_gha = fuse_heads ? ld_g2 : ha_n;
   const uint32_t* mbv = bits ? reinterpret_cast<const uint32_t*>(ws + L.mbv) : nullptr;
   auto MBl = [&](int layer) -> const uint32_t* {
     return bits ? reinterpret_cast<const uint32_t*>(ws + L.MB) + (int64_t)layer * M * L.bw : nullptr;
@@ -477,11 +485,11 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
     GemmArgs g{};
     g.A = GP; g.a_rs = PP; g.a_cs = 1;
     g.B = h->amA_g; g.b_rs = ha_n; g.b_cs = 1;
-    g.C = gh; g.c_rs = ha_n; g.M = M; g.N = ha_n; g.K = 3 * F; g.split_k = 1;
+    g.C = gha; g.c_rs = ld_gha; g.M = M; g.N = ha_n; g.K = 3 * F; g.split_k = 1;
     if ((rc = gemm(h, g, 1, s))) return rc;
-    if ((rc = wgrad_slot(h, h->s_halpha, gh, ha_n, h7, ld7, M, grads[h->s_halpha], grads[h->s_halpha + 1], dWp, s))) return rc;
-    // g_h7 (unmasked, first contribution) = g_ha W_halpha
-    if ((rc = dgrad(h, h->s_halpha, gh, ha_n, 0, W, G1, W, M, nullptr, 0, 0, s))) return rc;
+    if ((rc = wgrad_slot(h, h->s_halpha, gha, ld_gha, h7, ld7, M, grads[h->s_halpha], grads[h->s_halpha + 1], dWp, s))) return rc;
+    // g_h7 (unmasked, first contribution) = g_ha W_halpha  -- or, fused, left for the K-concatenated GEMM of step 3
+    if (!fuse_heads && (rc = dgrad(h, h->s_halpha, gha, ld_gha, 0, W, G1, W, M, nullptr, 0, 0, s))) return rc;
   }
   // 3. rgb conditioning branch
   {
@@ -498,10 +506,23 @@ int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N,
     if ((rc = dgrad(h, h->s_hrgb, gh, hr_n, 0, W / 2, gv, W / 2, M, ws + L.v, W / 2, 0, s, mbv, L.bwv))) return rc;
     if ((rc = wgrad_slot(h, h->s_views, gv, W / 2, ws + L.V, L.ldv, M, grads[h->s_views], grads[h->s_views + 1], dWp, s))) return rc;
     // g_feat = g_v W_view[:, :W]   (gamma(d) columns need no gradient)
-    if ((rc = dgrad(h, h->s_views, gv, W / 2, 0, W, G2, W, M, nullptr, 0, 0, s))) return rc;
-    if ((rc = wgrad_slot(h, h->s_feat, G2, W, h7, ld7, M, grads[h->s_feat], grads[h->s_feat + 1], dWp, s))) return rc;
-    // g_h7 = (g_h7 + g_feat W_feat) * relu'(h7)
-    if ((rc = dgrad(h, h->s_feat, G2, W, 0, W, G1, W, M, h7, ld7, 1, s, MBl(D - 1), L.bw))) return rc;
+    if ((rc = dgrad(h, h->s_views, gv, W / 2, 0, W, G2, ld_g2, M, nullptr, 0, 0, s))) return rc;
+    if ((rc = wgrad_slot(h, h->s_feat, G2, ld_g2, h7, ld7, M, grads[h->s_feat], grads[h->s_feat + 1], dWp, s))) return rc;
+    if (fuse_heads) {
+      // g_h7 = ([g_feat | g_ha] [W_feat ; W_halpha]) * relu'(h7): one GEMM over the concatenated K instead of a second,
+      // accumulating one (its read-modify-write of g_h7 cost three times a plain dgrad)
+      GemmArgs g{};
+      g.A = G2; g.a_rs = ld_g2; g.a_cs = 1;
+      g.B = h->wv[h->s_feat].p; g.b_rs = W; g.b_cs = 1;       // rows 0..W-1 = W_feat, rows W.. = W_halpha (adjacent in wg)
+      g.C = G1; g.c_rs = W;
+      g.aux = h7; g.aux_rs = ld7; g.aux_bits = MBl(D - 1); g.bits_ld = L.bw;
+      g.M = M; g.N = W; g.K = W + ha_n;
+      g.epilogue = EPI_RELU_MASK_MUL; g.split_k = 1;
+      if ((rc = gemm(h, g, 1, s))) return rc;
+    } else {
+      // g_h7 = (g_h7 + g_feat W_feat) * relu'(h7)
+      if ((rc = dgrad(h, h->s_feat, G2, W, 0, W, G1, W, M, h7, ld7, 1, s, MBl(D - 1), L.bw))) return rc;
+    }
   }
   // 4. trunk, last layer to first
   float* gout = G1;
