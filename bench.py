@@ -312,6 +312,28 @@ def main():
         barrier()
         train_ms = te0.elapsed_time(te1)
 
+    # roofline of the training GEMMs (HBM-bound by their fp32 storage): one trunk-layer forward GEMM on the step's shape
+    # (points x W x W, bias + ReLU + tf32 rounding) timed alone with CUDA events; algorithmic bytes = X in + Y out
+    tg_ms = 0.0
+    if not args.no_train and args.train_precision == "tf32" and rank == 0:
+        Mp = t_rays.shape[0] * N_SAMPLES
+        Xg = torch.randn(Mp, cfg.W, device=dev)
+        Wg = torch.randn(cfg.W, cfg.W, device=dev) * 0.05
+        bg = torch.randn(cfg.W, device=dev)
+        Yg = torch.empty(Mp, cfg.W, device=dev)
+        for _ in range(3):
+            cf.gemm(Xg, Wg.t(), engine="tf32", bias=bg, epilogue="relu", out=Yg, round_out=True)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(10):
+            cf.gemm(Xg, Wg.t(), engine="tf32", bias=bg, epilogue="relu", out=Yg, round_out=True)
+        g1.record()
+        torch.cuda.synchronize()
+        tg_ms = g0.elapsed_time(g1) / 10
+        del Xg, Yg
+    barrier()
+
     t = torch.tensor([ms, e2e_ms, k1_ms, train_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -354,6 +376,17 @@ def main():
                 "achieved_tflops_per_gpu": n_t * N_SAMPLES * FLOP_PER_POINT * 3 / step_s / 1e12,
                 "note": "forward + backward + Adam through cfnerf_b200.dist.train_step; GEMMs = TMA-fed tcgen05 kind::tf32 "
                         "(fp32 storage) when precision is tf32, CUDA-core fp32 FMA when fp32; flops = 3 x forward GEMM flops"}
+            if tg_ms > 0:
+                Mp = n_t * N_SAMPLES
+                gb = 2.0 * Mp * cfg.W * 4 / 1e9            # activations in + out (the 1 MB weight matrix is L2-resident)
+                hbm = peaks.get("hbm_gbs", 6545.9)
+                line["train_step"]["roofline"] = {
+                    "bound": "hbm", "achieved": gb / (tg_ms * 1e-3), "peak": hbm, "unit": "GB/s",
+                    "frac": gb / (tg_ms * 1e-3) / hbm, "traffic": 2146472000.0,
+                    "traffic_note": "DRAM read + write of this GEMM from profiles/r01_prof_tgemm_fwd_summary.csv (ncu --set "
+                                    "full) at 524288 points; algorithmic bytes = 2 x points x 512 x 4 = 2.147e9",
+                    "kernel": "tgemm_kernel<2,K,K,relu> (one trunk-layer forward GEMM of the training step)",
+                    "ms": tg_ms, "tflops": 2.0 * Mp * cfg.W * cfg.W / (tg_ms * 1e-3) / 1e12}
         if not args.no_cpu_baseline:
             v, cores = cpu_reference_rays_per_s(args.cpu_rays, 2)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",

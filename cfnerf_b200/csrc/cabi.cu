@@ -223,7 +223,7 @@ extern "C" int cfn_workspace_bytes(const CfnHandle* h, int64_t n_points, int sav
     *out = tc_workspace_bytes(h, n_points);
     return CFN_OK;
   }
-  *out = fp32_workspace_floats(h, n_points, save_for_backward) * sizeof(float) + 256;
+  *out = chain_workspace_floats(h, n_points, save_for_backward) * sizeof(float) + 256;
   return CFN_OK;
 }
 
@@ -258,7 +258,7 @@ extern "C" int cfn_network_fwd(CfnHandle* h, const float* rays, const float* z_v
   cudaStream_t s = (cudaStream_t)stream;
   if (h->tc && !save_for_backward)
     return tc_network_fwd(h, rays, z_vals, pts, viewdirs, B, N, flow_params, workspace, workspace_bytes, s);
-  return fp32_network_fwd(h, rays, z_vals, pts, viewdirs, B, N, flow_params, (float*)workspace, save_for_backward, s);
+  return chain_network_fwd(h, rays, z_vals, pts, viewdirs, B, N, flow_params, (float*)workspace, save_for_backward, s);
 }
 
 extern "C" int cfn_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, void* workspace,
@@ -271,7 +271,7 @@ extern "C" int cfn_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t
     set_error("cfn_network_bwd: workspace %zu bytes < required %zu", workspace_bytes, need);
     return CFN_ENOMEM;
   }
-  return fp32_network_bwd(h, g_flow_params, B, N, (float*)workspace, grads, (cudaStream_t)stream);
+  return chain_network_bwd(h, g_flow_params, B, N, (float*)workspace, grads, (cudaStream_t)stream);
 }
 
 extern "C" int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, const float* z_vals,
@@ -286,7 +286,8 @@ extern "C" int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, co
     return CFN_ESTATE;
   }
   // training (log-det sums requested) and the fp32 check mode keep the accurate functions
-  const int fast = (h->cfg.precision != CFN_PREC_FP32 && logdet_sums == nullptr) ? 1 : 0;
+  // one-MUFU transcendentals behind every tensor-core mode (render and training); the log of the log-det stays accurate
+  const int fast = (h->cfg.precision != CFN_PREC_FP32) ? 1 : 0;
   return launch_flow_composite_fwd(fast, h->cfg.F, h->cfg.K, h->globals, flow_params, z_vals, rays_d, rays_d_stride,
                                    eps_alpha, eps_rgb, B, N, white_bkgd, rgb_map, disp_map, depth_map, raw, weights,
                                    logdet_sums, kstats, (cudaStream_t)stream);
@@ -304,7 +305,7 @@ extern "C" int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, co
     set_error("cfn_flow_composite_bwd: call cfn_pack_weights first");
     return CFN_ESTATE;
   }
-  return launch_flow_composite_bwd(h->cfg.F, h->cfg.K, h->globals, flow_params, z_vals, rays_d, rays_d_stride,
+  return launch_flow_composite_bwd(h->cfg.precision != CFN_PREC_FP32 ? 1 : 0, h->cfg.F, h->cfg.K, h->globals, flow_params, z_vals, rays_d, rays_d_stride,
                                    eps_alpha, eps_rgb, B, N, white_bkgd, g_rgb_map, g_depth_map, g_logdet_alpha,
                                    g_logdet_rgb, g_flow_params, g_globals_partial, (cudaStream_t)stream);
 }

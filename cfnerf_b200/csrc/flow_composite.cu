@@ -278,7 +278,7 @@ int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals,
 // Gradients w.r.t. the global latent parameters through z0 = eps*std + mean are summed per ray into
 // g_globals_partial (B,8) (deterministic; the host sums over rays).
 // =====================================================================================================
-template <int FT>
+template <int FT, bool FAST>
 __global__ void __launch_bounds__(128)
 flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float* __restrict__ flow_params,
                           const float* __restrict__ z_vals, const float* __restrict__ rays_d, int rays_d_stride,
@@ -342,8 +342,8 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
         const float* P = prow + (int64_t)n * PP;   // warp-uniform address: one broadcast transaction
         float za = za0;
 #pragma unroll
-        for (int f = 0; f < F; ++f) za += __ldg(P + f) * tanhf(__ldg(P + F + f) * za + __ldg(P + 2 * F + f));
-        const float alpha = 1.0f - expf(-softplusf_(za) * sd[n]);
+        for (int f = 0; f < F; ++f) za += __ldg(P + f) * tanh_<FAST>(__ldg(P + F + f) * za + __ldg(P + 2 * F + f));
+        const float alpha = 1.0f - exp_<FAST>(-softplus_<FAST>(za) * sd[n]);
         sT[n * 32 + lane] = T;
         T = T * ((1.0f - alpha) + 1e-10f);
       }
@@ -362,7 +362,7 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
 #pragma unroll
       for (int f = 0; f < F; ++f) {
         za_in[f] = za;
-        ta[f] = tanhf(sP[F + f] * za + sP[2 * F + f]);
+        ta[f] = tanh_<FAST>(sP[F + f] * za + sP[2 * F + f]);
         za += sP[f] * ta[f];
       }
       // recompute rgb stack with intermediates
@@ -373,9 +373,9 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
         const float* Q = sP + 3 * F + kRgbFlowRec * f;
         const bool odd = f & 1;
         zp[f][0] = odd ? z[2] : z[0]; zp[f][1] = z[1]; zp[f][2] = odd ? z[0] : z[2];
-        tc[f][0] = tanhf(Q[6] * zp[f][0] + Q[7] * zp[f][1] + Q[8] * zp[f][2] + Q[12]);
-        tc[f][1] = tanhf(Q[9] * zp[f][1] + Q[10] * zp[f][2] + Q[13]);
-        tc[f][2] = tanhf(Q[11] * zp[f][2] + Q[14]);
+        tc[f][0] = tanh_<FAST>(Q[6] * zp[f][0] + Q[7] * zp[f][1] + Q[8] * zp[f][2] + Q[12]);
+        tc[f][1] = tanh_<FAST>(Q[9] * zp[f][1] + Q[10] * zp[f][2] + Q[13]);
+        tc[f][2] = tanh_<FAST>(Q[11] * zp[f][2] + Q[14]);
         const float s0 = Q[0] * tc[f][0] + Q[1] * tc[f][1] + Q[2] * tc[f][2];
         const float s1 = Q[3] * tc[f][1] + Q[4] * tc[f][2];
         const float s2 = Q[5] * tc[f][2];
@@ -383,17 +383,17 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
       }
       // ---- compositing adjoint (Appendix A.2) ----
       const float T = sT[n * 32 + lane];
-      const float alpha = 1.0f - expf(-softplusf_(za) * sd[n]);
+      const float alpha = 1.0f - exp_<FAST>(-softplus_<FAST>(za) * sd[n]);
       const float w = alpha * T;
       const float q = (1.0f - alpha) + 1e-10f;
       float col[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) col[c] = sigmoidf_(z[c]);
+      for (int c = 0; c < 3; ++c) col[c] = sigmoid_<FAST>(z[c]);
       const float v = gC[0] * col[0] + gC[1] * col[1] + gC[2] * col[2] + gD * sz[n] + gA;
       const float g_alpha = v * T - S / q;
       S += v * w;
       // d alpha / d raw_sigma = (1-alpha) * delta * sigmoid(raw_sigma);  entropy activation term (models.py:263)
-      float g_za = g_alpha * (1.0f - alpha) * sd[n] * sigmoidf_(za) + gl_a * (1.0f - sigmoidf_(za));
+      float g_za = g_alpha * (1.0f - alpha) * sd[n] * sigmoid_<FAST>(za) + gl_a * (1.0f - sigmoid_<FAST>(za));
       float gz[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c)
@@ -491,7 +491,7 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
   }
 }
 
-int launch_flow_composite_bwd(int F, int K, const float* globals, const float* flow_params, const float* z_vals,
+int launch_flow_composite_bwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
                               int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
                               float g_ld_alpha, float g_ld_rgb, float* g_flow_params, float* g_globals_partial,
@@ -504,7 +504,7 @@ int launch_flow_composite_bwd(int F, int K, const float* globals, const float* f
   unsigned grid = (unsigned)((B + 3) / 4);
 #define CFN_BWD_CASE(FF)                                                                                             \
   case FF: {                                                                                                         \
-    auto kern = flow_composite_bwd_kernel<FF>;                                                                       \
+    auto kern = fast_math ? flow_composite_bwd_kernel<FF, true> : flow_composite_bwd_kernel<FF, false>;              \
     CFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
     kern<<<grid, 128, smem, s>>>(K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N,   \
                                  white_bkgd, g_rgb_map, g_depth_map, g_ld_alpha, g_ld_rgb, g_flow_params,            \

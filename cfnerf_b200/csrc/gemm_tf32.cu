@@ -4,7 +4,7 @@
 //
 // This is the contraction of the TRAINING path (forward with saved activations, dgrad chain, split-K wgrad;
 // reference: loss.backward() through model/models.py:165-186, run_nerf_uncertainty_NF.py:1065-1067) and of the
-// CFN_PREC_TF32 render mode.  Operands stay fp32 in HBM exactly where mlp_fp32.cu's orchestration keeps them, so
+// CFN_PREC_TF32 render mode.  Operands stay fp32 in HBM exactly where mlp_chain.cu's orchestration keeps them, so
 // the three GEMM flavours of a Linear need no transposed copies:
 //   forward   Y = X W^T      A = X  (K-major)   B = W  (K-major)
 //   dgrad     dX = dY W      A = dY (K-major)   B = W  (N-major: tcgen05 "MN-major" operand)

@@ -53,7 +53,7 @@ struct CfnHandle {
   std::vector<GatherRow> gatherA, gatherC;
   float** grads_table_dev;  // (n slots) scratch pointer table for cfn_network_bwd
 
-  // GEMM operands of the layer-by-layer network stage (mlp_fp32.cu): fp32 FMA (gemm_tc = 0) or tcgen05 kind::tf32
+  // GEMM operands of the layer-by-layer network stage (mlp_chain.cu): fp32 FMA (gemm_tc = 0) or tcgen05 kind::tf32
   int gemm_tc;              // 1: contractions run on the tensor cores (every precision mode except CFN_PREC_FP32)
   int gp, gd;               // in_pos / in_dir rounded up to a multiple of 4 (activation / weight column padding)
   float* wg;                // padded operand copy of every weight matrix (tf32-rounded when gemm_tc)
@@ -66,11 +66,11 @@ struct CfnHandle {
 };
 
 namespace cfn {
-// fp32 path (mlp_fp32.cu)
-size_t fp32_workspace_floats(const CfnHandle* h, int64_t n_points, int save);
-int fp32_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts, const float* viewdirs,
+// layer-by-layer chain: check mode, CFN_PREC_TF32 and every training path (mlp_chain.cu)
+size_t chain_workspace_floats(const CfnHandle* h, int64_t n_points, int save);
+int chain_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts, const float* viewdirs,
                      int64_t B, int N, float* flow_params, float* ws, int save, cudaStream_t s);
-int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, float* ws, float* const* grads,
+int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, float* ws, float* const* grads,
                      cudaStream_t s);
 int pack_fp32(CfnHandle* h, const float* const* params, cudaStream_t s);
 

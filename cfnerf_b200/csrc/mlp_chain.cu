@@ -1,4 +1,4 @@
-// CFN_PREC_FP32 network stage: positional encoding (run_nerf_helpers.py:21-69), the 8x512 trunk with skip-concat,
+// The layer-by-layer network stage (K5): positional encoding (run_nerf_helpers.py:21-69), the 8x512 trunk with skip-concat,
 // the conditioning heads (model/models.py:165-186) and the amortised flow parameters (models.py:358-385, done ONCE
 // per point instead of K times), forward with optional saved activations and the full backward (dgrad chain +
 // split-K wgrad).  The contractions run as fp32 CUDA-core FMAs (sgemm.cu) in CFN_PREC_FP32 — the 1e-5 "check" mode
@@ -12,7 +12,7 @@ namespace cfn {
 // ---------------------------------------------------------------------------------------------------
 // workspace layout (floats; M = number of points)
 // ---------------------------------------------------------------------------------------------------
-struct Fp32Layout {
+struct ChainLayout {
   int ld5, ldv, ldg;
   int64_t X5, V, H, v, ha, hr;            // forward
   int64_t P, GP, G1, G2, gv, gh, dAm, dWp;  // saved outputs / backward scratch
@@ -24,8 +24,8 @@ struct Fp32Layout {
 // the tensor-core engine carries relu'(h) from the forward to the dgrad GEMMs as bit masks (needs every ReLU layer on it)
 static bool use_bits(const CfnHandle* h) { return h->gemm_tc && h->cfg.W % 8 == 0; }
 
-static Fp32Layout make_layout(const CfnHandle* h, int64_t M, int save) {
-  Fp32Layout L;
+static ChainLayout make_layout(const CfnHandle* h, int64_t M, int save) {
+  ChainLayout L;
   const int W = h->cfg.W;
   L.ld5 = h->gp + W;          // [gamma(p) | pad to 4 | h]: the h columns start 16-byte aligned
   L.ldv = W + h->gd;          // [feature | gamma(d) | pad to 4]
@@ -62,7 +62,7 @@ static Fp32Layout make_layout(const CfnHandle* h, int64_t M, int save) {
   return L;
 }
 
-size_t fp32_workspace_floats(const CfnHandle* h, int64_t M, int save) {
+size_t chain_workspace_floats(const CfnHandle* h, int64_t M, int save) {
   return (size_t)make_layout(h, M, save).total;
 }
 
@@ -245,7 +245,7 @@ struct LayerIO {
   float* out; int64_t ld_out;
 };
 
-static LayerIO trunk_io(const CfnHandle* h, const Fp32Layout& L, float* ws, int64_t M, int i, int save) {
+static LayerIO trunk_io(const CfnHandle* h, const ChainLayout& L, float* ws, int64_t M, int i, int save) {
   const int W = h->cfg.W;
   auto Hbuf = [&](int j) { return ws + L.H + (int64_t)(save ? j : (j & 1)) * M * W; };
   LayerIO io;
@@ -257,11 +257,11 @@ static LayerIO trunk_io(const CfnHandle* h, const Fp32Layout& L, float* ws, int6
   return io;
 }
 
-int fp32_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts, const float* viewdirs,
+int chain_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts, const float* viewdirs,
                      int64_t B, int N, float* flow_params, float* ws, int save, cudaStream_t s) {
   const int64_t M = B * N;
   const int W = h->cfg.W, D = h->cfg.D, F = h->cfg.F;
-  Fp32Layout L = make_layout(h, M, save);
+  ChainLayout L = make_layout(h, M, save);
   const size_t enc_smem = (size_t)ENC_PTS * ((h->gp | 1) + (h->gd | 1)) * sizeof(float);
   static bool enc_attr = false;
   if (!enc_attr) {
@@ -426,12 +426,12 @@ __global__ void scatter_rows_kernel(const float* __restrict__ dAm, const float* 
   if (gb && threadIdx.x == 0) gb[row] = dAb[r];
 }
 
-int fp32_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, float* ws, float* const* grads,
+int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, float* ws, float* const* grads,
                      cudaStream_t s) {
   const int64_t M = B * N;
   const int W = h->cfg.W, D = h->cfg.D, F = h->cfg.F, PP = h->PP;
   const int ha_n = h->cfg.h_alpha, hr_n = h->cfg.h_rgb;
-  Fp32Layout L = make_layout(h, M, 1);
+  ChainLayout L = make_layout(h, M, 1);
   int rc;
   for (int i = 4; i < (int)h->slots.size(); ++i)
     CFN_CHECK_ARG(grads[i] != nullptr, "cfn_network_bwd: grads[%d] (%s) is null", i, h->slots[i].name.c_str());

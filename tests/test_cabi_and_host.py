@@ -84,3 +84,21 @@ def test_kde_nll_loss_matches_oracle():
     b = O.kde_nll_loss(rgb, tgt, ent, 32, 0.01)
     for k in a:
         assert abs(float(a[k]) - float(b[k])) <= 1e-6 * max(1.0, abs(float(b[k]))), k
+
+
+def test_tf32_gemm_layout_contract_is_checked_on_the_host(lib):
+    """cfn_gemm_f32 engine 1 (TMA-fed tcgen05 GEMM) refuses operand layouts the TMA cannot address — unit stride along
+    one axis, 16-byte aligned bases and row strides — before any CUDA call is made (so this runs without a GPU)."""
+    import ctypes as C
+
+    def call(a_ptr, a_rs, a_cs, b_ptr, b_rs, b_cs, M=64, N=32, K=63, epi=0, split=1):
+        return lib.cfn_gemm_f32(1, C.c_void_p(a_ptr), a_rs, a_cs, C.c_void_p(b_ptr), b_rs, b_cs, C.c_void_p(4096), N,
+                                None, None, 0, M, N, K, epi, 0, split, 0, None)
+
+    assert call(1024, 63, 1, 2048, 32, 1) == -1          # A row stride 63 floats: not a multiple of 16 bytes
+    assert b"not supported" in lib.cfn_last_error()
+    assert call(1028, 64, 1, 2048, 32, 1) == -1          # A base not 16-byte aligned
+    assert call(1024, 64, 2, 2048, 32, 1) == -1          # no unit stride in A
+    assert call(1024, 64, 1, 2048, 32, 1, epi=1) == -1   # ReLU epilogue is only instantiated for K-major B
+    assert call(1024, 64, 1, 2048, 1, 64, split=4) == -1  # split-K (wgrad) needs M-major A and N-major B
+    assert lib.cfn_gemm_f32(2, None, 0, 0, None, 0, 0, None, 0, None, None, 0, 4, 4, 4, 0, 0, 1, 0, None) == -1   # engine id
