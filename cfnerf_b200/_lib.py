@@ -42,6 +42,8 @@ SYMBOLS = {
     "cfn_adam_step_f32": (_i32, [_i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64),
                           C.c_float, C.c_float, C.c_float, C.c_float, _i32, C.c_float, _vp]),
     "cfn_debug_profile": (_i32, [_vp, _vp, _i32]),
+    "cfn_gemm_bf16": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i64,
+                      _i32, _i32, _vp, _vp]),
     "cfn_gemm_f32": (_i32, [_i32, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i64,
                      _i32, _i32, _i32, _i32, _vp]),
 }

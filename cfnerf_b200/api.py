@@ -430,3 +430,26 @@ def gemm(A, B, *, engine="tf32", bias=None, epilogue="none", aux=None, out=None,
                                _ptr(aux) if aux is not None else None, aux_rs, M, N, K, epi, int(accumulate), int(split_k),
                                int(round_out), _stream()), "cfn_gemm_f32")
     return out
+
+
+def gemm_bf16(A, B, *, out_dtype=torch.bfloat16, bias=None, epilogue="none", aux=None, mask_out=None, aux_bits=None,
+              out=None, split_k=1, rowsum=None):
+    """bf16-storage flavour of `gemm` through cfn_gemm_bf16 (tcgen05 kind::f16, fp32 accumulation).  A (M,K), B (K,N)
+    bf16 CUDA tensors with arbitrary strides; C bf16 or fp32.  `mask_out` / `aux_bits`: int32 (M, ceil(N/32)) ReLU bit
+    masks written by epilogue "relu" / read by epilogue "relu_mask_mul"."""
+    lib = _lib.load()
+    M, K = A.shape
+    K2, N = B.shape
+    assert K == K2 and A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda
+    if out is None:
+        out = (torch.zeros if split_k > 1 else torch.empty)(M, N, device=A.device, dtype=out_dtype)
+    epi = {"none": 0, "relu": 1, "tanh_mask": 2, "relu_mask_mul": 3}[epilogue]
+    bits = mask_out if mask_out is not None else aux_bits
+    with torch.cuda.device(A.device):
+        check(lib.cfn_gemm_bf16(_ptr(A), A.stride(0), A.stride(1), _ptr(B), B.stride(0), B.stride(1), _ptr(out),
+                                out.stride(0), int(out.dtype == torch.bfloat16), _ptr(bias) if bias is not None else None,
+                                _ptr(aux) if aux is not None else None, _ptr(mask_out) if mask_out is not None else None,
+                                _ptr(aux_bits) if aux_bits is not None else None, bits.stride(0) if bits is not None else 0,
+                                M, N, K, epi, int(split_k), _ptr(rowsum) if rowsum is not None else None, _stream()),
+              "cfn_gemm_bf16")
+    return out

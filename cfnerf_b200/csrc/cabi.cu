@@ -360,6 +360,25 @@ extern "C" int cfn_gemm_f32(int engine, const float* A, int64_t a_rs, int64_t a_
   return launch_tgemm(g, round_out, (cudaStream_t)stream);
 }
 
+extern "C" int cfn_gemm_bf16(const void* A, int64_t a_rs, int64_t a_cs, const void* B, int64_t b_rs, int64_t b_cs, void* C,
+                             int64_t c_rs, int c_bf16, const float* bias, const float* aux, uint32_t* mask_out,
+                             const uint32_t* aux_bits, int64_t bits_ld, int64_t M, int N, int64_t K, int epilogue,
+                             int split_k, float* rowsum, void* stream) {
+  CFN_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "cfn_gemm_bf16: bad shape");
+  if (M == 0 || N == 0) return CFN_OK;
+  CFN_CHECK_ARG(A && B && C, "cfn_gemm_bf16: null argument");
+  GemmArgs g{};
+  g.A = (const float*)A; g.a_rs = a_rs; g.a_cs = a_cs;
+  g.B = (const float*)B; g.b_rs = b_rs; g.b_cs = b_cs;
+  g.C = (float*)C; g.c_rs = c_rs; g.bias = bias; g.aux = aux; g.aux_rs = 0;
+  g.M = M; g.N = N; g.K = K; g.epilogue = epilogue; g.split_k = split_k;
+  g.mask_out = mask_out; g.aux_bits = aux_bits; g.bits_ld = bits_ld; g.rowsum = rowsum;
+  g.ab_bf16 = 1; g.c_bf16 = c_bf16;
+  CFN_CHECK_ARG(tgemm_supported(g), "cfn_gemm_bf16: operand layout / epilogue flavour not supported");
+  CFN_CHECK_ARG(!rowsum || tgemm_can_rowsum(g), "cfn_gemm_bf16: rowsum needs split_k > 1 and at most one work item per CTA");
+  return launch_tgemm(g, 0, (cudaStream_t)stream);
+}
+
 extern "C" int cfn_kde_nll_f32(const float* rgb_map, const float* target, int64_t B, int K, float grad_scale, float* partial,
                                float* g_rgb_map, void* stream) {
   CFN_CHECK_ARG(B >= 0 && (B == 0 || (rgb_map && target && partial)), "cfn_kde_nll_f32: null argument");

@@ -102,6 +102,9 @@ struct GemmArgs {
   uint32_t* mask_out;
   const uint32_t* aux_bits;
   int64_t bits_ld;
+  // tensor-core engine only: bf16 STORAGE.  ab_bf16: A and B point to __nv_bfloat16 (strides in elements, tcgen05
+  // kind::f16 with bf16 operands); c_bf16: C is written as bf16 (else fp32).  Accumulation is fp32 either way.
+  int ab_bf16, c_bf16;
 };
 int launch_sgemm(const GemmArgs& g, cudaStream_t s);
 // same contract on the tensor cores (tcgen05.mma kind::tf32, TMA-fed; gemm_tf32.cu).  round_out: round the stored

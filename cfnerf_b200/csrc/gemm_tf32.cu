@@ -18,6 +18,7 @@
 // in K1 (warps 0-7 epilogue, 8 TMEM allocator, 10 TMA producer, 11 MMA issuer).
 // Out-of-range rows / columns / K tails are zero-filled by the TMA (the tensor maps carry the logical extents).
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <cstdlib>
 #include <math.h>
@@ -96,15 +97,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu) : "memory");
 }
-template <int CG>
+// DT = 0: fp32 storage, kind::tf32 (K = 8 per instruction); DT = 1: bf16 storage, kind::f16 (K = 16)
+template <int CG, int DT>
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  if (CG == 1)
+  if (CG == 1 && DT == 0)
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-  else
+  else if (CG == 2 && DT == 0)
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  else if (CG == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 template <int CG>
@@ -155,11 +165,16 @@ __device__ __forceinline__ uint64_t desc_hi_kmajor() {
 __device__ __forceinline__ uint64_t desc_hi_mnmajor(uint32_t lbo_bytes) {
   return ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
+// 16-bit operands, MN-major: the ordinary SWIZZLE_128B (type 2), 64-element column blocks `lbo` bytes apart, 8-k-row
+// groups 1024 bytes apart (cute::UMMA::Layout_MN_SW128_Atom)
+__device__ __forceinline__ uint64_t desc_hi_mnmajor16(uint32_t lbo_bytes) {
+  return ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 
 // EPI (compile-time epilogue flavour: one instruction stream per flavour keeps the epilogue loop short enough to unroll)
 enum { TG_PLAIN = 0, TG_RELU = 1, TG_TANH = 2, TG_MASK = 3, TG_ATOMIC = 4 };
 
-template <int CG, bool A_MN, bool B_MN, int EPI>
+template <int CG, bool A_MN, bool B_MN, int EPI, int DT, bool CBF>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -167,6 +182,9 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (smem_base & 1023u) __trap();
   TgBarriers* bars = reinterpret_cast<TgBarriers*>(smem_raw + (size_t)p.stages * p.stage_bytes);
 
+  constexpr int BKE = DT ? 64 : 32;            // elements per 128-byte K block
+  constexpr int MNB = DT ? 64 : 32;            // elements per 128-byte row of an MN-major block
+  constexpr uint32_t MN_BLOCK_BYTES = BKE * 128;   // one MN-major block: BKE k rows of 128 bytes
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int64_t unit0 = blockIdx.x / CG, n_grid_units = gridDim.x / CG;
@@ -181,8 +199,8 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // 2 KB of ones right after the barriers: the B operand of the optional row-sum MMA (any layout of ones is ones)
   const uint32_t ones_addr = smem_base + (uint32_t)p.stages * p.stage_bytes + 1024u;
   if (EPI == TG_ATOMIC && p.rowsum) {
-    float* ones = reinterpret_cast<float*>(smem_raw + (size_t)p.stages * p.stage_bytes + 1024);
-    for (int i = threadIdx.x; i < 512; i += TG_THREADS) ones[i] = 1.0f;
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p.stages * p.stage_bytes + 1024);
+    for (int i = threadIdx.x; i < 512; i += TG_THREADS) ones[i] = DT ? 0x3F803F80u : 0x3F800000u;   // bf16 pairs / fp32
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == TG_W_ALLOC) {
@@ -210,13 +228,13 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     k_begin = (int64_t)z * p.k_per_split;
     int64_t k_end = k_begin + p.k_per_split;
     if (k_end > p.K) k_end = p.K;
-    return (int)((k_end - k_begin + 31) / 32);
+    return (int)((k_end - k_begin + BKE - 1) / BKE);
   };
 
   if (warp == TG_W_TMA) {
     // ================================= TMA producer =================================
     int stage = 0; uint32_t phase = 0;
-    const uint32_t b_tx = B_MN ? (uint32_t)p.b_blocks * 4096u : (uint32_t)p.b_rows_cta * 128u;
+    const uint32_t b_tx = B_MN ? (uint32_t)p.b_blocks * MN_BLOCK_BYTES : (uint32_t)p.b_rows_cta * 128u;
     for (int64_t w = unit0; w < p.n_work; w += n_grid_units) {
       int64_t mt; int nt, z; decode(w, mt, nt, z);
       int64_t k_begin; const int nkb = k_blocks(z, k_begin);
@@ -230,15 +248,15 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           else mbar_arrive_cluster(bar_leader(&bars->full[stage]));
           const uint32_t dstA = smem_base + (uint32_t)stage * p.stage_bytes;
           const uint32_t dstB = dstA + TG_A_BYTES;
-          const int k0 = (int)(k_begin + (int64_t)kb * 32);
+          const int k0 = (int)(k_begin + (int64_t)kb * BKE);
           if (!A_MN) tma_load_2d<CG>(dstA, &tmA, k0, m0, full_bar);
           else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_2d<CG>(dstA + j * 4096, &tmA, m0 + 32 * j, k0, full_bar);
+            for (int j = 0; j < 128 / MNB; ++j) tma_load_2d<CG>(dstA + j * MN_BLOCK_BYTES, &tmA, m0 + MNB * j, k0, full_bar);
           }
           if (!B_MN) tma_load_2d<CG>(dstB, &tmB, k0, n0, full_bar);
           else
-            for (int j = 0; j < p.b_blocks; ++j) tma_load_2d<CG>(dstB + j * 4096, &tmB, n0 + 32 * j, k0, full_bar);
+            for (int j = 0; j < p.b_blocks; ++j) tma_load_2d<CG>(dstB + j * MN_BLOCK_BYTES, &tmB, n0 + MNB * j, k0, full_bar);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -249,12 +267,16 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (rank == 0) {
       int stage = 0; uint32_t phase = 0;
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A/B = tf32 (2), major bits 15 / 16
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+      constexpr uint32_t FMT = DT ? 1u : 2u;   // bf16 : tf32
+      const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
-      const uint64_t a_hi = A_MN ? desc_hi_mnmajor(4096) : desc_hi_kmajor();
-      const uint64_t b_hi = B_MN ? desc_hi_mnmajor(4096) : desc_hi_kmajor();
-      const uint32_t a_step = A_MN ? (1024u >> 4) : (32u >> 4);     // one K = 8 slice: 8 k rows, or 32 bytes along the row
-      const uint32_t b_step = B_MN ? (1024u >> 4) : (32u >> 4);
+      const uint64_t mn_hi = DT ? desc_hi_mnmajor16(MN_BLOCK_BYTES) : desc_hi_mnmajor(MN_BLOCK_BYTES);
+      const uint64_t a_hi = A_MN ? mn_hi : desc_hi_kmajor();
+      const uint64_t b_hi = B_MN ? mn_hi : desc_hi_kmajor();
+      // one MMA K slice (8 tf32 / 16 bf16 elements): 32 bytes along a K-major row, or 8 / 16 k rows of an MN-major block
+      constexpr uint32_t MN_STEP = (DT ? 2048u : 1024u) >> 4;
+      const uint32_t a_step = A_MN ? MN_STEP : (32u >> 4);
+      const uint32_t b_step = B_MN ? MN_STEP : (32u >> 4);
       const uint32_t idesc16 = (idesc & ~(0x3Fu << 17)) | ((16u >> 3) << 17);
       const uint64_t ones_desc = b_hi | (uint64_t)((ones_addr & 0x3FFFFu) >> 4);
       uint32_t it = 0;
@@ -275,11 +297,11 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_tf32<CG>(d_tmem, adesc + (uint64_t)(a_step * ks), bdesc + (uint64_t)(b_step * ks), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+              umma_tf32<CG, DT>(d_tmem, adesc + (uint64_t)(a_step * ks), bdesc + (uint64_t)(b_step * ks), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
             if (EPI == TG_ATOMIC && p.rowsum && nt == 0) {   // columns 256.. are free: a row-sum GEMM owns one work item per CTA (pair)
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_tf32<CG>(tmem_base + 256u, adesc + (uint64_t)(a_step * ks), ones_desc, idesc16, (kb > 0 || ks > 0) ? 1u : 0u);
+                umma_tf32<CG, DT>(tmem_base + 256u, adesc + (uint64_t)(a_step * ks), ones_desc, idesc16, (kb > 0 || ks > 0) ? 1u : 0u);
             }
             umma_commit<CG>(bar_local(&bars->empty[stage]));
           }
@@ -389,7 +411,15 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (EPI == TG_RELU) pos |= (y > 0.f ? 1u : 0u) << i;
               x[i] = y;
             }
-            *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+            if (CBF) {
+              // bf16 output: 4 columns = 8 bytes per lane, a row segment of 64 bytes per 8 lanes
+              __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + gm * p.c_rs + gn) = pk;
+            } else {
+              *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+            }
             if (EPI == TG_RELU && p.mask_out) {
               // relu'(y) of this row's 32 columns packed into one word by the 8 lanes that hold them
               uint32_t word = pos << (4 * (lane & 7));
@@ -432,7 +462,8 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (EPI == TG_MASK) y = (keep & (1u << i)) ? y : 0.f;
                 if (p.round_out) y = round_tf32(y);
                 if (y > 0.f) pos |= 1u << i;
-                cp[i] = y;
+                if (CBF) reinterpret_cast<__nv_bfloat16*>(p.C)[gm * p.c_rs + gn + i] = __float2bfloat16_rn(y);
+                else cp[i] = y;
               }
             }
             if (EPI == TG_RELU && p.mask_out) {
@@ -473,7 +504,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // row-major fp32 matrix (rows x cols, row stride ld floats) -> 2-D map with box {32 floats, box_rows}, SWIZZLE_128B
-int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool mn_major) {
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool mn_major, bool bf16) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -483,11 +514,12 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, in
     fn = (EncodeTiledFn)p;
   }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
+  cuuint32_t box[2] = {bf16 ? 64u : 32u, (cuuint32_t)box_rows};   // 128 bytes along the contiguous axis
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+  // 32-bit MN-major operands need the 32-byte-atom flavour of the 128-byte swizzle; 16-bit ones the ordinary one
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, (mn_major && !bf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -511,10 +543,10 @@ int num_sms() {
   return n;
 }
 
-template <int CG, bool A_MN, bool B_MN, int EPI>
+template <int CG, bool A_MN, bool B_MN, int EPI, int DT = 0, bool CBF = false>
 int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const TgParams& p, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
-  auto kern = tgemm_kernel<CG, A_MN, B_MN, EPI>;
+  auto kern = tgemm_kernel<CG, A_MN, B_MN, EPI, DT, CBF>;
   if (!attr_set) {
     CFN_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
@@ -546,13 +578,23 @@ bool tgemm_supported(const GemmArgs& g) {
   const bool b_k = (g.b_rs == 1), b_mn = (g.b_cs == 1);
   if (!(a_k || a_mn) || !(b_k || b_mn)) return false;
   const int64_t a_ld = a_k ? g.a_rs : g.a_cs, b_ld = b_k ? g.b_cs : g.b_rs;
-  if (a_ld % 4 || b_ld % 4 || a_ld <= 0 || b_ld <= 0) return false;
+  const int epb = g.ab_bf16 ? 8 : 4;   // elements per 16 bytes
+  if (a_ld % epb || b_ld % epb || a_ld <= 0 || b_ld <= 0) return false;
   if (!aligned16(g.A) || !aligned16(g.B)) return false;
+  if (g.c_bf16 && !g.ab_bf16) return false;
   // instantiated (operand majors x epilogue) combinations: what the network stage issues
   const bool atomic = g.split_k > 1;
   const bool a_mn_ = !a_k, b_mn_ = !b_k;
   const bool plain = !atomic && g.epilogue == EPI_NONE && !g.accumulate;
   const bool mask = !atomic && (g.epilogue == EPI_RELU_MASK_MUL || (g.epilogue == EPI_NONE && g.accumulate));
+  if (g.ab_bf16) {
+    // bf16 storage: exactly the flavours of the training chain
+    if (g.accumulate) return false;
+    if (!a_mn_ && !b_mn_) return (plain && g.c_bf16) || (g.epilogue == EPI_RELU && g.c_bf16 && !atomic) || (g.epilogue == EPI_TANH_MASK && !g.c_bf16 && !atomic);
+    if (!a_mn_ && b_mn_) return g.c_bf16 && (plain || (mask && g.aux_bits != nullptr));
+    if (a_mn_ && b_mn_) return atomic && !g.c_bf16;
+    return false;
+  }
   if (!a_mn_ && !b_mn_) return !atomic && (plain || mask || ((g.epilogue == EPI_RELU || g.epilogue == EPI_TANH_MASK) && !g.accumulate));
   if (!a_mn_ && b_mn_) return plain || mask;
   if (a_mn_ && b_mn_) return atomic || plain;
@@ -570,14 +612,16 @@ static void plan_tgemm(const GemmArgs& g, TgParams& p, int& CG, bool& a_mn, bool
   p.C = g.C; p.c_rs = g.c_rs; p.bias = g.bias; p.aux = g.aux; p.aux_rs = g.aux_rs;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.epilogue = g.epilogue; p.accumulate = g.accumulate; p.split_k = g.split_k > 1 ? g.split_k : 1;
-  p.vec_ok = (g.c_rs % 4 == 0) && aligned16(g.C) &&
-             (g.epilogue != EPI_RELU_MASK_MUL || (g.aux_rs % 4 == 0 && aligned16(g.aux)));
+  const int bke = g.ab_bf16 ? 64 : 32;      // elements per 128-byte K block / MN-major row
+  if (g.c_bf16) p.vec_ok = (g.c_rs % 4 == 0) && (((uintptr_t)g.C & 7u) == 0);
+  else p.vec_ok = (g.c_rs % 4 == 0) && aligned16(g.C) &&
+                  (g.epilogue != EPI_RELU_MASK_MUL || g.aux_bits || (g.aux_rs % 4 == 0 && aligned16(g.aux)));
   int bn = (g.N + 15) / 16 * 16;
   if (bn > 256) bn = 256;
   p.bn = bn;
   p.b_rows_cta = bn / CG;
-  p.b_blocks = (p.b_rows_cta + 31) / 32;
-  const int b_bytes = b_mn ? p.b_blocks * 4096 : ((p.b_rows_cta * 128 + 1023) / 1024) * 1024;
+  p.b_blocks = (p.b_rows_cta + bke - 1) / bke;
+  const int b_bytes = b_mn ? p.b_blocks * (bke * 128) : ((p.b_rows_cta * 128 + 1023) / 1024) * 1024;
   p.stage_bytes = TG_A_BYTES + b_bytes;
   int stages = (int)((227 * 1024 - 3072 - TG_STG_BYTES) / p.stage_bytes);
   if (stages > TG_MAX_STAGES) stages = TG_MAX_STAGES;
@@ -585,7 +629,7 @@ static void plan_tgemm(const GemmArgs& g, TgParams& p, int& CG, bool& a_mn, bool
   // split-K (wgrad): the caller pre-zeroes C and every split adds its partial sum with fp32 atomics
   p.atomic = g.split_k > 1 ? 1 : 0;
   int64_t kps = (g.K + p.split_k - 1) / p.split_k;
-  kps = (kps + 31) / 32 * 32;
+  kps = (kps + bke - 1) / bke * bke;
   p.k_per_split = kps;
   p.split_k = (int)((g.K + kps - 1) / kps);   // drop empty splits
   p.m_tiles = (g.M + 128 * CG - 1) / (128 * CG);
@@ -616,11 +660,13 @@ int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s) {
 
   CUtensorMap tmA, tmB;
   int rc;
-  if (!a_mn) rc = make_map(&tmA, g.A, g.M, g.K, g.a_rs, 128, false);
-  else rc = make_map(&tmA, g.A, g.K, g.M, g.a_cs, 32, true);
+  const bool bf = g.ab_bf16 != 0;
+  const int bke = bf ? 64 : 32;
+  if (!a_mn) rc = make_map(&tmA, g.A, g.M, g.K, g.a_rs, 128, false, bf);
+  else rc = make_map(&tmA, g.A, g.K, g.M, g.a_cs, bke, true, bf);
   if (rc) return rc;
-  if (!b_mn) rc = make_map(&tmB, g.B, g.N, g.K, g.b_cs, p.b_rows_cta, false);
-  else rc = make_map(&tmB, g.B, g.K, g.N, g.b_rs, 32, true);
+  if (!b_mn) rc = make_map(&tmB, g.B, g.N, g.K, g.b_cs, p.b_rows_cta, false, bf);
+  else rc = make_map(&tmB, g.B, g.K, g.N, g.b_rs, bke, true, bf);
   if (rc) return rc;
 
   // epilogue flavour (compile-time in the kernel); only the combinations the network stage issues are instantiated,
@@ -632,7 +678,16 @@ int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s) {
   else if (g.epilogue == EPI_RELU_MASK_MUL || g.accumulate) epi = TG_MASK;
 #define TG_LAUNCH(cg, am, bm, e) return launch_variant<cg, am, bm, e>(tmA, tmB, p, smem, s)
 #define TG_BY_CG(am, bm, e) do { if (CG == 1) TG_LAUNCH(1, am, bm, e); else TG_LAUNCH(2, am, bm, e); } while (0)
-  if (!a_mn && !b_mn) {
+#define TG_BF(am, bm, e, cbf) do { if (CG == 1) return launch_variant<1, am, bm, e, 1, cbf>(tmA, tmB, p, smem, s); \
+                                   else return launch_variant<2, am, bm, e, 1, cbf>(tmA, tmB, p, smem, s); } while (0)
+  if (bf) {
+    if (!a_mn && !b_mn && epi == TG_PLAIN && g.c_bf16) TG_BF(false, false, TG_PLAIN, true);
+    if (!a_mn && !b_mn && epi == TG_RELU && g.c_bf16) TG_BF(false, false, TG_RELU, true);
+    if (!a_mn && !b_mn && epi == TG_TANH && !g.c_bf16) TG_BF(false, false, TG_TANH, false);
+    if (!a_mn && b_mn && epi == TG_PLAIN && g.c_bf16) TG_BF(false, true, TG_PLAIN, true);
+    if (!a_mn && b_mn && epi == TG_MASK && g.c_bf16) TG_BF(false, true, TG_MASK, true);
+    if (a_mn && b_mn && epi == TG_ATOMIC && !g.c_bf16) TG_BF(true, true, TG_ATOMIC, false);
+  } else if (!a_mn && !b_mn) {
     if (epi == TG_PLAIN) TG_BY_CG(false, false, TG_PLAIN);
     if (epi == TG_RELU) TG_BY_CG(false, false, TG_RELU);
     if (epi == TG_TANH) TG_BY_CG(false, false, TG_TANH);
@@ -646,6 +701,7 @@ int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s) {
   } else {
     if (epi == TG_PLAIN) TG_BY_CG(true, false, TG_PLAIN);
   }
+#undef TG_BF
 #undef TG_BY_CG
 #undef TG_LAUNCH
   set_error("tgemm: operand-major / epilogue combination not instantiated (a_mn %d, b_mn %d, epilogue %d, split %d)",

@@ -180,6 +180,19 @@ int cfn_gemm_f32(int engine, const float* A, int64_t a_rs, int64_t a_cs, const f
                  float* C, int64_t c_rs, const float* bias, const float* aux, int64_t aux_rs, int64_t M, int N, int64_t K,
                  int epilogue, int accumulate, int split_k, int round_out, void* stream);
 
+
+/* The same primitive with bf16 STORAGE (tensor-core engine only: tcgen05.mma kind::f16, bf16 operands, fp32
+ * accumulation): A and B point to bf16 elements (strides in elements, 16-byte aligned bases / strides), C is bf16
+ * (c_bf16 = 1) or fp32.  epilogue as above; epilogue 1 can also write relu'(C) as a bit mask (mask_out: one 32-bit word
+ * per row and 32 columns, bits_ld words per row) and epilogue 3 reads such a mask (aux_bits) instead of an fp32 aux.
+ * split_k > 1: fp32 atomics into a pre-zeroed fp32 C; rowsum (optional, pre-zeroed, M floats) += sum_k A(m,k).
+ * Instantiated flavours = the ones the training chain issues (else CFN_EINVAL): K-major x K-major {none, ReLU -> bf16;
+ * tanh-mask -> fp32}, K-major x N-major {none, bit-mask -> bf16}, M-major x N-major split-K -> fp32. */
+int cfn_gemm_bf16(const void* A, int64_t a_rs, int64_t a_cs, const void* B, int64_t b_rs, int64_t b_cs, void* C,
+                  int64_t c_rs, int c_bf16, const float* bias, const float* aux, uint32_t* mask_out,
+                  const uint32_t* aux_bits, int64_t bits_ld, int64_t M, int N, int64_t K, int epilogue, int split_k,
+                  float* rowsum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
