@@ -101,6 +101,25 @@ def k1_dram_traffic(points_per_launch: int):
     return tot or None
 
 
+def tgemm_dram_traffic(precision: str, points: int):
+    """DRAM read + write of one trunk-layer forward GEMM of the training step from the committed ncu capture of that
+    precision (first kernel block of the summary); None when there is none for this shape."""
+    path = os.path.join(ROOT, "profiles", "r01_prof_tgemm_fwd_summary.csv" if precision == "tf32" else "r01_prof_tgemm_bf16_summary.csv")
+    if not os.path.isfile(path) or points != 524288:
+        return None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, blocks = 0.0, 0
+    for line in open(path):
+        if line.startswith("##"):
+            blocks += 1
+            if blocks > 1:
+                break
+        f = line.strip().split(",")
+        if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(f[2]) * mult.get(f[1], 1.0)
+    return tot or None
+
+
 def host_threads() -> int:
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -179,7 +198,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[2])")
     ap.add_argument("--train-rays", type=int, default=4096, help="rays per GPU per optimisation step")
-    ap.add_argument("--train-precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--train-precision", default="bf16", choices=["bf16", "tf32", "fp32"],
+                    help="GEMM engine of the training leg: bf16 storage + kind::f16 (BASELINE configs[2] wording), "
+                         "tf32 over fp32 storage, or the fp32 CUDA-core check engine")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -312,26 +333,36 @@ def main():
         barrier()
         train_ms = te0.elapsed_time(te1)
 
-    # roofline of the training GEMMs (HBM-bound by their fp32 storage): one trunk-layer forward GEMM on the step's shape
-    # (points x W x W, bias + ReLU + tf32 rounding) timed alone with CUDA events; algorithmic bytes = X in + Y out
+    # roofline of the training GEMMs (HBM-bound by their activation traffic): one trunk-layer forward GEMM on the step's
+    # shape (points x W x W, bias + ReLU + ReLU bit mask) timed alone with CUDA events; algorithmic bytes = X in + Y out
     tg_ms = 0.0
-    if not args.no_train and args.train_precision == "tf32" and rank == 0:
+    if not args.no_train and args.train_precision in ("tf32", "bf16") and rank == 0:
         Mp = t_rays.shape[0] * N_SAMPLES
-        Xg = torch.randn(Mp, cfg.W, device=dev)
-        Wg = torch.randn(cfg.W, cfg.W, device=dev) * 0.05
+        bf = args.train_precision == "bf16"
+        dt = torch.bfloat16 if bf else torch.float32
+        Xg = torch.randn(Mp, cfg.W, device=dev).to(dt)
+        Wg = (torch.randn(cfg.W, cfg.W, device=dev) * 0.05).to(dt)
         bg = torch.randn(cfg.W, device=dev)
-        Yg = torch.empty(Mp, cfg.W, device=dev)
+        Yg = torch.empty(Mp, cfg.W, device=dev, dtype=dt)
+        mb = torch.zeros(Mp, (cfg.W + 31) // 32, dtype=torch.int32, device=dev)
+
+        def one_gemm():
+            if bf:
+                cf.gemm_bf16(Xg, Wg.t(), bias=bg, epilogue="relu", mask_out=mb, out=Yg)
+            else:
+                cf.gemm(Xg, Wg.t(), engine="tf32", bias=bg, epilogue="relu", out=Yg, round_out=True)
+
         for _ in range(3):
-            cf.gemm(Xg, Wg.t(), engine="tf32", bias=bg, epilogue="relu", out=Yg, round_out=True)
+            one_gemm()
         torch.cuda.synchronize()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(10):
-            cf.gemm(Xg, Wg.t(), engine="tf32", bias=bg, epilogue="relu", out=Yg, round_out=True)
+            one_gemm()
         g1.record()
         torch.cuda.synchronize()
         tg_ms = g0.elapsed_time(g1) / 10
-        del Xg, Yg
+        del Xg, Yg, mb
     barrier()
 
     t = torch.tensor([ms, e2e_ms, k1_ms, train_ms], dtype=torch.float64, device=dev)
@@ -374,18 +405,21 @@ def main():
                 "value": n_t * world / step_s, "unit": "rays/s", "ms_per_step": step_s * 1e3, "rays_per_gpu": n_t,
                 "precision": args.train_precision, "loss": float(t_out["loss"]),
                 "achieved_tflops_per_gpu": n_t * N_SAMPLES * FLOP_PER_POINT * 3 / step_s / 1e12,
-                "note": "forward + backward + Adam through cfnerf_b200.dist.train_step; GEMMs = TMA-fed tcgen05 kind::tf32 "
-                        "(fp32 storage) when precision is tf32, CUDA-core fp32 FMA when fp32; flops = 3 x forward GEMM flops"}
+                "note": "forward + backward + Adam through cfnerf_b200.dist.train_step; GEMMs = TMA-fed tcgen05: kind::f16 over "
+                        "bf16-stored activations / gradients (bf16), kind::tf32 over fp32 storage (tf32), or CUDA-core fp32 "
+                        "FMA (fp32); fp32 accumulation, master weights and weight gradients throughout; flops = 3 x forward"}
             if tg_ms > 0:
                 Mp = n_t * N_SAMPLES
-                gb = 2.0 * Mp * cfg.W * 4 / 1e9            # activations in + out (the 1 MB weight matrix is L2-resident)
+                esz = 2 if args.train_precision == "bf16" else 4
+                gb = 2.0 * Mp * cfg.W * esz / 1e9          # activations in + out (the weight matrix is L2-resident)
                 hbm = peaks.get("hbm_gbs", 6545.9)
                 line["train_step"]["roofline"] = {
                     "bound": "hbm", "achieved": gb / (tg_ms * 1e-3), "peak": hbm, "unit": "GB/s",
-                    "frac": gb / (tg_ms * 1e-3) / hbm, "traffic": 2146472000.0,
-                    "traffic_note": "DRAM read + write of this GEMM from profiles/r01_prof_tgemm_fwd_summary.csv (ncu --set "
-                                    "full) at 524288 points; algorithmic bytes = 2 x points x 512 x 4 = 2.147e9",
-                    "kernel": "tgemm_kernel<2,K,K,relu> (one trunk-layer forward GEMM of the training step)",
+                    "frac": gb / (tg_ms * 1e-3) / hbm, "traffic": tgemm_dram_traffic(args.train_precision, Mp),
+                    "traffic_note": "DRAM read + write of this GEMM from the committed ncu --set full capture "
+                                    "(profiles/r01_prof_tgemm_*_summary.csv) at 524288 points; algorithmic bytes = "
+                                    f"2 x points x 512 x {esz} = {2 * 524288 * 512 * esz:.4g}",
+                    "kernel": "tgemm_kernel (one trunk-layer forward GEMM of the training step: bias + ReLU + bit mask)",
                     "ms": tg_ms, "tflops": 2.0 * Mp * cfg.W * cfg.W / (tg_ms * 1e-3) / 1e12}
         if not args.no_cpu_baseline:
             v, cores = cpu_reference_rays_per_s(args.cpu_rays, 2)

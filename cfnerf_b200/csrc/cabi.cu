@@ -62,8 +62,13 @@ extern "C" int cfn_create(const CfnConfig* cfg, CfnHandle** out) {
     if (!strcmp(e, "fp32")) h->gemm_tc = 0;
     if (!strcmp(e, "tf32")) h->gemm_tc = 1;
   }
-  h->gp = (h->in_pos + 3) & ~3;
-  h->gd = (h->in_dir + 3) & ~3;
+  h->gp = (h->in_pos + 7) & ~7;
+  h->gd = (h->in_dir + 7) & ~7;
+  // bf16 storage of the layer-by-layer chain (training in CFN_PREC_BF16): every row stride / column offset must be a
+  // multiple of 8 elements (16 bytes); other widths keep the fp32-storage tf32 chain
+  h->chain_bf16 = (h->gemm_tc && cfg->precision == CFN_PREC_BF16 && cfg->W % 16 == 0 && cfg->h_alpha % 8 == 0 &&
+                   cfg->h_rgb % 8 == 0) ? 1 : 0;
+  if (const char* e = getenv("CFN_TRAIN_GEMM")) if (!strcmp(e, "tf32") || !strcmp(e, "fp32")) h->chain_bf16 = 0;
   h->wg = h->amA_g = h->amC_g = nullptr;
   const int W = cfg->W, F = cfg->F;
   add_slot(h, "alpha_mean", 1, 1);
@@ -122,8 +127,8 @@ extern "C" int cfn_create(const CfnConfig* cfg, CfnHandle** out) {
       const bool skip_in = h->skip >= 0 && (int)i == h->s_pts(h->skip + 1, 0);
       v.gap_at = skip_in ? h->in_pos : sl.cols;
       v.gap = skip_in ? h->gp - h->in_pos : 0;
-      v.ld = (sl.cols + v.gap + 3) & ~3;
-      h->wg_floats += (int64_t)sl.rows * v.ld;
+      v.ld = (sl.cols + v.gap + 7) & ~7;
+      h->wg_floats += (int64_t)sl.rows * v.ld / (h->chain_bf16 ? 2 : 1);
     }
     h->wv.push_back(v);
   }

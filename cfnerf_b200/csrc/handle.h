@@ -55,11 +55,13 @@ struct CfnHandle {
 
   // GEMM operands of the layer-by-layer network stage (mlp_chain.cu): fp32 FMA (gemm_tc = 0) or tcgen05 kind::tf32
   int gemm_tc;              // 1: contractions run on the tensor cores (every precision mode except CFN_PREC_FP32)
-  int gp, gd;               // in_pos / in_dir rounded up to a multiple of 4 (activation / weight column padding)
-  float* wg;                // padded operand copy of every weight matrix (tf32-rounded when gemm_tc)
+  int chain_bf16;           // 1 (CFN_PREC_BF16): activations, gradients and operand weights of the chain are stored as bf16
+                            //   (tcgen05 kind::f16); 0: fp32 storage (kind::tf32 when gemm_tc, fp32 FMA otherwise)
+  int gp, gd;               // in_pos / in_dir rounded up to a multiple of 8 (activation / weight column padding)
+  float* wg;                // padded operand copy of every weight matrix (tf32-rounded fp32, or bf16 when chain_bf16)
   int64_t wg_floats;
   std::vector<WView> wv;    // per slot (biases: p = nullptr)
-  std::vector<int64_t> wg_offset;
+  std::vector<int64_t> wg_offset;   // in 4-byte slots
   float* amA_g; float* amC_g;   // operand copies of amA / amC (tf32-rounded when gemm_tc, else aliases)
 
   cfn::TcPlan* tc;   // nullptr in fp32 mode

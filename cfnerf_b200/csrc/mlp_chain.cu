@@ -5,6 +5,8 @@
 // — and as TMA-fed tcgen05 kind::tf32 GEMMs (gemm_tf32.cu) in every other mode: that is the training path of the
 // bf16 / fp16 modes and the whole network stage of CFN_PREC_TF32.  In the tensor-core flavour every buffer that is a
 // later GEMM's operand (activations, gradients, weights) is stored ROUNDED to tf32, because the tensor core truncates.
+#include <cuda_bf16.h>
+
 #include "handle.h"
 
 namespace cfn {
@@ -12,8 +14,12 @@ namespace cfn {
 // ---------------------------------------------------------------------------------------------------
 // workspace layout (floats; M = number of points)
 // ---------------------------------------------------------------------------------------------------
+// Buffers that hold activations / gradients are addressed in ELEMENTS (fp32, or bf16 when h->chain_bf16) through
+// float* bases: `at(base, n)` advances by n elements (n is always a multiple of 8 in bf16 mode), region sizes are in
+// 4-byte slots.
 struct ChainLayout {
   int ld5, ldv, ldg;
+  int gpa, ldGP;                            // gradient of the flow record: [3F | pad to 8 | 15F | pad to 8]
   int64_t X5, V, H, v, ha, hr;            // forward
   int64_t P, GP, G1, G2, gv, gh, dAm, dWp;  // saved outputs / backward scratch
   int64_t MB, mbv; int bw, bwv;             // ReLU bit masks of the trunk layers / the view layer (words per row)
@@ -30,27 +36,31 @@ static ChainLayout make_layout(const CfnHandle* h, int64_t M, int save) {
   L.ld5 = h->gp + W;          // [gamma(p) | pad to 4 | h]: the h columns start 16-byte aligned
   L.ldv = W + h->gd;          // [feature | gamma(d) | pad to 4]
   L.ldg = L.ld5 > L.ldv ? L.ld5 : L.ldv;
-  const int wc = W + ((h->cfg.h_alpha + 3) & ~3);   // [g_feat | g_h_alpha] rows of the fused head dgrad
+  const int wc = W + ((h->cfg.h_alpha + 7) & ~7);   // [g_feat | g_h_alpha] rows of the fused head dgrad
   if (wc > L.ldg) L.ldg = wc;
+  L.gpa = (3 * h->cfg.F + 7) & ~7;
+  L.ldGP = L.gpa + ((15 * h->cfg.F + 7) & ~7);
   L.nH = save ? h->cfg.D : 2;
+  const int e = h->chain_bf16 ? 2 : 1;              // elements per 4-byte slot
   int64_t o = 0;
-  auto take = [&](int64_t n) { int64_t r = o; o += (n + 3) & ~(int64_t)3; return r; };
-  L.X5 = take(M * L.ld5);
-  L.V = take(M * L.ldv);
-  L.H = take((int64_t)L.nH * M * W);
-  L.v = take(M * (W / 2));
-  L.ha = take(M * h->cfg.h_alpha);
-  L.hr = take(M * h->cfg.h_rgb);
+  auto take = [&](int64_t n) { int64_t r = o; o += (n + 3) & ~(int64_t)3; return r; };   // n 4-byte slots
+  auto take_e = [&](int64_t n) { return take((n + e - 1) / e); };                        // n elements
+  L.X5 = take_e(M * L.ld5);
+  L.V = take_e(M * L.ldv);
+  L.H = take_e((int64_t)L.nH * M * W);
+  L.v = take_e(M * (W / 2));
+  L.ha = take_e(M * h->cfg.h_alpha);
+  L.hr = take_e(M * h->cfg.h_rgb);
   L.P = L.GP = L.G1 = L.G2 = L.gv = L.gh = L.dAm = L.dWp = L.MB = L.mbv = 0;
   L.bw = (W + 31) / 32; L.bwv = (W / 2 + 31) / 32;
   if (save) {
     L.P = take(M * h->PP);
-    L.GP = take(M * h->PP);
-    L.G1 = take(M * L.ldg);
-    L.G2 = take(M * L.ldg);
-    L.gv = take(M * (W / 2));
+    L.GP = take_e(M * L.ldGP);
+    L.G1 = take_e(M * L.ldg);
+    L.G2 = take_e(M * L.ldg);
+    L.gv = take_e(M * (W / 2));
     int hm = h->cfg.h_alpha > h->cfg.h_rgb ? h->cfg.h_alpha : h->cfg.h_rgb;
-    L.gh = take(M * hm);
+    L.gh = take_e(M * hm);
     L.dAm = take((int64_t)h->PP * (hm + 1));
     L.dWp = take((int64_t)W * (h->gp + W + 4));   // padded weight gradient of the odd-width layers
     if (use_bits(h)) {
@@ -61,6 +71,9 @@ static ChainLayout make_layout(const CfnHandle* h, int64_t M, int save) {
   L.total = o;
   return L;
 }
+
+static inline float* at(const CfnHandle* h, float* base, int64_t elems) { return base + (h->chain_bf16 ? elems / 2 : elems); }
+static inline const float* at(const CfnHandle* h, const float* base, int64_t elems) { return base + (h->chain_bf16 ? elems / 2 : elems); }
 
 size_t chain_workspace_floats(const CfnHandle* h, int64_t M, int save) {
   return (size_t)make_layout(h, M, save).total;
@@ -85,6 +98,12 @@ __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
 }
 
+// element store of an operand buffer: mode 0 = fp32 as is, 1 = fp32 rounded to tf32, 2 = bf16
+__device__ __forceinline__ void store_elem(float* base, int64_t idx, float v, int mode) {
+  if (mode == 2) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+  else base[idx] = (mode == 1) ? round_tf32(v) : v;
+}
+
 // n_pos / n_dir: padded widths (pad columns are written as zeros); round: store tf32-rounded values.
 // One thread encodes one point into shared memory; the block then writes the rows out with consecutive lanes on
 // consecutive columns (the rows are 2304 bytes apart in X5: per-thread row stores would touch 32 lines per instruction).
@@ -92,7 +111,7 @@ constexpr int ENC_PTS = 128, ENC_MAXW = 104;   // up to multires 16: 3 + 6*16 = 
 __global__ void __launch_bounds__(ENC_PTS)
 encode_kernel(const float* __restrict__ rays, const float* __restrict__ z_vals, const float* __restrict__ pts,
               const float* __restrict__ viewdirs, int64_t M, int N, int L_pos, int L_dir, float* __restrict__ X5, int ld5,
-              float* __restrict__ Vd, int ldv, int n_pos, int n_dir, int round) {
+              float* __restrict__ Vd, int ldv, int n_pos, int n_dir, int mode) {
   extern __shared__ float enc_smem[];
   const int lp = n_pos | 1, ldd = n_dir | 1;            // odd row strides: conflict-free per-thread rows
   float* sp = enc_smem;
@@ -125,12 +144,12 @@ encode_kernel(const float* __restrict__ rays, const float* __restrict__ z_vals, 
   for (int i = threadIdx.x; i < rows * n_pos; i += ENC_PTS) {
     const int r = i / n_pos, c = i - r * n_pos;
     const float v = sp[r * lp + c];
-    X5[(m0 + r) * ld5 + c] = round ? round_tf32(v) : v;
+    store_elem(X5, (m0 + r) * ld5 + c, v, mode);
   }
   for (int i = threadIdx.x; i < rows * n_dir; i += ENC_PTS) {
     const int r = i / n_dir, c = i - r * n_dir;
     const float v = sd[r * ldd + c];
-    Vd[(m0 + r) * ldv + c] = round ? round_tf32(v) : v;
+    store_elem(Vd, (m0 + r) * ldv + c, v, mode);
   }
 }
 
@@ -140,18 +159,19 @@ struct RepackTable {
   int rows[64], cols[64], ld[64], gap_at[64], gap[64];
   int n;
 };
-__global__ void repack_weights_kernel(const float* __restrict__ w32, float* __restrict__ wg, RepackTable t, int round) {
+__global__ void repack_weights_kernel(const float* __restrict__ w32, float* __restrict__ wg, RepackTable t, int mode) {
   const int s = blockIdx.y;
   const int64_t n = (int64_t)t.rows[s] * t.cols[s];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / t.cols[s]), c = (int)(i % t.cols[s]);
     const float v = w32[t.src[s] + i];
-    wg[t.dst[s] + (int64_t)r * t.ld[s] + c + (c >= t.gap_at[s] ? t.gap[s] : 0)] = round ? round_tf32(v) : v;
+    // dst is in 4-byte slots: an element index in the buffer's own type
+    store_elem(wg, t.dst[s] * (mode == 2 ? 2 : 1) + (int64_t)r * t.ld[s] + c + (c >= t.gap_at[s] ? t.gap[s] : 0), v, mode);
   }
 }
-__global__ void round_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+__global__ void round_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int mode) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = round_tf32(src[i]);
+  if (i < n) store_elem(dst, i, src[i], mode);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -200,11 +220,12 @@ int pack_fp32(CfnHandle* h, const float* const* params, cudaStream_t s) {
       rt.rows[k] = h->slots[i].rows; rt.cols[k] = h->slots[i].cols;
       rt.ld[k] = h->wv[i].ld; rt.gap_at[k] = h->wv[i].gap_at; rt.gap[k] = h->wv[i].gap;
     }
-    repack_weights_kernel<<<dim3(64, rt.n), 256, 0, s>>>(h->w32, h->wg, rt, h->gemm_tc);
+    const int mode = h->chain_bf16 ? 2 : (h->gemm_tc ? 1 : 0);
+    repack_weights_kernel<<<dim3(64, rt.n), 256, 0, s>>>(h->w32, h->wg, rt, mode);
     if (h->gemm_tc) {
       const int na = 3 * h->cfg.F * h->cfg.h_alpha, nc = 15 * h->cfg.F * h->cfg.h_rgb;
-      round_copy_kernel<<<(na + 255) / 256, 256, 0, s>>>(h->amA, h->amA_g, na);
-      round_copy_kernel<<<(nc + 255) / 256, 256, 0, s>>>(h->amC, h->amC_g, nc);
+      round_copy_kernel<<<(na + 255) / 256, 256, 0, s>>>(h->amA, h->amA_g, na, mode);
+      round_copy_kernel<<<(nc + 255) / 256, 256, 0, s>>>(h->amC, h->amC_g, nc, mode);
     }
   }
   CFN_LAUNCH_CHECK();
@@ -213,6 +234,11 @@ int pack_fp32(CfnHandle* h, const float* const* params, cudaStream_t s) {
 
 // the contraction engine of this handle
 static int gemm(const CfnHandle* h, const GemmArgs& g, int round_out, cudaStream_t s) {
+  if (g.ab_bf16) {
+    CFN_CHECK_ARG(tgemm_supported(g), "bf16 chain: GEMM flavour not available (M %lld N %d K %lld epilogue %d split %d)",
+                  (long long)g.M, g.N, (long long)g.K, g.epilogue, g.split_k);
+    return launch_tgemm(g, 0, s);
+  }
   if (h->gemm_tc && tgemm_supported(g)) return launch_tgemm(g, round_out, s);
   return launch_sgemm(g, s);   // fp32 mode, or a shape the TMA path cannot address (e.g. an odd flow-record width)
 }
@@ -236,6 +262,7 @@ static int linear_fwd(const CfnHandle* h, int slot, const float* X, int64_t ldx,
   g.M = M; g.N = w.rows; g.K = v.ld;
   g.epilogue = epi; g.accumulate = 0; g.split_k = 1;
   g.mask_out = mask_out; g.bits_ld = bits_ld;
+  g.ab_bf16 = g.c_bf16 = h->chain_bf16;
   if (mask_out) CFN_CHECK_ARG(tgemm_supported(g), "linear_fwd: ReLU bit masks need the tensor-core engine");
   return gemm(h, g, 1, s);
 }
@@ -247,12 +274,12 @@ struct LayerIO {
 
 static LayerIO trunk_io(const CfnHandle* h, const ChainLayout& L, float* ws, int64_t M, int i, int save) {
   const int W = h->cfg.W;
-  auto Hbuf = [&](int j) { return ws + L.H + (int64_t)(save ? j : (j & 1)) * M * W; };
+  auto Hbuf = [&](int j) { return at(h, ws + L.H, (int64_t)(save ? j : (j & 1)) * M * W); };
   LayerIO io;
   if (i == 0) { io.in = ws + L.X5; io.ld_in = L.ld5; }
   else if (h->skip >= 0 && i == h->skip + 1) { io.in = ws + L.X5; io.ld_in = L.ld5; }
   else { io.in = Hbuf(i - 1); io.ld_in = W; }
-  if (h->skip >= 0 && i == h->skip) { io.out = ws + L.X5 + h->gp; io.ld_out = L.ld5; }
+  if (h->skip >= 0 && i == h->skip) { io.out = at(h, ws + L.X5, h->gp); io.ld_out = L.ld5; }
   else { io.out = Hbuf(i); io.ld_out = W; }
   return io;
 }
@@ -269,8 +296,8 @@ int chain_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, cons
     enc_attr = true;
   }
   encode_kernel<<<(unsigned)((M + ENC_PTS - 1) / ENC_PTS), ENC_PTS, enc_smem, s>>>(
-      rays, z_vals, pts, viewdirs, M, N, h->cfg.L_pos, h->cfg.L_dir, ws + L.X5, L.ld5, ws + L.V + W, L.ldv, h->gp, h->gd,
-      h->gemm_tc);
+      rays, z_vals, pts, viewdirs, M, N, h->cfg.L_pos, h->cfg.L_dir, ws + L.X5, L.ld5, at(h, ws + L.V, W), L.ldv, h->gp, h->gd,
+      h->chain_bf16 ? 2 : (h->gemm_tc ? 1 : 0));
   CFN_LAUNCH_CHECK();
   int rc;
   LayerIO last{};
@@ -295,6 +322,7 @@ int chain_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, cons
     g.B = h->amA_g; g.b_rs = 1; g.b_cs = h->cfg.h_alpha;
     g.C = flow_params; g.c_rs = h->PP;
     g.bias = h->amA_b; g.aux = h->tanh_flags; g.aux_rs = 0;
+    g.ab_bf16 = h->chain_bf16; g.c_bf16 = 0;       // the flow records stay fp32
     g.M = M; g.N = 3 * F; g.K = h->cfg.h_alpha; g.epilogue = EPI_TANH_MASK; g.split_k = 1;
     if ((rc = gemm(h, g, 0, s))) return rc;
     g.A = ws + L.hr; g.a_rs = h->cfg.h_rgb;
@@ -312,12 +340,14 @@ int chain_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, cons
 // backward
 // ---------------------------------------------------------------------------------------------------
 __global__ void tanh_bwd_kernel(const float* __restrict__ g, const float* __restrict__ p, const float* __restrict__ flags,
-                                float* __restrict__ out, int64_t total, int PP, int round) {
+                                float* __restrict__ out, int64_t total, int PP, int n_alpha, int gpa, int ldGP, int mode) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const float pv = p[i];
-  const float v = flags[i % PP] != 0.f ? g[i] * (1.0f - pv * pv) : g[i];
-  out[i] = round ? round_tf32(v) : v;
+  const int c = (int)(i % PP);
+  const float v = flags[c] != 0.f ? g[i] * (1.0f - pv * pv) : g[i];
+  // record column c -> [alpha block | pad | rgb block] so that both blocks start 16-byte aligned in either storage type
+  store_elem(out, (i / PP) * ldGP + (c < n_alpha ? c : gpa + c - n_alpha), v, mode);
 }
 
 // out[n] += sum over a slab of rows of g[m*ld + n]   (out pre-zeroed)
@@ -350,6 +380,8 @@ static int wgrad(const CfnHandle* h, const float* G, int64_t ldg, int out_f, con
   g.B = X; g.b_rs = ldx; g.b_cs = 1;        // B(k=pt, n=i) = X[pt*ldx + i]
   g.C = dW; g.c_rs = in_f;
   g.M = out_f; g.N = in_f; g.K = M;
+  g.ab_bf16 = h->chain_bf16; g.c_bf16 = 0;   // weight gradients are fp32
+  g.split_k = 2;                             // (so that tgemm_supported sees the split-K flavour)
   int64_t split;
   if (h->gemm_tc && tgemm_supported(g)) {
     // one K slice per CTA (pair): (m tiles x n tiles x splits) ~ number of SMs (pairs)
@@ -371,6 +403,9 @@ static int wgrad(const CfnHandle* h, const float* G, int64_t ldg, int out_f, con
     if (h->gemm_tc && tgemm_can_rowsum(g)) {
       CFN_CUDA(cudaMemsetAsync(db, 0, (size_t)out_f * sizeof(float), s));
       g.rowsum = db;
+    } else if (h->chain_bf16) {
+      set_error("bf16 chain: the bias gradient could not be fused into the wgrad (out %d in %d)", out_f, in_f);
+      return CFN_ESTATE;
     } else {
       int rc = colsum(G, ldg, M, out_f, db, s);
       if (rc) return rc;
@@ -405,10 +440,11 @@ static int dgrad(const CfnHandle* h, int slot, const float* Gout, int64_t ldgo, 
   const WView& v = h->wv[slot];
   GemmArgs g{};
   g.A = Gout; g.a_rs = ldgo; g.a_cs = 1;
-  g.B = v.p + col0 + (col0 >= v.gap_at ? v.gap : 0); g.b_rs = v.ld; g.b_cs = 1;   // B(k=o, n=i) = W[o*ld + col0' + i]
+  g.B = at(h, v.p, col0 + (col0 >= v.gap_at ? v.gap : 0)); g.b_rs = v.ld; g.b_cs = 1;   // B(k=o, n=i) = W[o*ld + col0' + i]
   g.C = Gin; g.c_rs = ldgi;
   g.aux = mask; g.aux_rs = ld_mask;
   g.aux_bits = mask ? mask_bits : nullptr; g.bits_ld = bits_ld;
+  g.ab_bf16 = g.c_bf16 = h->chain_bf16;
   g.M = M; g.N = n_cols; g.K = w.rows;
   g.epilogue = mask ? EPI_RELU_MASK_MUL : EPI_NONE;
   g.accumulate = accumulate; g.split_k = 1;
@@ -442,10 +478,13 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
   {
     int64_t total = M * PP;
     tanh_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g_flow_params, ws + L.P, h->tanh_flags, ws + L.GP,
-                                                                    total, PP, h->gemm_tc);
+                                                                    total, PP, 3 * F, L.gpa, L.ldGP,
+                                                                    h->chain_bf16 ? 2 : (h->gemm_tc ? 1 : 0));
     CFN_LAUNCH_CHECK();
   }
-  const float* GP = ws + L.GP;
+  const float* GPa = ws + L.GP;                   // gradient w.r.t. the alpha block of the (pre-tanh) flow record
+  const float* GPc = at(h, ws + L.GP, L.gpa);     // ... and the rgb block
+  const int ldGP = L.ldGP;
   LayerIO last = trunk_io(h, L, ws, M, D - 1, 1);
   const float* h7 = last.out;
   const int64_t ld7 = last.ld_out;
@@ -457,9 +496,9 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
   const bool bits = use_bits(h);
   // fused head dgrad: needs W_halpha stored right behind W_feat in the operand buffer with the same row stride
   const bool fuse_heads = h->wv[h->s_feat].ld == W && h->wv[h->s_halpha].ld == W &&
-                          h->wv[h->s_halpha].p == h->wv[h->s_feat].p + (int64_t)W * W;
-  const int64_t ld_g2 = fuse_heads ? W + ((ha_n + 3) & ~3) : W;
-  float* gha = fuse_heads ? G2 + W : gh;                 // g_h_alpha lives in columns W.. of the g_feat rows when fused
+                          h->wv[h->s_halpha].p == at(h, h->wv[h->s_feat].p, (int64_t)W * W);
+  const int64_t ld_g2 = fuse_heads ? W + ((ha_n + 7) & ~7) : W;
+  float* gha = fuse_heads ? at(h, G2, W) : gh;                 // g_h_alpha lives in columns W.. of the g_feat rows when fused
   const int64_t ld_gha = fuse_heads ? ld_g2 : ha_n;
   const uint32_t* mbv = bits ? reinterpret_cast<const uint32_t*>(ws + L.mbv) : nullptr;
   auto MBl = [&](int layer) -> const uint32_t* {
@@ -478,14 +517,15 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
   // 2. alpha conditioning branch
   {
     // gathered dAmA = GP[:, :3F]^T ha ; bias = colsum
-    if ((rc = wgrad(h, GP, PP, 3 * F, ws + L.ha, ha_n, ha_n, M, dAm, dAb, s))) return rc;
+    if ((rc = wgrad(h, GPa, ldGP, 3 * F, ws + L.ha, ha_n, ha_n, M, dAm, dAb, s))) return rc;
     scatter_rows_kernel<<<3 * F, 64, 0, s>>>(dAm, dAb, ha_n, h->gatherA_dev, 3 * F, table);
     CFN_LAUNCH_CHECK();
     // g_ha = GP[:, :3F] amA
     GemmArgs g{};
-    g.A = GP; g.a_rs = PP; g.a_cs = 1;
+    g.A = GPa; g.a_rs = ldGP; g.a_cs = 1;
     g.B = h->amA_g; g.b_rs = ha_n; g.b_cs = 1;
     g.C = gha; g.c_rs = ld_gha; g.M = M; g.N = ha_n; g.K = 3 * F; g.split_k = 1;
+    g.ab_bf16 = g.c_bf16 = h->chain_bf16;
     if ((rc = gemm(h, g, 1, s))) return rc;
     if ((rc = wgrad_slot(h, h->s_halpha, gha, ld_gha, h7, ld7, M, grads[h->s_halpha], grads[h->s_halpha + 1], dWp, s))) return rc;
     // g_h7 (unmasked, first contribution) = g_ha W_halpha  -- or, fused, left for the K-concatenated GEMM of step 3
@@ -493,13 +533,14 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
   }
   // 3. rgb conditioning branch
   {
-    if ((rc = wgrad(h, GP + 3 * F, PP, 15 * F, ws + L.hr, hr_n, hr_n, M, dAm, dAb, s))) return rc;
+    if ((rc = wgrad(h, GPc, ldGP, 15 * F, ws + L.hr, hr_n, hr_n, M, dAm, dAb, s))) return rc;
     scatter_rows_kernel<<<15 * F, 64, 0, s>>>(dAm, dAb, hr_n, h->gatherC_dev, 15 * F, table);
     CFN_LAUNCH_CHECK();
     GemmArgs g{};
-    g.A = GP + 3 * F; g.a_rs = PP; g.a_cs = 1;
+    g.A = GPc; g.a_rs = ldGP; g.a_cs = 1;
     g.B = h->amC_g; g.b_rs = hr_n; g.b_cs = 1;
     g.C = gh; g.c_rs = hr_n; g.M = M; g.N = hr_n; g.K = 15 * F; g.split_k = 1;
+    g.ab_bf16 = g.c_bf16 = h->chain_bf16;
     if ((rc = gemm(h, g, 1, s))) return rc;
     if ((rc = wgrad_slot(h, h->s_hrgb, gh, hr_n, ws + L.v, W / 2, M, grads[h->s_hrgb], grads[h->s_hrgb + 1], dWp, s))) return rc;
     // g_v = (g_hr W_hrgb) * relu'(v)
@@ -518,6 +559,7 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
       g.aux = h7; g.aux_rs = ld7; g.aux_bits = MBl(D - 1); g.bits_ld = L.bw;
       g.M = M; g.N = W; g.K = W + ha_n;
       g.epilogue = EPI_RELU_MASK_MUL; g.split_k = 1;
+      g.ab_bf16 = g.c_bf16 = h->chain_bf16;
       if ((rc = gemm(h, g, 1, s))) return rc;
     } else {
       // g_h7 = (g_h7 + g_feat W_feat) * relu'(h7)

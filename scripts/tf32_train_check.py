@@ -17,7 +17,7 @@ for kw, B in ((dict(), 64), (dict(W=256, K=64, h_alpha=32), 33), (dict(D=7, W=12
     t_rand = torch.rand(B, 128, generator=g).to(dev)
     ea, er = torch.randn(cfg.K, 1, generator=g).to(dev), torch.randn(cfg.K, 3, generator=g).to(dev)
     res = {}
-    for prec in ("fp32", "tf32"):
+    for prec in ("fp32", "tf32", "bf16"):
         net = cf.NeRFFlowsParams.from_oracle_params(cfg, p, sa, sr).to(dev)
         o_test = cf.render_rays(rays, net, None, 128, False, False, precision=prec)
         out = cf.render_rays(rays, net, None, 128, True, False, perturb=1., raw_noise_std=1., t_rand=t_rand, eps_alpha=ea,
@@ -26,18 +26,19 @@ for kw, B in ((dict(), 64), (dict(W=256, K=64, h_alpha=32), 33), (dict(D=7, W=12
         net.zero_grad()
         l["loss"].backward()
         res[prec] = dict(test=o_test, out=out, loss=float(l["loss"]), grads={n: q.grad.clone() for n, q in net.named_parameters() if q.grad is not None})
-    a, b = res["fp32"], res["tf32"]
-    print("config", kw, "B", B)
-    for k in ("rgb_map", "depth_map"):
-        print("  test  %-10s max abs diff %.3e" % (k, (a["test"][k] - b["test"][k]).abs().max().item()))
-        print("  train %-10s max abs diff %.3e" % (k, (a["out"][k] - b["out"][k]).abs().max().item()))
-    print("  loss fp32 %.6f tf32 %.6f" % (a["loss"], b["loss"]))
-    worst = 0.0
-    for n in a["grads"]:
-        ga, gb = a["grads"][n].double(), b["grads"][n].double()
-        na = ga.norm().item()
-        rel = (ga - gb).norm().item() / max(na, 1e-30)
-        worst = max(worst, rel if na > 0 else 0.0)
-        if rel > 5e-3 or not torch.isfinite(gb).all():
-            print("  grad %-36s |g| %.3e rel l2 err %.3e" % (n, na, rel))
-    print("  worst grad rel l2 err %.3e" % worst, flush=True)
+    for other in ("tf32", "bf16"):
+        a, b = res["fp32"], res[other]
+        print("config", kw, "B", B, "fp32 vs", other)
+        for k in ("rgb_map", "depth_map"):
+            print("  train %-10s max abs diff %.3e" % (k, (a["out"][k] - b["out"][k]).abs().max().item()))
+        print("  loss fp32 %.6f other %.6f" % (a["loss"], b["loss"]))
+        worst, wname = 0.0, ""
+        for n in a["grads"]:
+            ga, gb = a["grads"][n].double(), b["grads"][n].double()
+            na = ga.norm().item()
+            rel = (ga - gb).norm().item() / max(na, 1e-30)
+            if na > 0 and rel > worst:
+                worst, wname = rel, n
+            if not torch.isfinite(gb).all():
+                print("  NON-FINITE grad", n)
+        print("  worst grad rel l2 err %.3e (%s)" % (worst, wname), flush=True)

@@ -1,6 +1,7 @@
 """BASELINE.json configs[2]: one training step (render -> K-mean -> KDE-NLL + 0.01*entropy -> backward ->
 gradient all-reduce -> Adam) on a 4096-ray global batch, data-parallel over the ranks of torchrun.
-CFN_TRAIN_PRECISION selects the GEMM engine of the step: fp32 (CUDA-core FMA) or tf32 (tcgen05 kind::tf32, default)."""
+CFN_TRAIN_PRECISION selects the GEMM engine of the step: bf16 (bf16 storage, tcgen05 kind::f16; default), tf32 (fp32
+storage, tcgen05 kind::tf32) or fp32 (CUDA-core FMA check engine)."""
 import json
 import os
 import sys
@@ -22,7 +23,7 @@ dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 GLOBAL = int(os.environ.get("CFN_TRAIN_RAYS", "4096"))
-PREC = os.environ.get("CFN_TRAIN_PRECISION", "tf32")
+PREC = os.environ.get("CFN_TRAIN_PRECISION", "bf16")
 steps, warm = 5, 2
 cfg = O.CfnConfig()
 net = cf.NeRFFlowsParams.from_oracle_params(cfg, O.make_params(cfg, 0), *O.make_latents(cfg, 0)).to(dev)

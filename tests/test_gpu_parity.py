@@ -378,7 +378,7 @@ def test_install_behind_reference_render(cf, dev):
         np.testing.assert_allclose(x.cpu().numpy(), y.numpy(), rtol=2e-6, atol=4e-6)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_training_steps_track_the_oracle(cf, dev, precision):
     """PSNR after a fixed number of optimisation steps (north star: within 0.1 dB of the reference path).  Same
     weights, rays, targets, noise draws and Adam on both sides; the CUDA path on the GPU, the oracle (autograd on the
@@ -698,11 +698,15 @@ def test_tf32_gemm_rejects_unaligned_operands(cf, dev):
     assert torch.allclose(cf.gemm(A, B, engine="fp32"), A @ B, atol=1e-4)
 
 
+@pytest.mark.parametrize("tc_prec,tol_map,tol_grad", [("tf32", TOL_TC, 8e-2), ("bf16", 4e-3, 2.5e-1)])
 @pytest.mark.parametrize("kw,B", [(dict(), 48), (dict(W=256, K=64, h_alpha=32), 33), (dict(D=7, W=128, F=3), 17)])
-def test_training_step_tensor_core_vs_fp32_path(cf, dev, kw, B):
-    """The tf32 tensor-core training path against the fp32 check path of the same library on the same inputs: forward
-    maps at the 2e-3 bar, loss, and every parameter gradient (relative L2; the early trunk layers see the rounding of
-    the whole dgrad chain).  F=3 makes the flow-record width (54) unaligned: those GEMMs fall back to the CUDA cores."""
+def test_training_step_tensor_core_vs_fp32_path(cf, dev, kw, B, tc_prec, tol_map, tol_grad):
+    """The tensor-core training paths (tf32 GEMMs over fp32 storage; bf16 storage + kind::f16 GEMMs) against the fp32
+    check path of the same library on the same inputs: forward maps, loss, and every parameter gradient (relative L2;
+    the early trunk layers see the rounding of the whole dgrad chain and heavy cancellation in the sum over points).
+    The bf16 chain rounds h_alpha / h_rgb before the amortisation GEMMs (K1 composes them), so its train-mode depth
+    moves by up to 3e-3 absolute (depth is O(1..8)); its acceptance bar is the PSNR test above.  F=3 exercises an odd
+    flow-record width (54)."""
     cfg = O.CfnConfig(**kw)
     p = O.make_params(cfg, 3, "lively")
     sa, sr = O.make_latents(cfg, 3)
@@ -712,7 +716,7 @@ def test_training_step_tensor_core_vs_fp32_path(cf, dev, kw, B):
     t_rand = torch.rand(B, 128, generator=g).to(dev)
     ea, er = torch.randn(cfg.K, 1, generator=g).to(dev), torch.randn(cfg.K, 3, generator=g).to(dev)
     res = {}
-    for prec in ("fp32", "tf32"):
+    for prec in ("fp32", tc_prec):
         net = make_net(cf, cfg, p, sa, sr, dev)
         out = cf.render_rays(rays, net, None, 128, True, False, perturb=1., raw_noise_std=1., t_rand=t_rand, eps_alpha=ea,
                              eps_rgb=er, precision=prec)
@@ -720,13 +724,56 @@ def test_training_step_tensor_core_vs_fp32_path(cf, dev, kw, B):
         net.zero_grad()
         l["loss"].backward()
         res[prec] = (out, float(l["loss"]), {n: q.grad.clone() for n, q in net.named_parameters() if q.grad is not None})
-    (oa, la, ga), (ob, lb, gb) = res["fp32"], res["tf32"]
+    (oa, la, ga), (ob, lb, gb) = res["fp32"], res[tc_prec]
     for k in ("rgb_map", "depth_map"):
-        assert (oa[k] - ob[k]).abs().max().item() <= TOL_TC, k
+        assert (oa[k] - ob[k]).abs().max().item() <= tol_map, k
     assert abs(la - lb) <= 2e-3 * max(1.0, abs(la))
     assert set(ga) == set(gb)
     for n in ga:
         na = ga[n].double().norm().item()
         err = (ga[n].double() - gb[n].double()).norm().item()
         assert torch.isfinite(gb[n]).all(), n
-        assert err <= 8e-2 * na + 1e-9, f"grad {n}: |g| {na:.3e}, |diff| {err:.3e}"
+        assert err <= tol_grad * na + 1e-9, f"grad {n}: |g| {na:.3e}, |diff| {err:.3e}"
+
+
+def test_bf16_storage_tensor_core_gemm_vs_torch(cf, dev):
+    """cfn_gemm_bf16: every flavour the bf16 training chain issues, against fp64 on the same bf16 operands; the ReLU
+    bit mask written by the forward flavour is exactly (output > 0) and drives the dgrad flavour."""
+    bf = torch.bfloat16
+    g = torch.Generator().manual_seed(3)
+    rn = lambda *sh: torch.randn(*sh, generator=g).to(dev)
+    for (M, N, K) in [(128, 16, 64), (300, 104, 72), (3000, 512, 576)]:
+        A, W = rn(M, K).to(bf), rn(N, K).to(bf)
+        ref = A.double() @ W.double().t()
+        sc = max(1.0, ref.abs().max().item())
+        assert (cf.gemm_bf16(A, W.t()).double() - ref).abs().max().item() <= 6e-3 * sc
+        bias = rn(N)
+        bits = torch.zeros(M, (N + 31) // 32, dtype=torch.int32, device=dev)
+        Y = cf.gemm_bf16(A, W.t(), bias=bias, epilogue="relu", mask_out=bits)
+        assert (Y.double() - (ref + bias.double()).clamp_min(0)).abs().max().item() <= 6e-3 * sc
+        cols = torch.arange(N, device=dev)
+        got = ((bits[:, cols // 32] >> (cols % 32)[None, :]) & 1).bool()
+        assert torch.equal(got, Y.float() > 0)
+        flags = (torch.rand(N, generator=g) > 0.5).float().to(dev)
+        T = cf.gemm_bf16(A, W.t(), bias=bias, epilogue="tanh_mask", aux=flags, out_dtype=torch.float32)
+        reft = torch.where(flags.bool()[None, :], torch.tanh(ref + bias.double()), ref + bias.double())
+        assert (T.double() - reft).abs().max().item() <= 2e-5 * sc
+        G = rn(M, N).to(bf)
+        refd = G.double() @ W.double()
+        scd = max(1.0, refd.abs().max().item())
+        assert (cf.gemm_bf16(G, W).double() - refd).abs().max().item() <= 6e-3 * scd
+        act = rn(M, K)
+        kc = torch.arange(K, device=dev)
+        abits = torch.zeros(M, (K + 31) // 32, dtype=torch.int32, device=dev)
+        for w in range((K + 31) // 32):
+            sel = kc[(kc // 32) == w]
+            abits[:, w] = ((act[:, sel] > 0).int() << (sel % 32)[None, :]).sum(1).int()
+        D_ = cf.gemm_bf16(G, W, epilogue="relu_mask_mul", aux_bits=abits)
+        assert (D_.double() - torch.where(act > 0, refd, torch.zeros_like(refd))).abs().max().item() <= 6e-3 * scd
+    for (Of, If, P, split) in [(512, 576, 20000, 12), (64, 512, 15000, 74), (16, 64, 3000, 5)]:
+        G, X = rn(P, Of).to(bf), rn(P, If).to(bf)
+        rs = torch.zeros(Of, device=dev)
+        dW = cf.gemm_bf16(G.t(), X, out_dtype=torch.float32, split_k=split, rowsum=rs)
+        ref = G.double().t() @ X.double()
+        assert (dW.double() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+        assert (rs.double() - G.double().sum(0)).abs().max().item() <= 2e-5 * max(1.0, G.double().sum(0).abs().max().item())
