@@ -28,12 +28,15 @@
 namespace cfn {
 namespace {
 
-constexpr int TG_THREADS = 384;
-constexpr int TG_W_ALLOC = 8, TG_W_TMA = 10, TG_W_MMA = 11;
+// warps: 4 * EPW epilogue warps (EPW per TMEM lane quarter), then allocator, (spare), TMA producer, MMA issuer.
+// fp32 storage: EPW = 2 (the MMAs of a tile take 8192 cycles, two warps per quarter drain it in time);
+// bf16 storage: EPW = 4 (4096 cycles per tile: with two warps per quarter the epilogue, not the MMA, set the tile time)
+__host__ __device__ constexpr int tg_epw(int dt) { return dt ? 4 : 2; }
+__host__ __device__ constexpr int tg_threads(int dt) { return (4 * tg_epw(dt) + 4) * 32; }
 constexpr int TG_MAX_STAGES = 6;
 constexpr int TG_A_BYTES = 128 * 128;   // 128 rows x 32 floats
 constexpr int TG_STG_LD = 36;           // floats per row of an epilogue staging tile (32 + 4: conflict-free float4 rows)
-constexpr int TG_STG_BYTES = 8 * 32 * TG_STG_LD * 4;   // one 32 x 32 tile per epilogue warp
+__host__ __device__ constexpr int tg_stg_bytes(int dt) { return 4 * tg_epw(dt) * 32 * TG_STG_LD * 4; }   // one 32 x 32 tile per epilogue warp
 
 struct TgParams {
   float* C; int64_t c_rs;
@@ -175,13 +178,15 @@ __device__ __forceinline__ uint64_t desc_hi_mnmajor16(uint32_t lbo_bytes) {
 enum { TG_PLAIN = 0, TG_RELU = 1, TG_TANH = 2, TG_MASK = 3, TG_ATOMIC = 4 };
 
 template <int CG, bool A_MN, bool B_MN, int EPI, int DT, bool CBF>
-__global__ void __launch_bounds__(TG_THREADS, 1)
+__global__ void __launch_bounds__(tg_threads(DT), 1)
 tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();
   TgBarriers* bars = reinterpret_cast<TgBarriers*>(smem_raw + (size_t)p.stages * p.stage_bytes);
 
+  constexpr int EPW = tg_epw(DT), TG_THREADS = tg_threads(DT);
+  constexpr int TG_W_ALLOC = 4 * EPW, TG_W_TMA = 4 * EPW + 2, TG_W_MMA = 4 * EPW + 3;
   constexpr int BKE = DT ? 64 : 32;            // elements per 128-byte K block
   constexpr int MNB = DT ? 64 : 32;            // elements per 128-byte row of an MN-major block
   constexpr uint32_t MN_BLOCK_BYTES = BKE * 128;   // one MN-major block: BKE k rows of 128 bytes
@@ -193,7 +198,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TG_MAX_STAGES; ++s) { mbar_init(bar_local(&bars->full[s]), CG); mbar_init(bar_local(&bars->empty[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_local(&bars->acc_full[b]), 1); mbar_init(bar_local(&bars->acc_empty[b]), 8 * CG); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_local(&bars->acc_full[b]), 1); mbar_init(bar_local(&bars->acc_empty[b]), 4 * EPW * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // 2 KB of ones right after the barriers: the B operand of the optional row-sum MMA (any layout of ones is ones)
@@ -312,7 +317,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 4 * EPW) {
     // ================================= epilogue warps =================================
     const int q = warp & 3, hh = warp >> 2;
     float* stg = reinterpret_cast<float*>(smem_raw + (size_t)p.stages * p.stage_bytes + 3072) + warp * (32 * TG_STG_LD);
@@ -340,12 +345,12 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       };
       if (use_bits) {
         if (hh < n_chunks) pb1 = load_bits(hh);
-        if (hh + 2 < n_chunks) pb2 = load_bits(hh + 2);
+        if (hh + EPW < n_chunks) pb2 = load_bits(hh + EPW);
       }
       mbar_wait(bar_local(&bars->acc_full[buf]), (it >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = hh; c < n_chunks; c += 2) {
+      for (int c = hh; c < n_chunks; c += EPW) {
         // phase 1: this warp's 32 x 32 accumulator block, TMEM -> registers (thread = row) -> padded shared-memory tile
         {
           uint32_t v[32];
@@ -360,7 +365,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t curb = pb1;
         if (use_bits) {
           pb1 = pb2;
-          if (c + 4 < n_chunks) pb2 = load_bits(c + 4);
+          if (c + 2 * EPW < n_chunks) pb2 = load_bits(c + 2 * EPW);
         }
         // phase 2: 8 lanes per row, 4 rows per instruction: every global access of the warp is 4 full 128-byte lines
         const int gn = n_tile0 + c * 32 + c4;
@@ -555,7 +560,7 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const TgParam
   if (units > p.n_work) units = p.n_work;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(units * CG));
-  cfg.blockDim = dim3(TG_THREADS);
+  cfg.blockDim = dim3(tg_threads(DT));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -623,7 +628,8 @@ static void plan_tgemm(const GemmArgs& g, TgParams& p, int& CG, bool& a_mn, bool
   p.b_blocks = (p.b_rows_cta + bke - 1) / bke;
   const int b_bytes = b_mn ? p.b_blocks * (bke * 128) : ((p.b_rows_cta * 128 + 1023) / 1024) * 1024;
   p.stage_bytes = TG_A_BYTES + b_bytes;
-  int stages = (int)((227 * 1024 - 3072 - TG_STG_BYTES) / p.stage_bytes);
+  const int stg_bytes = tg_stg_bytes(g.ab_bf16 ? 1 : 0);
+  int stages = (int)((227 * 1024 - 3072 - stg_bytes) / p.stage_bytes);
   if (stages > TG_MAX_STAGES) stages = TG_MAX_STAGES;
   p.stages = stages;
   // split-K (wgrad): the caller pre-zeroes C and every split adds its partial sum with fp32 atomics
@@ -635,7 +641,7 @@ static void plan_tgemm(const GemmArgs& g, TgParams& p, int& CG, bool& a_mn, bool
   p.m_tiles = (g.M + 128 * CG - 1) / (128 * CG);
   p.n_tiles = (g.N + bn - 1) / bn;
   p.n_work = p.m_tiles * p.n_tiles * p.split_k;
-  smem = (size_t)p.stages * p.stage_bytes + 3072 + TG_STG_BYTES;   // ring | barriers (1 KB) | ones (2 KB) | staging tiles
+  smem = (size_t)p.stages * p.stage_bytes + 3072 + stg_bytes;   // ring | barriers (1 KB) | ones (2 KB) | staging tiles
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each allocates all 512 TMEM columns
 }
 
