@@ -410,17 +410,26 @@ def main():
                         "FMA (fp32); fp32 accumulation, master weights and weight gradients throughout; flops = 3 x forward"}
             if tg_ms > 0:
                 Mp = n_t * N_SAMPLES
-                esz = 2 if args.train_precision == "bf16" else 4
+                bf = args.train_precision == "bf16"
+                esz = 2 if bf else 4
                 gb = 2.0 * Mp * cfg.W * esz / 1e9          # activations in + out (the weight matrix is L2-resident)
+                tf = 2.0 * Mp * cfg.W * cfg.W / (tg_ms * 1e-3) / 1e12
                 hbm = peaks.get("hbm_gbs", 6545.9)
-                line["train_step"]["roofline"] = {
-                    "bound": "hbm", "achieved": gb / (tg_ms * 1e-3), "peak": hbm, "unit": "GB/s",
-                    "frac": gb / (tg_ms * 1e-3) / hbm, "traffic": tgemm_dram_traffic(args.train_precision, Mp),
+                tpeak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+                # arithmetic intensity W / esz FLOP per byte: 256 (bf16 storage, above the 209 FLOP/B ridge of this part:
+                # tensor-bound) or 128 (fp32 storage: HBM-bound)
+                roof = ({"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                         "hbm_gbs": gb / (tg_ms * 1e-3), "hbm_frac": gb / (tg_ms * 1e-3) / hbm} if bf else
+                        {"bound": "hbm", "achieved": gb / (tg_ms * 1e-3), "peak": hbm, "unit": "GB/s",
+                         "frac": gb / (tg_ms * 1e-3) / hbm, "tflops": tf})
+                roof.update({
+                    "traffic": tgemm_dram_traffic(args.train_precision, Mp),
                     "traffic_note": "DRAM read + write of this GEMM from the committed ncu --set full capture "
                                     "(profiles/r01_prof_tgemm_*_summary.csv) at 524288 points; algorithmic bytes = "
                                     f"2 x points x 512 x {esz} = {2 * 524288 * 512 * esz:.4g}",
                     "kernel": "tgemm_kernel (one trunk-layer forward GEMM of the training step: bias + ReLU + bit mask)",
-                    "ms": tg_ms, "tflops": 2.0 * Mp * cfg.W * cfg.W / (tg_ms * 1e-3) / 1e12}
+                    "ms": tg_ms})
+                line["train_step"]["roofline"] = roof
         if not args.no_cpu_baseline:
             v, cores = cpu_reference_rays_per_s(args.cpu_rays, 2)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",

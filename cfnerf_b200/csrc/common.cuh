@@ -107,7 +107,7 @@ struct GemmArgs {
   int ab_bf16, c_bf16;
 };
 int launch_sgemm(const GemmArgs& g, cudaStream_t s);
-// same contract on the tensor cores (tcgen05.mma kind::tf32, TMA-fed; gemm_tf32.cu).  round_out: round the stored
+// same contract on the tensor cores (tcgen05.mma kind::tf32, TMA-fed; gemm_tc.cu).  round_out: round the stored
 // outputs to the tf32 grid (they are the next GEMM's operands).
 bool tgemm_supported(const GemmArgs& g);
 int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s);

@@ -1,21 +1,25 @@
-// K5-TC — general strided GEMM on the 5th-generation tensor cores with fp32 storage (tcgen05.mma kind::tf32).
+// K5-TC — general strided GEMM on the 5th-generation tensor cores, TMA-fed, fp32 accumulation in TMEM.
 //
 //   C(m,n) = epi( [C(m,n) +] sum_k A(m,k) B(k,n) + bias[n] )        (same contract as sgemm.cu's launch_sgemm)
 //
+// Two storage flavours of the operands (template parameter DT):
+//   DT = 0  fp32 storage, tcgen05.mma kind::tf32 (K = 8 per instruction)   — CFN_PREC_TF32 and the tf32 training chain
+//   DT = 1  bf16 storage, tcgen05.mma kind::f16  (K = 16 per instruction)  — the bf16 training chain (CFN_PREC_BF16)
 // This is the contraction of the TRAINING path (forward with saved activations, dgrad chain, split-K wgrad;
 // reference: loss.backward() through model/models.py:165-186, run_nerf_uncertainty_NF.py:1065-1067) and of the
-// CFN_PREC_TF32 render mode.  Operands stay fp32 in HBM exactly where mlp_chain.cu's orchestration keeps them, so
-// the three GEMM flavours of a Linear need no transposed copies:
+// CFN_PREC_TF32 render mode.  Operands stay row-major in HBM exactly where mlp_chain.cu's orchestration keeps them,
+// so the three GEMM flavours of a Linear need no transposed copies:
 //   forward   Y = X W^T      A = X  (K-major)   B = W  (K-major)
 //   dgrad     dX = dY W      A = dY (K-major)   B = W  (N-major: tcgen05 "MN-major" operand)
 //   wgrad     dW = dY^T X    A = dY (M-major)   B = X  (N-major), K = points, split over CTAs, fp32 atomics
-// Both majors are fed by the same TMA tensor maps over the row-major buffers (SWIZZLE_128B boxes of 32 floats);
-// only the shared-memory matrix descriptor and the instruction descriptor's major bits differ.
+// Both majors are fed by the same kind of TMA tensor map over the row-major buffers (boxes with 128 contiguous bytes);
+// only the shared-memory matrix descriptor and the instruction descriptor's major bits differ.  MN-major layouts:
+// 32-bit operands need SWIZZLE_128B_BASE32B (TMA 128B_ATOM_32B), 16-bit operands the ordinary SWIZZLE_128B.
 //
 // Structure: persistent CTAs (or CTA pairs, cta_group::2: M = 256 rows per pair, each CTA stages half of B), tiles
 // of 128 x bn (bn <= 256) accumulated in TMEM, TWO accumulator buffers (2 x 256 columns) so the epilogue of tile i
-// overlaps the MMAs of tile i+1; a ring of TMA stages (A 16 KB + B <= 32 KB per 32-float K block); warp roles as
-// in K1 (warps 0-7 epilogue, 8 TMEM allocator, 10 TMA producer, 11 MMA issuer).
+// overlaps the MMAs of tile i+1; a ring of TMA stages (A 16 KB + B <= 32 KB per 128-byte K block); warp roles:
+// 4 * EPW epilogue warps (EPW = 2 for fp32 storage, 4 for bf16), TMEM allocator, TMA producer, MMA issuer.
 // Out-of-range rows / columns / K tails are zero-filled by the TMA (the tensor maps carry the logical extents).
 #include <cuda.h>
 #include <cuda_bf16.h>

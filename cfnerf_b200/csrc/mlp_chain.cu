@@ -2,7 +2,7 @@
 // the conditioning heads (model/models.py:165-186) and the amortised flow parameters (models.py:358-385, done ONCE
 // per point instead of K times), forward with optional saved activations and the full backward (dgrad chain +
 // split-K wgrad).  The contractions run as fp32 CUDA-core FMAs (sgemm.cu) in CFN_PREC_FP32 — the 1e-5 "check" mode
-// — and as TMA-fed tcgen05 kind::tf32 GEMMs (gemm_tf32.cu) in every other mode: that is the training path of the
+// — and as TMA-fed tcgen05 kind::tf32 GEMMs (gemm_tc.cu) in every other mode: that is the training path of the
 // bf16 / fp16 modes and the whole network stage of CFN_PREC_TF32.  In the tensor-core flavour every buffer that is a
 // later GEMM's operand (activations, gradients, weights) is stored ROUNDED to tf32, because the tensor core truncates.
 #include <cuda_bf16.h>

@@ -171,7 +171,7 @@ int cfn_debug_profile(CfnHandle* h, uint64_t* out_host, int n);
 
 /* The dense contraction primitive of the network stage, exposed for unit tests and micro-benchmarks:
  *   C(m,n) = epi( [C(m,n) +] sum_k A[m*a_rs + k*a_cs] * B[k*b_rs + n*b_cs] + bias[n] )      (fp32 storage)
- * engine 0: CUDA-core fp32 FMA (sgemm.cu); engine 1: tcgen05.mma kind::tf32 fed by TMA (gemm_tf32.cu; needs unit stride
+ * engine 0: CUDA-core fp32 FMA (sgemm.cu); engine 1: tcgen05.mma kind::tf32 fed by TMA (gemm_tc.cu; needs unit stride
  * along one axis of each operand and 16-byte aligned bases / strides, else CFN_EINVAL).
  * epilogue: 0 none, 1 ReLU, 2 tanh where aux[n] != 0, 3 zero where aux[m*aux_rs + n] <= 0.  split_k > 1: partial sums
  * are added atomically into a pre-zeroed C (no bias / epilogue).  round_out (engine 1): round outputs to tf32.

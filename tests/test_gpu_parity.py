@@ -634,7 +634,7 @@ def test_large_ragged_batch_tensor_core_vs_fp32(cf, dev):
 
 
 # ------------------------------------------------------------------------------------------------
-# the TF32 tensor-core GEMM (gemm_tf32.cu) and the training path built on it
+# the TF32 tensor-core GEMM (gemm_tc.cu) and the training path built on it
 # ------------------------------------------------------------------------------------------------
 def _tf32_round(x):
     i = x.view(torch.int32)
