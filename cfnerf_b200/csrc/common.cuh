@@ -97,7 +97,8 @@ struct GemmArgs {
   int split_k;                          // >1: atomicAdd partial sums into a pre-zeroed C (no bias/epilogue)
   float* rowsum;                        // tensor-core engine, split_k > 1 only: rowsum[m] += sum_k A(m,k) (pre-zeroed; the bias
                                         // gradient of a wgrad, produced by one extra N=16 MMA against a tile of ones)
-  // tensor-core engine only: ReLU derivative as a bit mask, one word per row and 32 output columns (bits_ld words/row).
+  // tensor-core engine only: ReLU derivative as a bit mask, one word per row and 32 output columns (bits_ld words/row;
+  // column n of the chunk sits at bit 8 * (n % 4) + (n % 32) / 4 — the order the epilogue's warp votes produce).
   // EPI_RELU writes it (mask_out); EPI_RELU_MASK_MUL reads it (aux_bits) instead of the fp32 aux, 32x fewer bytes.
   uint32_t* mask_out;
   const uint32_t* aux_bits;

@@ -55,7 +55,7 @@ struct TgParams {
   int64_t n_work;      // m_tiles * n_tiles * split_k
   int stages; int stage_bytes;
   float* rowsum;       // optional (atomic GEMMs): rowsum[m] += sum_k A(m,k)
-  uint32_t* mask_out;  // optional (EPI_RELU): bit n of word [m][n / 32] = output (m, n) > 0
+  uint32_t* mask_out;  // optional (EPI_RELU): word [m][n / 32], bit 8 * (n % 4) + (n % 32) / 4 = output (m, n) > 0
   const uint32_t* aux_bits;   // optional (EPI_RELU_MASK_MUL): the same words, read instead of the fp32 aux
   int64_t bits_ld;     // words per row of either
 };
@@ -389,6 +389,8 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const bool block_inside = p.vec_ok && (tile_m0 + q * 32 + 31 < p.M) && (n_tile0 + c * 32 + 31 < p.N);
         if (block_inside) {
           // ---- fast path: the whole 32 x 32 block is inside the matrix and 16-byte addressable ----
+          const uint32_t sel_row = (uint32_t)sub_r | ((uint32_t)(4 + sub_r) << 4);   // byte sub_r of each vote pair
+          uint32_t* mask_row = (EPI == TG_RELU && p.mask_out) ? p.mask_out + gm0 * p.bits_ld + ((n_tile0 + c * 32) >> 5) : nullptr;
 #pragma unroll 4
           for (int t = 0; t < 8; ++t) {
             const int r = t * 4 + sub_r;
@@ -400,24 +402,22 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(cp), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
               continue;
             }
-            uint32_t keep = 0xFu;
+            uint32_t keep = 0x01010101u;   // relu'(h) of column slot i at bit 8 * i
             if (EPI == TG_MASK) {
-              if (use_bits) keep = __shfl_sync(0xffffffffu, curb, r) >> (4 * (lane & 7));
+              if (use_bits) keep = __shfl_sync(0xffffffffu, curb, r) >> (lane & 7);
               else if (p.epilogue == EPI_RELU_MASK_MUL) {
                 const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.aux + gm * p.aux_rs + gn));
-                keep = (t4.x > 0.f ? 1u : 0u) | (t4.y > 0.f ? 2u : 0u) | (t4.z > 0.f ? 4u : 0u) | (t4.w > 0.f ? 8u : 0u);
+                keep = (t4.x > 0.f ? 1u : 0u) | (t4.y > 0.f ? 0x100u : 0u) | (t4.z > 0.f ? 0x10000u : 0u) | (t4.w > 0.f ? 0x1000000u : 0u);
               }
               if (p.accumulate) { const float4 t4 = *reinterpret_cast<const float4*>(cp); x[0] += t4.x; x[1] += t4.y; x[2] += t4.z; x[3] += t4.w; }
             }
-            uint32_t pos = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               float y = x[i] + b4[i];
               if (EPI == TG_RELU) y = fmaxf(y, 0.f);
               if (EPI == TG_TANH) { if (tanh_nib & (1u << i)) y = tanhf(y); }
-              if (EPI == TG_MASK) y = (keep & (1u << i)) ? y : 0.f;
+              if (EPI == TG_MASK) y = (keep & (1u << (8 * i))) ? y : 0.f;
               if (p.round_out) y = round_tf32(y);
-              if (EPI == TG_RELU) pos |= (y > 0.f ? 1u : 0u) << i;
               x[i] = y;
             }
             if (CBF) {
@@ -430,12 +430,13 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
             }
             if (EPI == TG_RELU && p.mask_out) {
-              // relu'(y) of this row's 32 columns packed into one word by the 8 lanes that hold them
-              uint32_t word = pos << (4 * (lane & 7));
-              word |= __shfl_xor_sync(0xffffffffu, word, 1);
-              word |= __shfl_xor_sync(0xffffffffu, word, 2);
-              word |= __shfl_xor_sync(0xffffffffu, word, 4);
-              if ((lane & 7) == 0) p.mask_out[gm * p.bits_ld + ((n_tile0 + c * 32) >> 5)] = word;
+              // relu'(y) of this row's 32 columns as one word: four warp votes (one per column slot) hold the bits of all
+              // four rows of this instruction; three byte permutes pick this row's byte of each.  Layout (private to the
+              // forward / dgrad pair): bit 8 * i + l of the word = column 4 * l + i of the 32-column chunk.
+              const uint32_t v0 = __ballot_sync(0xffffffffu, x[0] > 0.f), v1 = __ballot_sync(0xffffffffu, x[1] > 0.f);
+              const uint32_t v2 = __ballot_sync(0xffffffffu, x[2] > 0.f), v3 = __ballot_sync(0xffffffffu, x[3] > 0.f);
+              const uint32_t word = __byte_perm(__byte_perm(v0, v1, sel_row), __byte_perm(v2, v3, sel_row), 0x5410);
+              if ((lane & 7) == 0) mask_row[(int64_t)t * 4 * p.bits_ld] = word;
             }
           }
         } else {
@@ -451,13 +452,13 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             float* cp = p.C + gm * p.c_rs + gn;
             uint32_t pos = 0;
             if (ok) {
-              uint32_t keep = 0xFu;
+              uint32_t keep = 0x01010101u;
               if (EPI == TG_MASK) {
-                if (use_bits) keep = rowbits >> (4 * (lane & 7));
+                if (use_bits) keep = rowbits >> (lane & 7);
                 else if (p.epilogue == EPI_RELU_MASK_MUL) {
                   keep = 0;
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) if (gn + i < p.N && __ldg(p.aux + gm * p.aux_rs + gn + i) > 0.f) keep |= 1u << i;
+                  for (int i = 0; i < 4; ++i) if (gn + i < p.N && __ldg(p.aux + gm * p.aux_rs + gn + i) > 0.f) keep |= 1u << (8 * i);
                 }
               }
 #pragma unroll
@@ -468,15 +469,15 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (EPI == TG_MASK && p.accumulate) y += cp[i];
                 if (EPI == TG_RELU) y = fmaxf(y, 0.f);
                 if (EPI == TG_TANH) { if (tanh_nib & (1u << i)) y = tanhf(y); }
-                if (EPI == TG_MASK) y = (keep & (1u << i)) ? y : 0.f;
+                if (EPI == TG_MASK) y = (keep & (1u << (8 * i))) ? y : 0.f;
                 if (p.round_out) y = round_tf32(y);
-                if (y > 0.f) pos |= 1u << i;
+                if (y > 0.f) pos |= 1u << (8 * i);
                 if (CBF) reinterpret_cast<__nv_bfloat16*>(p.C)[gm * p.c_rs + gn + i] = __float2bfloat16_rn(y);
                 else cp[i] = y;
               }
             }
             if (EPI == TG_RELU && p.mask_out) {
-              uint32_t word = pos << (4 * (lane & 7));
+              uint32_t word = pos << (lane & 7);
               word |= __shfl_xor_sync(0xffffffffu, word, 1);
               word |= __shfl_xor_sync(0xffffffffu, word, 2);
               word |= __shfl_xor_sync(0xffffffffu, word, 4);

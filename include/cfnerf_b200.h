@@ -184,7 +184,7 @@ int cfn_gemm_f32(int engine, const float* A, int64_t a_rs, int64_t a_cs, const f
 /* The same primitive with bf16 STORAGE (tensor-core engine only: tcgen05.mma kind::f16, bf16 operands, fp32
  * accumulation): A and B point to bf16 elements (strides in elements, 16-byte aligned bases / strides), C is bf16
  * (c_bf16 = 1) or fp32.  epilogue as above; epilogue 1 can also write relu'(C) as a bit mask (mask_out: one 32-bit word
- * per row and 32 columns, bits_ld words per row) and epilogue 3 reads such a mask (aux_bits) instead of an fp32 aux.
+ * per row and 32 columns, bits_ld words per row; column n at bit 8 * (n % 4) + (n % 32) / 4) and epilogue 3 reads such a mask (aux_bits) instead of an fp32 aux.
  * split_k > 1: fp32 atomics into a pre-zeroed fp32 C; rowsum (optional, pre-zeroed, M floats) += sum_k A(m,k).
  * Instantiated flavours = the ones the training chain issues (else CFN_EINVAL): K-major x K-major {none, ReLU -> bf16;
  * tanh-mask -> fp32}, K-major x N-major {none, bit-mask -> bf16}, M-major x N-major split-K -> fp32. */

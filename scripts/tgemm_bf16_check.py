@@ -28,7 +28,7 @@ for (M, N, K) in [(128, 16, 64), (300, 104, 72), (5000, 512, 576), (1000, 256, 5
     # bit mask == (Y > 0)
     want = (Y.float() > 0)
     got = torch.zeros_like(want)
-    for j in range(N): got[:, j] = ((bits[:, j // 32] >> (j % 32)) & 1).bool()
+    for j in range(N): got[:, j] = ((bits[:, j // 32] >> (8 * (j % 4) + (j % 32) // 4)) & 1).bool()
     same = bool((want == got).all()); ok &= same
     print("OK " if same else "BAD", "  relu bit mask", flush=True)
     flags = (torch.rand(N, device=dev) > 0.5).float()
@@ -41,7 +41,7 @@ for (M, N, K) in [(128, 16, 64), (300, 104, 72), (5000, 512, 576), (1000, 256, 5
     report(f"KMN plain M={M} N={K} K={N}", gemm_bf16(G, W), refd, 6e-3)
     act = torch.randn(M, K, device=dev)
     abits = torch.zeros(M, (K + 31) // 32, dtype=torch.int32, device=dev)
-    for j in range(K): abits[:, j // 32] |= ((act[:, j] > 0).int() << (j % 32))
+    for j in range(K): abits[:, j // 32] |= ((act[:, j] > 0).int() << (8 * (j % 4) + (j % 32) // 4))
     D = gemm_bf16(G, W, epilogue="relu_mask_mul", aux_bits=abits)
     report(f"KMN mask  M={M} N={K} K={N}", D, torch.where(act > 0, refd, torch.zeros_like(refd)), 6e-3)
 

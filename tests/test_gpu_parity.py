@@ -752,7 +752,8 @@ def test_bf16_storage_tensor_core_gemm_vs_torch(cf, dev):
         Y = cf.gemm_bf16(A, W.t(), bias=bias, epilogue="relu", mask_out=bits)
         assert (Y.double() - (ref + bias.double()).clamp_min(0)).abs().max().item() <= 6e-3 * sc
         cols = torch.arange(N, device=dev)
-        got = ((bits[:, cols // 32] >> (cols % 32)[None, :]) & 1).bool()
+        bitpos = 8 * (cols % 4) + (cols % 32) // 4           # the epilogue's vote order (include/cfnerf_b200.h)
+        got = ((bits[:, cols // 32] >> bitpos[None, :]) & 1).bool()
         assert torch.equal(got, Y.float() > 0)
         flags = (torch.rand(N, generator=g) > 0.5).float().to(dev)
         T = cf.gemm_bf16(A, W.t(), bias=bias, epilogue="tanh_mask", aux=flags, out_dtype=torch.float32)
@@ -767,7 +768,7 @@ def test_bf16_storage_tensor_core_gemm_vs_torch(cf, dev):
         abits = torch.zeros(M, (K + 31) // 32, dtype=torch.int32, device=dev)
         for w in range((K + 31) // 32):
             sel = kc[(kc // 32) == w]
-            abits[:, w] = ((act[:, sel] > 0).int() << (sel % 32)[None, :]).sum(1).int()
+            abits[:, w] = ((act[:, sel] > 0).long() << (8 * (sel % 4) + (sel % 32) // 4)[None, :]).sum(1).to(torch.int32)
         D_ = cf.gemm_bf16(G, W, epilogue="relu_mask_mul", aux_bits=abits)
         assert (D_.double() - torch.where(act > 0, refd, torch.zeros_like(refd))).abs().max().item() <= 6e-3 * scd
     for (Of, If, P, split) in [(512, 576, 20000, 12), (64, 512, 15000, 74), (16, 64, 3000, 5)]:
