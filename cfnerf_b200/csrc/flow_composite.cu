@@ -290,12 +290,13 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
   constexpr int PP = 18 * F;
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_warp = 2 * N + N * 32 + PP * 33 + PP;
+  constexpr int GLD = 36;               // row stride of the transpose scratch: 32 lanes + 4 (rows stay 16-byte aligned)
+  const int per_warp = ((2 * N + 3) & ~3) + N * 32 + PP * GLD + ((PP + 3) & ~3);   // every region 16-byte aligned
   float* sz = smem + warp * per_warp;   // z
   float* sd = sz + N;                   // dists
-  float* sT = sd + N;                   // T_n per lane      [N][32]
-  float* sG = sT + N * 32;              // gradient transpose scratch [PP][33]
-  float* sP = sG + PP * 33;             // parameters of the current point [PP]
+  float* sT = sz + ((2 * N + 3) & ~3);  // T_n per lane      [N][32]
+  float* sG = sT + N * 32;              // gradient transpose scratch [PP][GLD]
+  float* sP = sG + PP * GLD;            // parameters of the current point [PP]
   const int64_t b = (int64_t)blockIdx.x * 4 + warp;
   if (b >= B) return;
 
@@ -352,10 +353,20 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
 
     // ---- pass 2: back to front ----
     float S = 0.f;
+    // the parameters of point n-1 are requested while point n is processed (PP <= 144: at most 5 values per lane)
+    constexpr int NPRE = (PP + 31) / 32;
+    float pre[NPRE];
+#pragma unroll
+    for (int u = 0; u < NPRE; ++u) pre[u] = (lane + 32 * u < PP) ? __ldg(prow + (int64_t)(N - 1) * PP + lane + 32 * u) : 0.f;
     for (int n = N - 1; n >= 0; --n) {
       // stage the point's parameters (PP floats) into shared memory
-      for (int i = lane; i < PP; i += 32) sP[i] = __ldg(prow + (int64_t)n * PP + i);
+#pragma unroll
+      for (int u = 0; u < NPRE; ++u) if (lane + 32 * u < PP) sP[lane + 32 * u] = pre[u];
       __syncwarp();
+      if (n > 0) {
+#pragma unroll
+        for (int u = 0; u < NPRE; ++u) pre[u] = (lane + 32 * u < PP) ? __ldg(prow + (int64_t)(n - 1) * PP + lane + 32 * u) : 0.f;
+      }
       // recompute alpha stack with intermediates
       float za_in[F], ta[F];
       float za = za0;
@@ -414,15 +425,15 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
         const float gpre = gt * omt2;
         const float g_d2 = gpre * za_in[f] + sl * omt2 * d1;
         g_za = g_za + d2 * gpre;
-        sG[(f)*33 + lane] = g_d1;
-        sG[(F + f) * 33 + lane] = g_d2;
-        sG[(2 * F + f) * 33 + lane] = gpre;
+        sG[(f)*GLD + lane] = g_d1;
+        sG[(F + f) * GLD + lane] = g_d2;
+        sG[(2 * F + f) * GLD + lane] = gpre;
       }
       // ---- rgb stack adjoint ----
 #pragma unroll
       for (int f = F - 1; f >= 0; --f) {
         const float* Q = sP + 3 * F + kRgbFlowRec * f;
-        float* G = sG + (3 * F + kRgbFlowRec * f) * 33 + lane;
+        float* G = sG + (3 * F + kRgbFlowRec * f) * GLD + lane;
         const bool odd = f & 1;
         // gy = P g'
         const float gy0 = odd ? gz[2] : gz[0], gy1 = gz[1], gy2 = odd ? gz[0] : gz[2];
@@ -434,27 +445,27 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
         const float sl1 = glc * ((u1 > 0.f) ? 1.f : ((u1 < 0.f) ? -1.f : 0.f)) / (fabsf(u1) + 1e-8f);
         const float sl2 = glc * ((u2 > 0.f) ? 1.f : ((u2 < 0.f) ? -1.f : 0.f)) / (fabsf(u2) + 1e-8f);
         // gR1 = gy t^T (upper), diagonal gets the log-det term
-        G[0 * 33] = gy0 * t0 + sl0 * o0 * Q[6];
-        G[1 * 33] = gy0 * t1;
-        G[2 * 33] = gy0 * t2;
-        G[3 * 33] = gy1 * t1 + sl1 * o1 * Q[9];
-        G[4 * 33] = gy1 * t2;
-        G[5 * 33] = gy2 * t2 + sl2 * o2 * Q[11];
+        G[0 * GLD] = gy0 * t0 + sl0 * o0 * Q[6];
+        G[1 * GLD] = gy0 * t1;
+        G[2 * GLD] = gy0 * t2;
+        G[3 * GLD] = gy1 * t1 + sl1 * o1 * Q[9];
+        G[4 * GLD] = gy1 * t2;
+        G[5 * GLD] = gy2 * t2 + sl2 * o2 * Q[11];
         // gt = R1^T gy + log-det term
         const float gt0 = Q[0] * gy0 + sl0 * (-2.0f * t0 * dd0);
         const float gt1 = Q[1] * gy0 + Q[3] * gy1 + sl1 * (-2.0f * t1 * dd1);
         const float gt2 = Q[2] * gy0 + Q[4] * gy1 + Q[5] * gy2 + sl2 * (-2.0f * t2 * dd2);
         const float gp0 = gt0 * o0, gp1 = gt1 * o1, gp2 = gt2 * o2;
         // gR2 = gpre zp^T (upper), diagonal gets the log-det term
-        G[6 * 33] = gp0 * zp[f][0] + sl0 * o0 * Q[0];
-        G[7 * 33] = gp0 * zp[f][1];
-        G[8 * 33] = gp0 * zp[f][2];
-        G[9 * 33] = gp1 * zp[f][1] + sl1 * o1 * Q[3];
-        G[10 * 33] = gp1 * zp[f][2];
-        G[11 * 33] = gp2 * zp[f][2] + sl2 * o2 * Q[5];
-        G[12 * 33] = gp0;
-        G[13 * 33] = gp1;
-        G[14 * 33] = gp2;
+        G[6 * GLD] = gp0 * zp[f][0] + sl0 * o0 * Q[0];
+        G[7 * GLD] = gp0 * zp[f][1];
+        G[8 * GLD] = gp0 * zp[f][2];
+        G[9 * GLD] = gp1 * zp[f][1] + sl1 * o1 * Q[3];
+        G[10 * GLD] = gp1 * zp[f][2];
+        G[11 * GLD] = gp2 * zp[f][2] + sl2 * o2 * Q[5];
+        G[12 * GLD] = gp0;
+        G[13 * GLD] = gp1;
+        G[14 * GLD] = gp2;
         // gz = g' + P (R2^T gpre)
         const float r0 = Q[6] * gp0;
         const float r1 = Q[7] * gp0 + Q[9] * gp1;
@@ -471,10 +482,10 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
       // ---- reduce the PP per-point parameter gradients over the 32 latent lanes ----
       __syncwarp();
       for (int j = lane; j < PP; j += 32) {
-        const float* row = sG + j * 33;
+        const float4* row = reinterpret_cast<const float4*>(sG + j * GLD);
         float acc = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc += row[i];
+        for (int i = 0; i < 8; ++i) { const float4 q4 = row[i]; acc += (q4.x + q4.y) + (q4.z + q4.w); }
         float* dst = grow + (int64_t)n * PP + j;
         if (kg == 0) *dst = acc; else *dst += acc;
       }
@@ -500,7 +511,7 @@ int launch_flow_composite_bwd(int fast_math, int F, int K, const float* globals,
   CFN_CHECK_ARG(F >= 1 && F <= kMaxF, "flow_composite_bwd: n_flows=%d unsupported (1..%d)", F, kMaxF);
   CFN_CHECK_ARG(N >= 2 && N <= 320 && K >= 1, "flow_composite_bwd: unsupported N=%d (<=320) K=%d", N, K);
   const int PP = 18 * F;
-  size_t smem = (size_t)4 * (2 * N + N * 32 + PP * 33 + PP) * sizeof(float);
+  size_t smem = (size_t)4 * (((2 * N + 3) & ~3) + N * 32 + PP * 36 + ((PP + 3) & ~3)) * sizeof(float);
   unsigned grid = (unsigned)((B + 3) / 4);
 #define CFN_BWD_CASE(FF)                                                                                             \
   case FF: {                                                                                                         \
