@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-echo "=== smoke"; timeout -s KILL 300 python __graft_entry__.py smoke 2>&1 | grep -E "smoke|rror" | tail -16
-echo "=== bench"; timeout -s KILL 400 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r01.json 2> gpurun_out/bench.err; cut -c1-160 gpurun_out/bench_r01.json; tail -2 gpurun_out/bench.err
-echo "=== train steps"; for p in bf16 tf32; do CFN_TRAIN_PRECISION=$p timeout -s KILL 90 python scripts/train_step_bench.py 2>&1 | tail -1; done > gpurun_out/train_steps.json; cat gpurun_out/train_steps.json | cut -c1-200
+echo "=== memcheck: tensor-core GEMMs (tf32 + bf16 flavours) and one training step on each chain"
+timeout -s KILL 500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests -m gpu -q -x -k "test_tf32_tensor_core_gemm_vs_torch or test_bf16_storage_tensor_core_gemm_vs_torch or (test_training_step_tensor_core_vs_fp32_path and kw2)" 2>&1 | tail -6
