@@ -10,7 +10,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libcfnerf_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-    "-shared", "-Xptxas", "-v",
+    "-shared", "-Xptxas", "-v", "--threads", "0",
 ]
 
 
