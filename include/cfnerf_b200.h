@@ -39,7 +39,9 @@ extern "C" {
 #define CFN_PREC_FP16 2 /* tcgen05.mma kind::f16, fp16 operands (11-bit significand, TF32-class), fp32 acc  */
 #define CFN_PREC_TF32 3 /* tcgen05.mma kind::tf32 layer by layer, fp32 storage (operands rounded to tf32)       */
 /* Training (cfn_network_fwd with save_for_backward + cfn_network_bwd) runs the layer-by-layer chain with saved
- * activations in every mode: fp32 FMA GEMMs in CFN_PREC_FP32, tf32 tensor-core GEMMs in the other three. */
+ * activations in every mode: fp32 FMA GEMMs in CFN_PREC_FP32; TMA-fed tcgen05 GEMMs otherwise — kind::f16 over
+ * bf16-stored activations / gradients in CFN_PREC_BF16 (fp32 accumulation, master weights and weight gradients),
+ * kind::tf32 over fp32 storage in CFN_PREC_TF32 and CFN_PREC_FP16. */
 
 /* Architecture of one NeRF_Flows network (model/models.py:20-36; run_nerf_uncertainty_NF.py:317-336). */
 typedef struct CfnConfig {
