@@ -316,7 +316,8 @@ def main():
         from cfnerf_b200 import dist as D
         tparams = [q for n, q in net.named_parameters()
                    if not n.startswith("alpha_linear") and not n.startswith("alpha_std_linear")]
-        opt = torch.optim.Adam(tparams, lr=5e-4, betas=(0.9, 0.999))
+        from cfnerf_b200.optim import FusedAdam
+        opt = FusedAdam(tparams, lr=5e-4, betas=(0.9, 0.999))      # torch.optim.Adam semantics in one launch (F3)
         bucket = D.GradBucket(tparams) if world > 1 else None
         gt = torch.Generator().manual_seed(100 + rank)
         t_rays = rays_dev[torch.randperm(B, generator=gt)[:args.train_rays].to(dev)].contiguous()

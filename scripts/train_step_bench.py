@@ -28,7 +28,8 @@ steps, warm = 5, 2
 cfg = O.CfnConfig()
 net = cf.NeRFFlowsParams.from_oracle_params(cfg, O.make_params(cfg, 0), *O.make_latents(cfg, 0)).to(dev)
 params = [q for n, q in net.named_parameters() if not n.startswith("alpha_linear") and not n.startswith("alpha_std_linear")]
-opt = torch.optim.Adam(params, lr=5e-4, betas=(0.9, 0.999))
+from cfnerf_b200.optim import FusedAdam
+opt = FusedAdam(params, lr=5e-4, betas=(0.9, 0.999)) if os.environ.get("CFN_TORCH_ADAM") != "1" else torch.optim.Adam(params, lr=5e-4)
 bucket = D.GradBucket(params)
 rays = D.shard_rays(O.synthetic_rays(GLOBAL, 1), rank, world).to(dev)
 g = torch.Generator().manual_seed(2)
