@@ -314,22 +314,20 @@ def main():
     train_ms = 0.0
     if not args.no_train:
         from cfnerf_b200 import dist as D
-        tparams = [q for n, q in net.named_parameters()
-                   if not n.startswith("alpha_linear") and not n.startswith("alpha_std_linear")]
-        from cfnerf_b200.optim import FusedAdam
-        opt = FusedAdam(tparams, lr=5e-4, betas=(0.9, 0.999))      # torch.optim.Adam semantics in one launch (F3)
-        bucket = D.GradBucket(tparams) if world > 1 else None
+        # the repo's own trainer step: a straight chain of C-ABI calls (no autograd graph), flat gradient buffer =
+        # all-reduce bucket, fused Adam
+        trainer = D.FusedTrainStep(net, lr=5e-4, precision=args.train_precision)
         gt = torch.Generator().manual_seed(100 + rank)
         t_rays = rays_dev[torch.randperm(B, generator=gt)[:args.train_rays].to(dev)].contiguous()
         t_target = torch.rand(t_rays.shape[0], 3, generator=gt).to(dev)
         torch.manual_seed(100 + rank)
         for _ in range(3):
-            D.train_step(net, opt, t_rays, t_target, bucket, precision=args.train_precision)
+            trainer.step(t_rays, t_target)
         barrier()
         te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         te0.record()
         for _ in range(args.steps):
-            t_out = D.train_step(net, opt, t_rays, t_target, bucket, precision=args.train_precision)
+            t_out = trainer.step(t_rays, t_target)
         te1.record()
         barrier()
         train_ms = te0.elapsed_time(te1)
@@ -406,7 +404,7 @@ def main():
                 "value": n_t * world / step_s, "unit": "rays/s", "ms_per_step": step_s * 1e3, "rays_per_gpu": n_t,
                 "precision": args.train_precision, "loss": float(t_out["loss"]),
                 "achieved_tflops_per_gpu": n_t * N_SAMPLES * FLOP_PER_POINT * 3 / step_s / 1e12,
-                "note": "forward + backward + Adam through cfnerf_b200.dist.train_step; GEMMs = TMA-fed tcgen05: kind::f16 over "
+                "note": "forward + loss + backward + all-reduce + Adam through cfnerf_b200.dist.FusedTrainStep; GEMMs = TMA-fed tcgen05: kind::f16 over "
                         "bf16-stored activations / gradients (bf16), kind::tf32 over fp32 storage (tf32), or CUDA-core fp32 "
                         "FMA (fp32); fp32 accumulation, master weights and weight gradients throughout; flops = 3 x forward"}
             if tg_ms > 0:

@@ -38,11 +38,18 @@ def reference_t_schedule(n_samples: int, device) -> torch.Tensor:
     """main:510 — the hard-coded 96+32 schedule (the reference requires N_samples == 128, main:516).  For any other
     N_samples (extension) the upstream linspace(0,1,N) schedule is used.  Computed on the CPU in fp32 like
     the oracle, then moved: torch's CUDA linspace may differ in the last bit."""
-    if n_samples == 128:
-        t = torch.cat([torch.linspace(0., 0.5, steps=97)[:-1], torch.linspace(0.5, 1., steps=32)], 0)
-    else:
-        t = torch.linspace(0., 1., steps=n_samples)
-    return t.to(device)
+    key = (int(n_samples), str(device))
+    t = _T_SCHEDULES.get(key)
+    if t is None:       # cached per device: a pageable host-to-device copy per call would stall the host every step
+        if n_samples == 128:
+            t = torch.cat([torch.linspace(0., 0.5, steps=97)[:-1], torch.linspace(0.5, 1., steps=32)], 0)
+        else:
+            t = torch.linspace(0., 1., steps=n_samples)
+        t = _T_SCHEDULES[key] = t.to(device)
+    return t
+
+
+_T_SCHEDULES: dict = {}
 
 
 def test_latents(module, device):
@@ -153,10 +160,11 @@ class _RenderTrainFn(torch.autograd.Function):
         dev = rays.device
         g_rgb = _f32c(g_rgb, dev) if g_rgb is not None else torch.zeros(B, 3, eng.K, device=dev)
         g_depth = _f32c(g_depth, dev) if g_depth is not None else None
-        gl = g_ld.detach().float().cpu().tolist() if g_ld is not None else [0.0, 0.0]
+        # the log-det gradient seeds stay on the device: reading them back would stall the host once per step
+        gl = _f32c(g_ld.detach(), dev) if g_ld is not None else torch.zeros(2, device=dev)
         with torch.cuda.device(dev):
             g_fp, g_glob = eng.flow_composite_bwd(fp, z_vals, rays[:, 3:6], 11, eps_a, eps_c, ctx.white_bkgd, g_rgb,
-                                                  g_depth, gl[0], gl[1])
+                                                  g_depth, gl)
             grads = eng.network_bwd(g_fp, B, N, ws)
         gg = g_glob.sum(0)
         grads[0], grads[1] = gg[0:1], gg[1:2]

@@ -298,11 +298,11 @@ extern "C" int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, co
                                    logdet_sums, kstats, (cudaStream_t)stream);
 }
 
-extern "C" int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, const float* z_vals,
-                                      const float* rays_d, int rays_d_stride, const float* eps_alpha,
-                                      const float* eps_rgb, int64_t B, int N, int white_bkgd, const float* g_rgb_map,
-                                      const float* g_depth_map, float g_logdet_alpha, float g_logdet_rgb,
-                                      float* g_flow_params, float* g_globals_partial, void* stream) {
+static int flow_composite_bwd_impl(CfnHandle* h, const float* flow_params, const float* z_vals, const float* rays_d,
+                                  int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t B, int N,
+                                  int white_bkgd, const float* g_rgb_map, const float* g_depth_map, float g_logdet_alpha,
+                                  float g_logdet_rgb, const float* g_logdet_dev, float* g_flow_params,
+                                  float* g_globals_partial, void* stream) {
   CFN_CHECK_ARG(h && flow_params && z_vals && rays_d && eps_alpha && eps_rgb && g_rgb_map && g_flow_params &&
                     g_globals_partial,
                 "cfn_flow_composite_bwd: null argument");
@@ -310,9 +310,30 @@ extern "C" int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, co
     set_error("cfn_flow_composite_bwd: call cfn_pack_weights first");
     return CFN_ESTATE;
   }
-  return launch_flow_composite_bwd(h->cfg.precision != CFN_PREC_FP32 ? 1 : 0, h->cfg.F, h->cfg.K, h->globals, flow_params, z_vals, rays_d, rays_d_stride,
-                                   eps_alpha, eps_rgb, B, N, white_bkgd, g_rgb_map, g_depth_map, g_logdet_alpha,
-                                   g_logdet_rgb, g_flow_params, g_globals_partial, (cudaStream_t)stream);
+  return launch_flow_composite_bwd(h->cfg.precision != CFN_PREC_FP32 ? 1 : 0, h->cfg.F, h->cfg.K, h->globals, flow_params,
+                                   z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N, white_bkgd, g_rgb_map,
+                                   g_depth_map, g_logdet_alpha, g_logdet_rgb, g_logdet_dev, g_flow_params,
+                                   g_globals_partial, (cudaStream_t)stream);
+}
+
+extern "C" int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, const float* z_vals,
+                                      const float* rays_d, int rays_d_stride, const float* eps_alpha,
+                                      const float* eps_rgb, int64_t B, int N, int white_bkgd, const float* g_rgb_map,
+                                      const float* g_depth_map, float g_logdet_alpha, float g_logdet_rgb,
+                                      float* g_flow_params, float* g_globals_partial, void* stream) {
+  return flow_composite_bwd_impl(h, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N, white_bkgd,
+                                 g_rgb_map, g_depth_map, g_logdet_alpha, g_logdet_rgb, nullptr, g_flow_params,
+                                 g_globals_partial, stream);
+}
+
+extern "C" int cfn_flow_composite_bwd_dev(CfnHandle* h, const float* flow_params, const float* z_vals,
+                                          const float* rays_d, int rays_d_stride, const float* eps_alpha,
+                                          const float* eps_rgb, int64_t B, int N, int white_bkgd,
+                                          const float* g_rgb_map, const float* g_depth_map, const float* g_logdet_dev,
+                                          float* g_flow_params, float* g_globals_partial, void* stream) {
+  CFN_CHECK_ARG(g_logdet_dev != nullptr, "cfn_flow_composite_bwd_dev: g_logdet_dev is null");
+  return flow_composite_bwd_impl(h, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N, white_bkgd,
+                                 g_rgb_map, g_depth_map, 0.f, 0.f, g_logdet_dev, g_flow_params, g_globals_partial, stream);
 }
 
 extern "C" int cfn_raw2outputs_f32(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,

@@ -80,7 +80,7 @@ int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals,
 int launch_flow_composite_bwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
                               int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
-                              float g_ld_alpha, float g_ld_rgb, float* g_flow_params, float* g_globals,
+                              float g_ld_alpha, float g_ld_rgb, const float* g_ld_dev, float* g_flow_params, float* g_globals,
                               cudaStream_t s);
 
 // C[m,n] = epi( sum_k A(m,k) * B(k,n) + bias[n] ) with arbitrary element strides (fp32 CUDA-core GEMM).

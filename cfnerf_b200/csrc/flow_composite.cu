@@ -284,8 +284,12 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
                           const float* __restrict__ z_vals, const float* __restrict__ rays_d, int rays_d_stride,
                           const float* __restrict__ eps_alpha, const float* __restrict__ eps_rgb, int64_t B, int N,
                           int white_bkgd, const float* __restrict__ g_rgb_map, const float* __restrict__ g_depth_map,
-                          float gl_a, float gl_c, float* __restrict__ g_flow_params,
-                          float* __restrict__ g_globals_partial) {
+                          float gl_a_host, float gl_c_host, const float* __restrict__ g_ld_dev,
+                          float* __restrict__ g_flow_params, float* __restrict__ g_globals_partial) {
+  // gradient seeds of the two log-det sums: by value, or (g_ld_dev != nullptr) read from the device so that the host
+  // never has to wait for the loss graph before it can issue the backward
+  const float gl_a = g_ld_dev ? g_ld_dev[0] : gl_a_host;
+  const float gl_c = g_ld_dev ? g_ld_dev[1] : gl_c_host;
   constexpr int F = FT;
   constexpr int PP = 18 * F;
   extern __shared__ __align__(16) float smem[];
@@ -505,7 +509,8 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
 int launch_flow_composite_bwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
                               int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
-                              float g_ld_alpha, float g_ld_rgb, float* g_flow_params, float* g_globals_partial,
+                              float g_ld_alpha, float g_ld_rgb, const float* g_ld_dev, float* g_flow_params,
+                              float* g_globals_partial,
                               cudaStream_t s) {
   if (B == 0) return CFN_OK;
   CFN_CHECK_ARG(F >= 1 && F <= kMaxF, "flow_composite_bwd: n_flows=%d unsupported (1..%d)", F, kMaxF);
@@ -518,7 +523,7 @@ int launch_flow_composite_bwd(int fast_math, int F, int K, const float* globals,
     auto kern = fast_math ? flow_composite_bwd_kernel<FF, true> : flow_composite_bwd_kernel<FF, false>;              \
     CFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
     kern<<<grid, 128, smem, s>>>(K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N,   \
-                                 white_bkgd, g_rgb_map, g_depth_map, g_ld_alpha, g_ld_rgb, g_flow_params,            \
+                                 white_bkgd, g_rgb_map, g_depth_map, g_ld_alpha, g_ld_rgb, g_ld_dev, g_flow_params,  \
                                  g_globals_partial);                                                                 \
   } break;
   switch (F) {

@@ -451,13 +451,17 @@ static int dgrad(const CfnHandle* h, int slot, const float* Gout, int64_t ldgo, 
   return gemm(h, g, 1, s);
 }
 
+// gradient tensors by parameter slot, passed BY VALUE as a kernel parameter: copying the table to the device from pageable
+// host memory would make cudaMemcpyAsync synchronise the stream (and stall the host) once per training step
+struct GradPtrs { float* p[64]; };
+
 __global__ void scatter_rows_kernel(const float* __restrict__ dAm, const float* __restrict__ dAb, int cols,
-                                    const int* __restrict__ gather, int rows, float* const* __restrict__ grads) {
+                                    const int* __restrict__ gather, int rows, const GradPtrs grads) {
   int r = blockIdx.x;
   if (r >= rows) return;
   const int slot_w = gather[r * 4 + 0], slot_b = gather[r * 4 + 1], row = gather[r * 4 + 2];
-  float* gw = grads[slot_w];
-  float* gb = grads[slot_b];
+  float* gw = grads.p[slot_w];
+  float* gb = grads.p[slot_b];
   if (gw) for (int c = threadIdx.x; c < cols; c += blockDim.x) gw[(int64_t)row * cols + c] = dAm[r * cols + c];
   if (gb && threadIdx.x == 0) gb[row] = dAb[r];
 }
@@ -510,9 +514,9 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
     for (int j = 0; j < 8; ++j)
       CFN_CUDA(cudaMemsetAsync(grads[base + j], 0, h->slots[base + j].numel * sizeof(float), s));
 
-  // pointer table on the device (handle-owned; the pageable copy is staged before the call returns)
-  float** table = h->grads_table_dev;
-  CFN_CUDA(cudaMemcpyAsync(table, grads, h->slots.size() * sizeof(float*), cudaMemcpyHostToDevice, s));
+  // gradient pointers of every slot, handed to the scatter kernels by value
+  GradPtrs table;
+  for (size_t i = 0; i < 64; ++i) table.p[i] = i < h->slots.size() ? grads[i] : nullptr;
 
   // 2. alpha conditioning branch
   {

@@ -141,21 +141,24 @@ class Engine:
         return dict(rgb_map=rgb, disp_map=disp, depth_map=depth, raw=raw, weights=w, logdet_sums=ld, kstats=ks)
 
     def flow_composite_bwd(self, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, white_bkgd,
-                           g_rgb, g_depth, g_ld_a: float, g_ld_c: float):
+                           g_rgb, g_depth, g_ld):
+        """g_ld: device tensor (2,) = d loss / d (sum of the alpha / rgb log-dets); stays on the device (no host sync)."""
         B, N = z_vals.shape
         g_fp = torch.empty_like(flow_params)
         g_glob = torch.empty(B, 8, dtype=torch.float32, device=self.device)
-        check(self.lib.cfn_flow_composite_bwd(self.h, _ptr(flow_params), _ptr(z_vals), _ptr(rays_d), rays_d_stride,
-                                              _ptr(eps_alpha), _ptr(eps_rgb), B, N, int(white_bkgd), _ptr(g_rgb),
-                                              _ptr(g_depth), float(g_ld_a), float(g_ld_c), _ptr(g_fp), _ptr(g_glob),
-                                              _stream()), "cfn_flow_composite_bwd")
+        check(self.lib.cfn_flow_composite_bwd_dev(self.h, _ptr(flow_params), _ptr(z_vals), _ptr(rays_d), rays_d_stride,
+                                                  _ptr(eps_alpha), _ptr(eps_rgb), B, N, int(white_bkgd), _ptr(g_rgb),
+                                                  _ptr(g_depth), _ptr(g_ld), _ptr(g_fp), _ptr(g_glob), _stream()),
+              "cfn_flow_composite_bwd_dev")
         return g_fp, g_glob
 
-    def network_bwd(self, g_flow_params, B: int, N: int, ws):
-        """-> list of gradient tensors in parameter order (entries 0..3 are None: globals come from the flow stage)."""
-        grads = [None] * 4 + [torch.empty_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
-                              for p in self.params[4:]]
-        arr = (C.c_void_p * len(grads))(*[(g.data_ptr() if g is not None else 0) for g in grads])
+    def network_bwd(self, g_flow_params, B: int, N: int, ws, grads=None):
+        """-> list of gradient tensors in parameter order (entries 0..3 are None: globals come from the flow stage).
+        `grads`: optional preallocated fp32 tensors to write into (entries 0..3 ignored)."""
+        if grads is None:
+            grads = [None] * 4 + [torch.empty_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+                                  for p in self.params[4:]]
+        arr = (C.c_void_p * len(grads))(*[(g.data_ptr() if (g is not None and i >= 4) else 0) for i, g in enumerate(grads)])
         check(self.lib.cfn_network_bwd(self.h, _ptr(g_flow_params), B, N, _ptr(ws), ws.numel(), arr, len(grads),
                                        _stream()), "cfn_network_bwd")
         return grads

@@ -134,6 +134,12 @@ int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, const float* 
                            int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t B, int N,
                            int white_bkgd, const float* g_rgb_map, const float* g_depth_map, float g_logdet_alpha,
                            float g_logdet_rgb, float* g_flow_params, float* g_globals_partial, void* stream);
+/* Same, with the two log-det gradient seeds read from DEVICE memory (g_logdet_dev[0] = alpha, [1] = rgb): the host
+ * does not have to wait for the loss graph before it issues the backward (no device-to-host sync per step). */
+int cfn_flow_composite_bwd_dev(CfnHandle* h, const float* flow_params, const float* z_vals, const float* rays_d,
+                               int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t B, int N,
+                               int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
+                               const float* g_logdet_dev, float* g_flow_params, float* g_globals_partial, void* stream);
 
 /* ---- A8 stand-alone: raw2outputs (run_nerf_uncertainty_NF.py:411-454) ------------------------ */
 int cfn_raw2outputs_f32(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,

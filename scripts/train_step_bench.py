@@ -35,15 +35,18 @@ rays = D.shard_rays(O.synthetic_rays(GLOBAL, 1), rank, world).to(dev)
 g = torch.Generator().manual_seed(2)
 target = D.shard_rays(torch.rand(GLOBAL, 3, generator=g), rank, world).to(dev)
 torch.manual_seed(100 + rank)       # each rank draws its own latent noise, like each DataParallel replica (models.py:233-235)
+FUSED = os.environ.get("CFN_TRAIN_AUTOGRAD") != "1"      # default: the autograd-free FusedTrainStep
+trainer = D.FusedTrainStep(net, lr=5e-4, precision=PREC) if FUSED else None
+one_step = (lambda: trainer.step(rays, target)) if FUSED else (lambda: D.train_step(net, opt, rays, target, bucket, precision=PREC))
 for _ in range(warm):
-    out = D.train_step(net, opt, rays, target, bucket, precision=PREC)
+    out = one_step()
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(steps):
-    out = D.train_step(net, opt, rays, target, bucket, precision=PREC)
+    out = one_step()
 e1.record()
 torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

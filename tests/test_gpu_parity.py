@@ -778,3 +778,42 @@ def test_bf16_storage_tensor_core_gemm_vs_torch(cf, dev):
         ref = G.double().t() @ X.double()
         assert (dW.double() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
         assert (rs.double() - G.double().sum(0)).abs().max().item() <= 2e-5 * max(1.0, G.double().sum(0).abs().max().item())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_train_step_equals_the_autograd_path(cf, dev, precision):
+    """dist.FusedTrainStep (straight chain of C-ABI calls, no autograd graph) against dist.train_step (the autograd
+    drop-in path + FusedAdam) on the same draws: same gradients, same weights after two optimisation steps."""
+    from cfnerf_b200 import dist as D
+    from cfnerf_b200.optim import FusedAdam
+    cfg = O.CfnConfig()
+    p = O.make_params(cfg, 4, "lively")
+    sa, sr = O.make_latents(cfg, 4)
+    B = 24
+    rays = O.synthetic_rays(B, 6).to(dev)
+    g = torch.Generator().manual_seed(9)
+    target = torch.rand(B, 3, generator=g).to(dev)
+    draws = [(torch.rand(B, 128, generator=g).to(dev), torch.randn(cfg.K, 1, generator=g).to(dev),
+              torch.randn(cfg.K, 3, generator=g).to(dev)) for _ in range(2)]
+    net_a, net_b = make_net(cf, cfg, p, sa, sr, dev), make_net(cf, cfg, p, sa, sr, dev)
+    live = lambda net: [q for n, q in net.named_parameters()
+                        if not n.startswith("alpha_linear") and not n.startswith("alpha_std_linear")]
+    opt = FusedAdam(live(net_a), lr=5e-4)
+    fused = D.FusedTrainStep(net_b, lr=5e-4, precision=precision)
+    for it, (t_rand, ea, er) in enumerate(draws):
+        la = D.train_step(net_a, opt, rays, target, None, t_rand=t_rand, eps_alpha=ea, eps_rgb=er, precision=precision)
+        lb = fused.step(rays, target, t_rand=t_rand, eps_alpha=ea, eps_rgb=er)
+        assert abs(float(la["loss"]) - float(lb["loss"])) <= 1e-5 * max(1.0, abs(float(la["loss"]))), it
+        assert abs(float(la["psnr"]) - float(lb["psnr"])) <= 1e-4
+        if it == 0:
+            ga = {n: q.grad for n, q in net_a.named_parameters() if q.grad is not None}
+            for name, gb in zip(fused.eng.names, fused.grads):
+                ref = ga[name]
+                # same kernels on both sides; the split-K wgrad accumulates with fp32 atomics, whose order is not fixed
+                assert (ref - gb).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-9, name
+    # Adam's first steps move a weight by ~lr * sign(grad): only where |grad| is at the level of the atomics noise
+    # (a handful of elements) may the two runs part by more than rounding
+    for (n, qa), (_, qb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        d = (qa - qb).abs()
+        assert d.max().item() <= 2 * 2 * 5e-4 + 1e-6, n
+        assert (d > 2e-6).float().mean().item() <= 2e-3, n
