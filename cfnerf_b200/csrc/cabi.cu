@@ -134,8 +134,6 @@ extern "C" int cfn_create(const CfnConfig* cfg, CfnHandle** out) {
   }
   h->w32 = h->amA = h->amA_b = h->amC = h->amC_b = h->tanh_flags = nullptr;
   h->gatherA_dev = h->gatherC_dev = nullptr;
-  h->grads_table_dev = nullptr;
-  if (cudaMalloc(&h->grads_table_dev, 64 * sizeof(float*)) != cudaSuccess) return fail("cudaMalloc");
   if (cudaMalloc(&h->w32, h->n_floats * sizeof(float)) != cudaSuccess) return fail("cudaMalloc(w32)");
   h->globals = h->w32;
   if (cudaMalloc(&h->wg, (h->wg_floats + 4) * sizeof(float)) != cudaSuccess) return fail("cudaMalloc(wg)");
@@ -190,7 +188,6 @@ extern "C" int cfn_destroy(CfnHandle* h) {
   cudaFree(h->tanh_flags);
   cudaFree(h->gatherA_dev);
   cudaFree(h->gatherC_dev);
-  cudaFree(h->grads_table_dev);
   delete h;
   return CFN_OK;
 }

@@ -373,7 +373,6 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         // phase 2: 8 lanes per row, 4 rows per instruction: every global access of the warp is 4 full 128-byte lines
         const int gn = n_tile0 + c * 32 + c4;
-        const bool vec = p.vec_ok && (gn + 3 < p.N);
         float b4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t tanh_nib = 0;
         if (EPI != TG_ATOMIC) {

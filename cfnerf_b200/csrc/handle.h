@@ -51,7 +51,6 @@ struct CfnHandle {
   int* gatherA_dev;  // (3F,4) GatherRow
   int* gatherC_dev;  // (15F,4)
   std::vector<GatherRow> gatherA, gatherC;
-  float** grads_table_dev;  // (n slots) scratch pointer table for cfn_network_bwd
 
   // GEMM operands of the layer-by-layer network stage (mlp_chain.cu): fp32 FMA (gemm_tc = 0) or tcgen05 kind::tf32
   int gemm_tc;              // 1: contractions run on the tensor cores (every precision mode except CFN_PREC_FP32)
