@@ -29,6 +29,9 @@ DEFAULT_PRECISION = "fp16"
 # Training (forward with saved activations + backward) runs layer by layer: "fp32" = CUDA-core FMA GEMMs (the exact
 # check mode), "tf32" / "bf16" / "fp16" = tcgen05 kind::tf32 GEMMs over fp32 storage with tf32-rounded operands.
 DEFAULT_TRAIN_PRECISION = "tf32"
+# points per network call of the reference: netchunk_per_gpu (65536, main:604) x n_gpus (main:336); it decides how many
+# independent latent draws a training batch sees (see render_rays)
+DEFAULT_NETCHUNK = 1024 * 64
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -137,52 +140,88 @@ def mean_over_k(w):
 # ------------------------------------------------------------------------------------------------------
 class _RenderTrainFn(torch.autograd.Function):
     """forward: cfn_network_fwd(save) + cfn_flow_composite_fwd(train); backward: cfn_flow_composite_bwd +
-    cfn_network_bwd.  The parameters are inputs so that autograd writes into the reference module's own .grad."""
+    cfn_network_bwd.  The parameters are inputs so that autograd writes into the reference module's own .grad.
+    eps_a (G,K) / eps_c (G,K,3): one latent draw per group of `group_rays` rays (0: G = 1)."""
 
     @staticmethod
-    def forward(ctx, eng: Engine, rays, z_vals, eps_a, eps_c, white_bkgd, want_weights, *params):
+    def forward(ctx, eng: Engine, rays, z_vals, eps_a, eps_c, white_bkgd, want_weights, group_rays, *params):
         B, N = z_vals.shape
         fp, ws = eng.network(B, N, rays=rays, z_vals=z_vals, save=True)
         out = eng.flow_composite(fp, z_vals, rays[:, 3:6], 11, eps_a, eps_c, white_bkgd, want_raw=True,
-                                 want_weights=want_weights, train=True)
-        ctx.eng, ctx.white_bkgd = eng, white_bkgd
-        ctx.save_for_backward(rays, z_vals, eps_a, eps_c, fp, ws)
-        ld = out["logdet_sums"].sum(0)  # totals over rays: (2,)
+                                 want_weights=want_weights, train=True, eps_group_rays=group_rays, want_trans=True)
+        ctx.eng, ctx.white_bkgd, ctx.group_rays = eng, white_bkgd, group_rays
+        ctx.save_for_backward(rays, z_vals, eps_a, eps_c, fp, ws, out["trans"])
         w = out["weights"] if want_weights else torch.empty(0, device=rays.device)
         ctx.mark_non_differentiable(out["disp_map"], out["raw"], w)
-        return out["rgb_map"], out["disp_map"], out["depth_map"], out["raw"], ld, w
+        # logdet_sums (B,2): per-ray sums of the alpha / rgb log-det terms (the entropy scalars are built from them)
+        return out["rgb_map"], out["disp_map"], out["depth_map"], out["raw"], out["logdet_sums"], w
 
     @staticmethod
     def backward(ctx, g_rgb, g_disp, g_depth, g_raw, g_ld, g_w):
         eng = ctx.eng
-        rays, z_vals, eps_a, eps_c, fp, ws = ctx.saved_tensors
+        rays, z_vals, eps_a, eps_c, fp, ws, trans = ctx.saved_tensors
         B, N = z_vals.shape
         dev = rays.device
         g_rgb = _f32c(g_rgb, dev) if g_rgb is not None else torch.zeros(B, 3, eng.K, device=dev)
         g_depth = _f32c(g_depth, dev) if g_depth is not None else None
-        # the log-det gradient seeds stay on the device: reading them back would stall the host once per step
-        gl = _f32c(g_ld.detach(), dev) if g_ld is not None else torch.zeros(2, device=dev)
+        # the per-ray log-det gradient seeds stay on the device: reading them back would stall the host once per step
+        gl = _f32c(g_ld.detach(), dev) if g_ld is not None else torch.zeros(B, 2, device=dev)
         with torch.cuda.device(dev):
             g_fp, g_glob = eng.flow_composite_bwd(fp, z_vals, rays[:, 3:6], 11, eps_a, eps_c, ctx.white_bkgd, g_rgb,
-                                                  g_depth, gl)
+                                                  g_depth, gl, trans=trans, eps_group_rays=ctx.group_rays)
             grads = eng.network_bwd(g_fp, B, N, ws)
         gg = g_glob.sum(0)
         grads[0], grads[1] = gg[0:1], gg[1:2]
         grads[2], grads[3] = gg[2:5], gg[5:8]
         grads = [g.reshape(p.shape) for g, p in zip(grads, eng.params)]
-        return (None, None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, None, *grads)
+
+
+def latent_groups(B: int, N: int, netchunk: int):
+    """How the reference's `batchify` (main:47-64) cuts a training batch of B rays x N samples into network calls of
+    `netchunk` points, each of which draws its own latent noise (models.py:233-251): -> (rays per call, number of
+    calls).  Whole rays per call need N | netchunk — true for the reference's only N (128 | 65536); otherwise (the
+    192-sample fine grid of the extension) the batch is treated as one call."""
+    if netchunk and netchunk % N == 0 and B * N > netchunk:
+        r = netchunk // N
+        return r, (B + r - 1) // r
+    return 0, 1
 
 
 def _entropy_base_terms(module, eps_a, eps_c):
     """base log-densities of models.py:268/283 (no 2*pi term), written like the reference so autograd gives the same
-    gradient for the global std parameters."""
+    gradient for the global std parameters.  eps_a (K) / eps_c (K,3) -> two scalars; with a leading group axis
+    ((G,K) / (G,K,3)) -> two (G,) tensors, one pair per network call."""
     a_mean, a_std = module.alpha_mean, module.alpha_std
     c_mean, c_std = module.rgb_mean, module.rgb_std
-    a0 = eps_a.reshape(-1, 1) * a_std[None, :] + a_mean[None, :]
-    c0 = eps_c * c_std[None, :] + c_mean[None, :]
+    grouped = eps_c.dim() == 3
+    ea = eps_a.reshape(eps_c.shape[0], -1, 1) if grouped else eps_a.reshape(1, -1, 1)
+    ec = eps_c if grouped else eps_c[None]
+    a0 = ea * a_std + a_mean
+    c0 = ec * c_std + c_mean
     base_a = -0.5 * (a_std.log() * 2 + (a0 - a_mean) * (a0 - a_mean) * (a_std ** 2).reciprocal())
     base_c = -0.5 * (c_std.log() * 2 + (c0 - c_mean) * (c0 - c_mean) * (c_std ** 2).reciprocal())
-    return base_a.mean(), base_c.mean()
+    ba, bc = base_a.mean((1, 2)), base_c.mean((1, 2))
+    return (ba, bc) if grouped else (ba[0], bc[0])
+
+
+def _entropy_rows(module, eps_a, eps_c, logdet_sums, B, N, K, group_rays):
+    """The (B*N, K, 1) `loss_entropy` tensor `render_rays` returns in train mode: every network call's entropy scalar
+    (models.py:286) broadcast over the rows of that call (models.py:291; cat in batchify, main:57-62)."""
+    if not group_rays:
+        base_a, base_c = _entropy_base_terms(module, eps_a.reshape(-1), eps_c.reshape(-1, 3))
+        ld = logdet_sums.sum(0)
+        cnt = float(B * N * K)
+        ent = base_a - ld[0] / cnt + base_c - ld[1] / cnt
+        return ent.expand(B * N, K, 1)
+    G = eps_c.shape[0]
+    base_a, base_c = _entropy_base_terms(module, eps_a, eps_c)                                 # (G,), (G,)
+    sizes = torch.tensor([min(group_rays, B - g * group_rays) for g in range(G)], device=logdet_sums.device)
+    gid = torch.repeat_interleave(torch.arange(G, device=logdet_sums.device), sizes)
+    ld = torch.zeros(G, 2, device=logdet_sums.device, dtype=logdet_sums.dtype).index_add(0, gid, logdet_sums)
+    cnt = sizes.to(ld.dtype) * float(N * K)
+    ent = base_a - ld[:, 0] / cnt + base_c - ld[:, 1] / cnt                                    # (G,)
+    return torch.repeat_interleave(ent, sizes * N)[:, None, None].expand(B * N, K, 1)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -191,8 +230,10 @@ def _entropy_base_terms(module, eps_a, eps_c):
 def run_network(inputs, viewdirs, fn, is_val, is_test, embed_fn=None, embeddirs_fn=None, netchunk=1024 * 64, *,
                 eps_alpha=None, eps_rgb=None, precision=None):
     """main:67-85.  inputs (B,N,3), viewdirs (B,3) -> (outputs (B,N,K,4) [rgb|sigma raw], loss_entropy).
-    `embed_fn` / `embeddirs_fn` / `netchunk` are accepted for signature compatibility: the encoding is fused into the
-    network kernel and chunking "does not affect final results" (main:112-113).  Test mode returns zeros for
+    `embed_fn` / `embeddirs_fn` are accepted for signature compatibility (the encoding is fused into the network
+    kernel).  `netchunk` does not chunk anything here (memory is bounded inside the library); it only decides, in
+    train mode, how many independent latent draws / entropy scalars the batch sees, as in the reference (one per
+    `batchify` call of netchunk points).  Test mode returns zeros for
     loss_entropy like the reference (models.py:223); train mode returns the entropy scalar broadcast to (B*N,K,1)
     (models.py:291) — use render_rays for a differentiable training step."""
     module = _unwrap(fn)
@@ -206,37 +247,52 @@ def run_network(inputs, viewdirs, fn, is_val, is_test, embed_fn=None, embeddirs_
     if vd.shape[0] != B:
         raise ValueError("viewdirs must be (B,3): one direction per ray (main:74-76)")
     train = not is_test
+    # train mode: one latent draw per batchify call of `netchunk` points (main:47-64, models.py:233-251)
+    group_rays, G = latent_groups(B, N, int(netchunk)) if train else (0, 1)
     if eps_alpha is None:
         if train:
-            eps_alpha = torch.empty([eng.K, 1], device=dev).normal_()      # models.py:234
-            eps_rgb = torch.empty([eng.K, 3], device=dev).normal_()        # models.py:246
+            pairs = [(torch.empty([eng.K, 1], device=dev).normal_(),                          # models.py:234
+                      torch.empty([eng.K, 3], device=dev).normal_()) for _ in range(G)]      # models.py:246
+            eps_alpha = torch.stack([a for a, _ in pairs], 0) if G > 1 else pairs[0][0]
+            eps_rgb = torch.stack([c for _, c in pairs], 0) if G > 1 else pairs[0][1]
         else:
             eps_alpha, eps_rgb = test_latents(module, dev)
-    eps_a, eps_c = _f32c(eps_alpha.reshape(-1), dev), _f32c(eps_rgb, dev)
+    if G > 1:
+        if eps_rgb.dim() != 3 or eps_rgb.shape[0] != G:
+            raise ValueError(f"the batch makes {G} network calls: pass eps_alpha (G,K,1) and eps_rgb (G,K,3)")
+        eps_a, eps_c = _f32c(eps_alpha.reshape(G, -1), dev), _f32c(eps_rgb, dev)
+    else:
+        eps_a, eps_c = _f32c(eps_alpha.reshape(-1), dev), _f32c(eps_rgb.reshape(-1, 3), dev)
     with torch.cuda.device(dev), torch.no_grad():
         fp = eng.network(B, N, pts=pts, viewdirs=vd)
         # raw comes out of the flow stage; compositing outputs are discarded here (z/dirs are dummies)
         z_dummy = torch.zeros(B, N, device=dev)
-        out = eng.flow_composite(fp, z_dummy, vd, 3, eps_a, eps_c, False, want_raw=True, train=train)
+        out = eng.flow_composite(fp, z_dummy, vd, 3, eps_a, eps_c, False, want_raw=True, train=train,
+                                 eps_group_rays=group_rays)
     raw = out["raw"]
     if not train:
         return raw, torch.zeros_like(raw)
     with torch.no_grad():
-        base_a, base_c = _entropy_base_terms(module, eps_a, eps_c)
-        ld = out["logdet_sums"].sum(0) / float(B * N * eng.K)
-        ent = base_a - ld[0] + base_c - ld[1]
-    return raw, ent.expand(B * N, eng.K, 1)
+        ent = _entropy_rows(module, eps_a, eps_c, out["logdet_sums"], B, N, eng.K, group_rays)
+    return raw, ent
 
 
 def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=128, is_train=False, uniformsample=False,
                 retraw=False, lindisp=False, K_samples=0, perturb=0., N_importance=0, network_fine=None,
                 white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False, *, t_rand=None, eps_alpha=None,
-                eps_rgb=None, u=None, precision=None, want_weights=False, want_kstats=False):
+                eps_rgb=None, u=None, precision=None, want_weights=False, want_kstats=False, netchunk=None):
     """main:457-553, plus the coarse+fine extension when N_importance > 0 and network_fine is given.
 
     Returns the reference dict: rgb_map (B,3,K), disp_map (B,K), depth_map (B,K); when is_train also raw
     (B,N,K,4), loss_entropy (B*N,K,1) (the per-call scalar broadcast, models.py:291) and pts (B,N,3).
-    `network_query_fn` is accepted and ignored (encoding + chunking are fused)."""
+    `network_query_fn` is accepted and ignored (encoding + chunking are fused).
+
+    `netchunk` (default: the reference's netchunk_per_gpu * 1 GPU = 65536, main:336, 604; `install(..., netchunk=)`
+    changes it) only matters in train mode, and only for what the reference's chunking makes observable: every
+    network call of netchunk points draws its own latent noise (models.py:233-251) and returns its own entropy scalar,
+    so a training batch of more than netchunk / N rays uses one (eps_alpha, eps_rgb) pair per group of netchunk / N
+    rays, drawn in the reference's order, and `loss_entropy` carries one scalar per group.  `eps_alpha` / `eps_rgb` may
+    be passed as (K,1) / (K,3) (one call) or (G,K,1) / (G,K,3) (one pair per call)."""
     module = _unwrap(network_fn)
     dev = ray_batch.device
     prec = precision or DEFAULT_PRECISION
@@ -260,13 +316,29 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=128, is_
         if t_rand is not None:
             t_rand = _f32c(t_rand, dev)
         z_vals = eng.zvals(rays, t_vals, t_rand if perturb > 0. or t_rand is not None else None, lindisp)
+        # latent draws: one pair per network call of the reference (train mode), the constructor-time draws in test mode
+        group_rays, G = (0, 1)
+        if is_train and not hier:
+            group_rays, G = latent_groups(B, N_samples, DEFAULT_NETCHUNK if netchunk is None else int(netchunk))
         if eps_alpha is None:
             if is_train:
-                eps_alpha = torch.empty([eng.K, 1], device=dev).normal_()                     # models.py:234
-                eps_rgb = torch.empty([eng.K, 3], device=dev).normal_()                       # models.py:246
+                pairs = [(torch.empty([eng.K, 1], device=dev).normal_(),                      # models.py:234
+                          torch.empty([eng.K, 3], device=dev).normal_()) for _ in range(G)]  # models.py:246
+                eps_alpha = torch.stack([a for a, _ in pairs], 0) if G > 1 else pairs[0][0]
+                eps_rgb = torch.stack([c for _, c in pairs], 0) if G > 1 else pairs[0][1]
             else:
                 eps_alpha, eps_rgb = test_latents(module, dev)
-        eps_a, eps_c = _f32c(eps_alpha.reshape(-1), dev), _f32c(eps_rgb, dev)
+        if eps_rgb.dim() == 3:      # (G,K,3): the caller fixed the draws of every network call
+            if eps_rgb.shape[0] != G and not (G == 1 and eps_rgb.shape[0] == 1):
+                raise ValueError(f"{eps_rgb.shape[0]} latent draws given but the batch makes {G} network calls "
+                                 f"({B} rays x {N_samples} samples, netchunk {netchunk or DEFAULT_NETCHUNK})")
+            eps_a, eps_c = _f32c(eps_alpha.reshape(eps_rgb.shape[0], -1), dev), _f32c(eps_rgb, dev)
+            if G == 1:
+                eps_a, eps_c = eps_a[0].contiguous(), eps_c[0].contiguous()
+        else:
+            if G > 1:
+                raise ValueError(f"the batch makes {G} network calls: pass eps_alpha (G,K,1) and eps_rgb (G,K,3)")
+            eps_a, eps_c = _f32c(eps_alpha.reshape(-1), dev), _f32c(eps_rgb, dev)
         if is_train and raw_noise_std > 0.:
             # the reference draws noise here and never adds it (main:432-442); same count keeps the RNG stream aligned
             torch.randn(B, N_samples, eng.K, device=dev)
@@ -276,10 +348,8 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=128, is_
             N = z.shape[1]
             if train:
                 rgb, disp, depth, raw, ld, w = _RenderTrainFn.apply(e, rays, z, eps_a, eps_c, bool(white_bkgd),
-                                                                    need_w, *e.params)
-                base_a, base_c = _entropy_base_terms(_unwrap(net), eps_a, eps_c)
-                cnt = float(B * N * e.K)
-                ent = base_a - ld[0] / cnt + base_c - ld[1] / cnt                             # models.py:286
+                                                                    need_w, group_rays, *e.params)
+                ent = _entropy_rows(_unwrap(net), eps_a, eps_c, ld, B, N, e.K, group_rays)    # models.py:286-291
                 return dict(rgb_map=rgb, disp_map=disp, depth_map=depth, raw=raw, weights=w if need_w else None,
                             loss_entropy=ent)
             with torch.no_grad():
@@ -312,12 +382,12 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=128, is_
             if want_kstats and o.get("kstats") is not None:
                 ret["kstats"] = o["kstats"]
             if is_train:
-                ret["loss_entropy0"] = oc["loss_entropy"].expand(B * N_samples, eng.K, 1)
+                ret["loss_entropy0"] = oc["loss_entropy"]
             z_vals = z_all
             N = z_all.shape[1]
         if is_train:
             ret["raw"] = o["raw"]
-            ret["loss_entropy"] = o["loss_entropy"].expand(B * N, eng.K, 1)                    # models.py:291
+            ret["loss_entropy"] = o["loss_entropy"]                                            # (B*N,K,1), models.py:291
             ret["pts"] = rays[:, None, 0:3] + rays[:, None, 3:6] * z_vals[..., :, None]       # main:534
     return ret
 
@@ -351,15 +421,23 @@ def render_image(H, W, focal, c2w, network_fn, near=0., far=1., ndc=False, chunk
     return [allr[k] for k in ex] + [{k: v for k, v in allr.items() if k not in ex}]
 
 
-def install(ref_module, precision: str | None = None, train_precision: str | None = None):
-    """Rebind the reference's module-global names (SURVEY §8(b)): `batchify_rays` looks `render_rays` up by global
-    name (main:93) and `render_rays` looks `raw2outputs` up the same way (main:540).  `precision` selects the render
-    mode ("fp16" default, "bf16", "tf32", "fp32"), `train_precision` the training mode ("tf32" default, "fp32")."""
-    global DEFAULT_PRECISION, DEFAULT_TRAIN_PRECISION
+def configure(precision: str | None = None, train_precision: str | None = None, netchunk: int | None = None):
+    """Module defaults used when a call does not say otherwise: render precision ("fp16" | "bf16" | "tf32" | "fp32"),
+    training precision ("tf32" | "bf16" | "fp32") and the reference's netchunk (points per network call, main:336)."""
+    global DEFAULT_PRECISION, DEFAULT_TRAIN_PRECISION, DEFAULT_NETCHUNK
+    if netchunk is not None:        # args.netchunk_per_gpu * args.n_gpus of the host script (main:336)
+        DEFAULT_NETCHUNK = int(netchunk)
     if precision is not None:
         DEFAULT_PRECISION = precision
     if train_precision is not None:
         DEFAULT_TRAIN_PRECISION = train_precision
+
+
+def install(ref_module, precision: str | None = None, train_precision: str | None = None, netchunk: int | None = None):
+    """Rebind the reference's module-global names (SURVEY §8(b)): `batchify_rays` looks `render_rays` up by global
+    name (main:93) and `render_rays` looks `raw2outputs` up the same way (main:540).  `precision` selects the render
+    mode ("fp16" default, "bf16", "tf32", "fp32"), `train_precision` the training mode ("tf32" default, "fp32")."""
+    configure(precision, train_precision, netchunk)
     ref_module.render_rays = render_rays
     ref_module.raw2outputs = raw2outputs
     return ref_module
@@ -384,13 +462,69 @@ class _KdeNllFn(torch.autograd.Function):
                   "cfn_kde_nll_f32")
         ctx.save_for_backward(g)
         tot = partial.sum(0) / (3.0 * B)
-        ctx.mark_non_differentiable(tot[1])
-        return tot[0], tot[1]
+        nll, mse = tot[0].clone(), tot[1].clone()
+        ctx.mark_non_differentiable(mse)        # the mark applies to the very tensor object that is returned
+        return nll, mse
 
     @staticmethod
     def backward(ctx, g_nll, g_mse):
         (g,) = ctx.saved_tensors
         return g * g_nll, None
+
+
+class _TrainerLossFn(torch.autograd.Function):
+    """cfn_trainer_loss_f32: KDE-NLL + mse over the colour rays and the depth squared error over the depth rays in one
+    kernel, both gradient seeds computed in the same pass."""
+
+    @staticmethod
+    def forward(ctx, rgb_map, depth_map, target, target_depth):
+        lib = _lib.load()
+        dev = rgb_map.device
+        x, d, t = _f32c(rgb_map.detach(), dev), _f32c(depth_map.detach(), dev), _f32c(target, dev)
+        B, _, K = x.shape
+        B_rgb = t.shape[0]
+        B_depth = B - B_rgb
+        td = _f32c(target_depth, dev) if B_depth else None
+        if B_depth and td.shape[0] != B_depth:
+            raise ValueError(f"{B} rays rendered, {B_rgb} colour targets, {td.shape[0]} depth targets")
+        partial = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        g_rgb, g_depth = torch.empty_like(x), torch.empty_like(d)
+        with torch.cuda.device(dev):
+            check(lib.cfn_trainer_loss_f32(_ptr(x), _ptr(d), _ptr(t), _ptr(td), B_rgb, B_depth, K, 1.0 / (3.0 * B_rgb),
+                                           (1.0 / B_depth) if B_depth else 0.0, _ptr(partial), _ptr(g_rgb), _ptr(g_depth),
+                                           _stream()), "cfn_trainer_loss_f32")
+        ctx.save_for_backward(g_rgb, g_depth)
+        tot = partial.sum(0)
+        nll, mse = tot[0] / (3.0 * B_rgb), tot[1] / (3.0 * B_rgb)
+        dl = tot[2] / B_depth if B_depth else tot[2] * 0
+        ctx.mark_non_differentiable(mse)
+        return nll, mse, dl
+
+    @staticmethod
+    def backward(ctx, g_nll, g_mse, g_dl):
+        g_rgb, g_depth = ctx.saved_tensors
+        return g_rgb * g_nll, g_depth * g_dl, None, None
+
+
+def trainer_loss(out, target_s, K, beta1=0.01, target_depth=None, depth_lambda=0.0):
+    """The loss of the trainer body, main:1018-1055, on the dict `render_rays(cat[colour rays, depth rays], ...)`
+    returned in train mode.  With depth supervision (--colmap_depth) the batch is [N_batch colour rays | depth rays]
+    (main:1009-1011): colours / entropy use the first N_batch entries (main:1021-1023 — note that `extras[x][:N_batch]`
+    slices the ROWS of the (B*N,K,1) entropy tensor, i.e. the first network call's scalar), the depth loss is
+    `img2mse(mean_K depth_map[N_batch:], target_depth)` weighted by depth_lambda (main:1020, 1053-1054)."""
+    B = out["rgb_map"].shape[0]
+    B_depth = 0 if target_depth is None else int(target_depth.shape[0])
+    N_batch = B - B_depth
+    nll, mse, dl = _TrainerLossFn.apply(out["rgb_map"], out["depth_map"], target_s, target_depth)
+    ent_rows = out["loss_entropy"]
+    ent = ent_rows[:N_batch].mean() if B_depth else ent_rows.mean()
+    loss = nll + beta1 * ent if beta1 else nll
+    res = {"loss_nll": nll, "mse": mse, "psnr": -10. * torch.log(mse) / math.log(10.), "loss_entropy": ent}
+    if B_depth:
+        loss = loss + depth_lambda * dl
+        res["depth_loss"] = dl
+    res["loss"] = loss
+    return res
 
 
 def kde_nll_loss(rgb_map, target, loss_entropy, K, beta1=0.01, fused=None):

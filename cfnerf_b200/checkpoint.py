@@ -46,9 +46,19 @@ def _load_into(module, pretrained: dict):
     return sorted(picked)
 
 
-def load_checkpoint(path, network_fn, network_fine=None, map_location="cpu"):
-    """-> (global_step, keys loaded).  The optimizer state is deliberately not restored (main:360)."""
-    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+def load_checkpoint(path, network_fn, network_fine=None, map_location="cpu", trust: bool = False):
+    """-> (global_step, keys loaded).  The optimizer state is deliberately not restored (main:360).
+
+    The file is read with `weights_only=True`: a checkpoint holds only tensors, ints and plain dicts (including the
+    optimizer state_dict and the latent key), so the restricted unpickler is enough and a third-party file cannot run
+    code.  `trust=True` falls back to the full unpickler for files that carry other Python objects (e.g. an argparse
+    namespace someone added) — only for files you produced yourself."""
+    try:
+        ckpt = torch.load(path, map_location=map_location, weights_only=True)
+    except Exception:
+        if not trust:
+            raise
+        ckpt = torch.load(path, map_location=map_location, weights_only=False)
     keys = _load_into(network_fn, ckpt["network_fn_state_dict"])
     if network_fine is not None and "network_fine_state_dict" in ckpt:
         _load_into(network_fine, ckpt["network_fine_state_dict"])

@@ -219,12 +219,17 @@ extern "C" int cfn_pack_weights(CfnHandle* h, const float* const* params, int n_
   return CFN_OK;
 }
 
+static constexpr int64_t kChainPassPoints = 262144;   // points per internal pass of the non-saving chain (~2.6 GB fp32)
+
 extern "C" int cfn_workspace_bytes(const CfnHandle* h, int64_t n_points, int save_for_backward, size_t* out) {
   CFN_CHECK_ARG(h && out && n_points >= 0, "cfn_workspace_bytes: bad argument");
   if (h->tc && !save_for_backward) {
     *out = tc_workspace_bytes(h, n_points);
     return CFN_OK;
   }
+  // the layer-by-layer chain without saved activations walks the points in passes of at most kChainPassPoints, so its
+  // workspace is bounded whatever the caller's ray chunk is (the reference bounds memory with netchunk, main:47-64)
+  if (!save_for_backward && n_points > kChainPassPoints) n_points = kChainPassPoints;
   *out = chain_workspace_floats(h, n_points, save_for_backward) * sizeof(float) + 256;
   return CFN_OK;
 }
@@ -260,7 +265,19 @@ extern "C" int cfn_network_fwd(CfnHandle* h, const float* rays, const float* z_v
   cudaStream_t s = (cudaStream_t)stream;
   if (h->tc && !save_for_backward)
     return tc_network_fwd(h, rays, z_vals, pts, viewdirs, B, N, flow_params, workspace, workspace_bytes, s);
-  return chain_network_fwd(h, rays, z_vals, pts, viewdirs, B, N, flow_params, (float*)workspace, save_for_backward, s);
+  if (save_for_backward || B * N <= kChainPassPoints)
+    return chain_network_fwd(h, rays, z_vals, pts, viewdirs, B, N, flow_params, (float*)workspace, save_for_backward, s);
+  // bounded-memory passes over whole rays (results are independent of the split: every point is independent)
+  CFN_CHECK_ARG(N <= kChainPassPoints, "cfn_network_fwd: N = %d samples per ray is too large", N);
+  const int64_t rays_per_pass = kChainPassPoints / N;
+  for (int64_t b0 = 0; b0 < B; b0 += rays_per_pass) {
+    const int64_t nb = (B - b0 < rays_per_pass) ? (B - b0) : rays_per_pass;
+    int rc = chain_network_fwd(h, rays ? rays + b0 * 11 : nullptr, z_vals ? z_vals + b0 * N : nullptr,
+                               pts ? pts + b0 * N * 3 : nullptr, viewdirs ? viewdirs + b0 * 3 : nullptr, nb, N,
+                               flow_params + b0 * N * h->PP, (float*)workspace, 0, s);
+    if (rc != CFN_OK) return rc;
+  }
+  return CFN_OK;
 }
 
 extern "C" int cfn_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, void* workspace,
@@ -278,9 +295,11 @@ extern "C" int cfn_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t
 
 extern "C" int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, const float* z_vals,
                                       const float* rays_d, int rays_d_stride, const float* eps_alpha,
-                                      const float* eps_rgb, int64_t B, int N, int white_bkgd, float* rgb_map,
-                                      float* disp_map, float* depth_map, float* raw, float* weights,
-                                      float* logdet_sums, float* kstats, void* stream) {
+                                      const float* eps_rgb, int64_t eps_group_rays, int64_t B, int N, int white_bkgd,
+                                      float* rgb_map, float* disp_map, float* depth_map, float* raw, float* weights,
+                                      float* logdet_sums, float* kstats, float* trans, void* stream) {
+  CFN_CHECK_ARG(eps_group_rays >= 0, "cfn_flow_composite_fwd: negative eps_group_rays");
+  CFN_CHECK_ARG(!trans || logdet_sums, "cfn_flow_composite_fwd: trans is written by the training flavour only (pass logdet_sums)");
   CFN_CHECK_ARG(h && B >= 0 && (B == 0 || (flow_params && z_vals && rays_d && eps_alpha && eps_rgb && rgb_map && disp_map && depth_map)),
                 "cfn_flow_composite_fwd: null argument");
   if (!h->packed) {
@@ -291,46 +310,50 @@ extern "C" int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, co
   // one-MUFU transcendentals behind every tensor-core mode (render and training); the log of the log-det stays accurate
   const int fast = (h->cfg.precision != CFN_PREC_FP32) ? 1 : 0;
   return launch_flow_composite_fwd(fast, h->cfg.F, h->cfg.K, h->globals, flow_params, z_vals, rays_d, rays_d_stride,
-                                   eps_alpha, eps_rgb, B, N, white_bkgd, rgb_map, disp_map, depth_map, raw, weights,
-                                   logdet_sums, kstats, (cudaStream_t)stream);
+                                   eps_alpha, eps_rgb, eps_group_rays, B, N, white_bkgd, rgb_map, disp_map, depth_map, raw,
+                                   weights, logdet_sums, kstats, trans, (cudaStream_t)stream);
 }
 
 static int flow_composite_bwd_impl(CfnHandle* h, const float* flow_params, const float* z_vals, const float* rays_d,
-                                  int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t B, int N,
-                                  int white_bkgd, const float* g_rgb_map, const float* g_depth_map, float g_logdet_alpha,
-                                  float g_logdet_rgb, const float* g_logdet_dev, float* g_flow_params,
-                                  float* g_globals_partial, void* stream) {
+                                  int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t eps_group_rays,
+                                  int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
+                                  float g_logdet_alpha, float g_logdet_rgb, const float* g_logdet_dev, float* trans,
+                                  int trans_valid, float* g_flow_params, float* g_globals_partial, void* stream) {
   CFN_CHECK_ARG(h && flow_params && z_vals && rays_d && eps_alpha && eps_rgb && g_rgb_map && g_flow_params &&
-                    g_globals_partial,
+                    g_globals_partial && trans,
                 "cfn_flow_composite_bwd: null argument");
+  CFN_CHECK_ARG(eps_group_rays >= 0, "cfn_flow_composite_bwd: negative eps_group_rays");
   if (!h->packed) {
     set_error("cfn_flow_composite_bwd: call cfn_pack_weights first");
     return CFN_ESTATE;
   }
   return launch_flow_composite_bwd(h->cfg.precision != CFN_PREC_FP32 ? 1 : 0, h->cfg.F, h->cfg.K, h->globals, flow_params,
-                                   z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N, white_bkgd, g_rgb_map,
-                                   g_depth_map, g_logdet_alpha, g_logdet_rgb, g_logdet_dev, g_flow_params,
-                                   g_globals_partial, (cudaStream_t)stream);
+                                   z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, eps_group_rays, B, N, white_bkgd,
+                                   g_rgb_map, g_depth_map, g_logdet_alpha, g_logdet_rgb, g_logdet_dev, trans, trans_valid,
+                                   g_flow_params, g_globals_partial, (cudaStream_t)stream);
 }
 
 extern "C" int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, const float* z_vals,
                                       const float* rays_d, int rays_d_stride, const float* eps_alpha,
-                                      const float* eps_rgb, int64_t B, int N, int white_bkgd, const float* g_rgb_map,
-                                      const float* g_depth_map, float g_logdet_alpha, float g_logdet_rgb,
-                                      float* g_flow_params, float* g_globals_partial, void* stream) {
-  return flow_composite_bwd_impl(h, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N, white_bkgd,
-                                 g_rgb_map, g_depth_map, g_logdet_alpha, g_logdet_rgb, nullptr, g_flow_params,
-                                 g_globals_partial, stream);
+                                      const float* eps_rgb, int64_t eps_group_rays, int64_t B, int N, int white_bkgd,
+                                      const float* g_rgb_map, const float* g_depth_map, float g_logdet_alpha,
+                                      float g_logdet_rgb, float* trans, int trans_valid, float* g_flow_params,
+                                      float* g_globals_partial, void* stream) {
+  return flow_composite_bwd_impl(h, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, eps_group_rays, B, N,
+                                 white_bkgd, g_rgb_map, g_depth_map, g_logdet_alpha, g_logdet_rgb, nullptr, trans,
+                                 trans_valid, g_flow_params, g_globals_partial, stream);
 }
 
 extern "C" int cfn_flow_composite_bwd_dev(CfnHandle* h, const float* flow_params, const float* z_vals,
                                           const float* rays_d, int rays_d_stride, const float* eps_alpha,
-                                          const float* eps_rgb, int64_t B, int N, int white_bkgd,
+                                          const float* eps_rgb, int64_t eps_group_rays, int64_t B, int N, int white_bkgd,
                                           const float* g_rgb_map, const float* g_depth_map, const float* g_logdet_dev,
-                                          float* g_flow_params, float* g_globals_partial, void* stream) {
+                                          float* trans, int trans_valid, float* g_flow_params, float* g_globals_partial,
+                                          void* stream) {
   CFN_CHECK_ARG(g_logdet_dev != nullptr, "cfn_flow_composite_bwd_dev: g_logdet_dev is null");
-  return flow_composite_bwd_impl(h, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N, white_bkgd,
-                                 g_rgb_map, g_depth_map, 0.f, 0.f, g_logdet_dev, g_flow_params, g_globals_partial, stream);
+  return flow_composite_bwd_impl(h, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, eps_group_rays, B, N,
+                                 white_bkgd, g_rgb_map, g_depth_map, 0.f, 0.f, g_logdet_dev, trans, trans_valid,
+                                 g_flow_params, g_globals_partial, stream);
 }
 
 extern "C" int cfn_raw2outputs_f32(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
@@ -408,10 +431,41 @@ extern "C" int cfn_kde_nll_f32(const float* rgb_map, const float* target, int64_
   return launch_kde_nll(rgb_map, target, B, K, grad_scale, partial, g_rgb_map, (cudaStream_t)stream);
 }
 
+extern "C" int cfn_trainer_loss_f32(const float* rgb_map, const float* depth_map, const float* target_rgb,
+                                    const float* target_depth, int64_t B_rgb, int64_t B_depth, int K, float nll_scale,
+                                    float depth_scale, float* partial, float* g_rgb_map, float* g_depth_map, void* stream) {
+  CFN_CHECK_ARG(B_rgb >= 0 && B_depth >= 0, "cfn_trainer_loss_f32: negative batch");
+  CFN_CHECK_ARG(B_rgb + B_depth == 0 || (rgb_map && depth_map && partial), "cfn_trainer_loss_f32: null argument");
+  CFN_CHECK_ARG(B_rgb == 0 || target_rgb, "cfn_trainer_loss_f32: target_rgb is null");
+  CFN_CHECK_ARG(B_depth == 0 || target_depth, "cfn_trainer_loss_f32: target_depth is null");
+  return launch_trainer_loss(rgb_map, depth_map, target_rgb, target_depth, B_rgb, B_depth, K, nll_scale, depth_scale, partial,
+                             g_rgb_map, g_depth_map, (cudaStream_t)stream);
+}
+
 extern "C" int cfn_adam_step_f32(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                                  float* const* exp_avg_sq, const int64_t* numels, float lr, float beta1, float beta2,
                                  float eps, int step, float grad_scale, void* stream) {
   CFN_CHECK_ARG(n_tensors == 0 || (params && grads && exp_avg && exp_avg_sq && numels), "cfn_adam_step_f32: null argument");
   return launch_adam(n_tensors, params, grads, exp_avg, exp_avg_sq, numels, lr, beta1, beta2, eps, step, grad_scale,
                      (cudaStream_t)stream);
+}
+
+extern "C" int cfn_adam_step_dev_f32(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                                     float* const* exp_avg_sq, const int64_t* numels, float* state_dev, float lr0,
+                                     float decay_rate, float decay_steps, float beta1, float beta2, float eps,
+                                     float grad_scale, void* stream) {
+  CFN_CHECK_ARG(n_tensors == 0 || (params && grads && exp_avg && exp_avg_sq && numels), "cfn_adam_step_dev_f32: null argument");
+  CFN_CHECK_ARG(state_dev != nullptr, "cfn_adam_step_dev_f32: state_dev is null");
+  return launch_adam_dev(n_tensors, params, grads, exp_avg, exp_avg_sq, numels, state_dev, lr0, decay_rate, decay_steps, beta1,
+                         beta2, eps, grad_scale, (cudaStream_t)stream);
+}
+
+extern "C" int cfn_globals_grad_f32(const CfnHandle* h, const float* g_globals_partial, int64_t B, float entropy_coef,
+                                    float* out8, void* stream) {
+  CFN_CHECK_ARG(h && g_globals_partial && out8 && B >= 0, "cfn_globals_grad_f32: bad argument");
+  if (!h->packed) {
+    set_error("cfn_globals_grad_f32: call cfn_pack_weights first");
+    return CFN_ESTATE;
+  }
+  return launch_globals_grad(g_globals_partial, B, h->globals, entropy_coef, out8, (cudaStream_t)stream);
 }

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/cfnerf_b200.h"
 
 namespace cfn {
@@ -28,6 +30,29 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 #define CFN_LAUNCH_CHECK() CFN_CUDA(cudaGetLastError())
+
+// ---- per-device process state ---------------------------------------------------------------------------
+// cudaFuncSetAttribute and the SM count belong to ONE device; an Engine may be created on any device of the process
+// (and from any thread), so "done once" flags are kept per device ordinal.  Setting an attribute twice is harmless,
+// which makes the relaxed atomics sufficient.
+constexpr int kMaxDevices = 64;
+inline int current_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < kMaxDevices) ? d : 0; }
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool done() const { return (mask.load(std::memory_order_acquire) >> current_device()) & 1ull; }
+  void mark() { mask.fetch_or(1ull << current_device(), std::memory_order_release); }
+};
+inline int device_num_sms() {
+  static std::atomic<int> n[kMaxDevices];
+  const int d = current_device();
+  int v = n[d].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d);
+    if (v <= 0) v = 148;
+    n[d].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 
 // ---- fp32 math of the non-GEMM kernels (the library is compiled WITHOUT --use_fast_math) --------------
 // Two flavours.  FAST = false: accurate libdevice functions, used by the fp32 "check" path (1e-5 bar).
@@ -68,20 +93,28 @@ int launch_sample_pdf(const float* bins, const float* weights, const float* u, f
 int launch_merge_sorted(const float* a, const float* b, float* out, int64_t B, int Na, int Nb, cudaStream_t s);
 int launch_kde_nll(const float* rgb_map, const float* target, int64_t B, int K, float grad_scale, float* partial, float* g,
                    cudaStream_t s);
+int launch_trainer_loss(const float* rgb_map, const float* depth_map, const float* target_rgb, const float* target_depth,
+                        int64_t B_rgb, int64_t B_depth, int K, float nll_scale, float depth_scale, float* partial, float* g_rgb,
+                        float* g_depth, cudaStream_t s);
 int launch_adam(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                 float* const* exp_avg_sq, const int64_t* numels, float lr, float beta1, float beta2, float eps, int step,
                 float grad_scale, cudaStream_t s);
+int launch_adam_dev(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                    float* const* exp_avg_sq, const int64_t* numels, float* state, float lr0, float decay_rate,
+                    float decay_steps, float beta1, float beta2, float eps, float grad_scale, cudaStream_t s);
+int launch_globals_grad(const float* partial, int64_t B, const float* globals8, float ent_coef, float* out, cudaStream_t s);
 int launch_mean_over_k(const float* w, float* out, int64_t rows, int K, cudaStream_t s);
 
 int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
-                              int64_t B, int N, int white_bkgd, float* rgb_map, float* disp_map, float* depth_map,
-                              float* raw, float* weights, float* logdet_sums, float* kstats, cudaStream_t s);
+                              int64_t eps_group_rays, int64_t B, int N, int white_bkgd, float* rgb_map, float* disp_map,
+                              float* depth_map, float* raw, float* weights, float* logdet_sums, float* kstats, float* trans,
+                              cudaStream_t s);
 int launch_flow_composite_bwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
-                              int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
-                              float g_ld_alpha, float g_ld_rgb, const float* g_ld_dev, float* g_flow_params, float* g_globals,
-                              cudaStream_t s);
+                              int64_t eps_group_rays, int64_t B, int N, int white_bkgd, const float* g_rgb_map,
+                              const float* g_depth_map, float g_ld_alpha, float g_ld_rgb, const float* g_ld_dev,
+                              float* trans, int trans_valid, float* g_flow_params, float* g_globals, cudaStream_t s);
 
 // C[m,n] = epi( sum_k A(m,k) * B(k,n) + bias[n] ) with arbitrary element strides (fp32 CUDA-core GEMM).
 enum Epilogue { EPI_NONE = 0, EPI_RELU = 1, EPI_TANH_MASK = 2, EPI_RELU_MASK_MUL = 3 };

@@ -42,10 +42,11 @@ template <int MAXV, bool TRAIN, bool FAST, int FT>
 __global__ void __launch_bounds__(128)
 flow_composite_fwd_kernel(int F_rt, int K, const float* __restrict__ globals, const float* __restrict__ flow_params,
                           const float* __restrict__ z_vals, const float* __restrict__ rays_d, int rays_d_stride,
-                          const float* __restrict__ eps_alpha, const float* __restrict__ eps_rgb, int64_t B, int N,
+                          const float* __restrict__ eps_alpha, const float* __restrict__ eps_rgb,
+                          int64_t eps_group_rays, int64_t B, int N,
                           int white_bkgd, float* __restrict__ rgb_map, float* __restrict__ disp_map,
                           float* __restrict__ depth_map, float* __restrict__ raw, float* __restrict__ weights,
-                          float* __restrict__ logdet_sums, float* __restrict__ kstats) {
+                          float* __restrict__ logdet_sums, float* __restrict__ kstats, float* __restrict__ trans) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // FT > 0: the number of flows is a compile-time constant (the shipped recipe, F = 4): a point's 18F scalars are
@@ -58,6 +59,11 @@ flow_composite_fwd_kernel(int F_rt, int K, const float* __restrict__ globals, co
   float* sd = sz + N;                  // dists * |d|
   const int64_t b = (int64_t)blockIdx.x * 4 + warp;
   if (b >= B) return;
+  // base latent draws: one (K) / (K,3) set per group of eps_group_rays consecutive rays (the reference draws fresh noise
+  // in every network call of netchunk points, models.py:233-251; 0 = one set shared by all rays)
+  const int64_t egrp = eps_group_rays > 0 ? b / eps_group_rays : 0;
+  eps_alpha += egrp * K;
+  eps_rgb += egrp * K * 3;
 
   for (int n = lane; n < N; n += 32) sz[n] = z_vals[b * N + n];
   const float* d = rays_d + b * rays_d_stride;
@@ -162,6 +168,7 @@ flow_composite_fwd_kernel(int F_rt, int K, const float* __restrict__ globals, co
         // ---- compositing (raw2outputs) ----
         const float alpha = 1.0f - exp_<FAST>(-softplus_<FAST>(za) * sd[n]);
         const float w = alpha * T;
+        if (TRAIN && trans && active) trans[(b * N + n) * K + k] = T;   // transmittance in front of sample n (K4 reads it)
         T = T * ((1.0f - alpha) + 1e-10f);
         cr += w * sigmoid_<FAST>(z0);
         cg += w * sigmoid_<FAST>(z1);
@@ -243,8 +250,9 @@ static size_t fwd_smem_bytes(int F, int N) { return (size_t)4 * ((kChunk * 18 * 
 
 int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
-                              int64_t B, int N, int white_bkgd, float* rgb_map, float* disp_map, float* depth_map,
-                              float* raw, float* weights, float* logdet_sums, float* kstats, cudaStream_t s) {
+                              int64_t eps_group_rays, int64_t B, int N, int white_bkgd, float* rgb_map, float* disp_map,
+                              float* depth_map, float* raw, float* weights, float* logdet_sums, float* kstats, float* trans,
+                              cudaStream_t s) {
   if (B == 0) return CFN_OK;
   CFN_CHECK_ARG(F >= 1 && F <= kMaxF, "flow_composite: n_flows=%d unsupported (1..%d)", F, kMaxF);
   CFN_CHECK_ARG(N >= 1 && N <= 2048 && K >= 1, "flow_composite: unsupported N=%d K=%d (need 1 <= N <= 2048)", N, K);
@@ -256,8 +264,9 @@ int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals,
     auto kern = fast_math ? (F == 4 ? flow_composite_fwd_kernel<MAXV, TR, true, 4> : flow_composite_fwd_kernel<MAXV, TR, true, 0>)\
                           : (F == 4 ? flow_composite_fwd_kernel<MAXV, TR, false, 4> : flow_composite_fwd_kernel<MAXV, TR, false, 0>);                                                            \
     if (smem > 48 * 1024) CFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, 128, smem, s>>>(F, K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N, \
-                                 white_bkgd, rgb_map, disp_map, depth_map, raw, weights, logdet_sums, kstats);    \
+    kern<<<grid, 128, smem, s>>>(F, K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb,   \
+                                 eps_group_rays, B, N, white_bkgd, rgb_map, disp_map, depth_map, raw, weights,    \
+                                 logdet_sums, kstats, trans);                                                     \
   } while (0)
   if (F <= 4) {
     if (train) CFN_FWD_LAUNCH(9, true); else CFN_FWD_LAUNCH(9, false);
@@ -270,39 +279,117 @@ int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals,
 }
 
 // =====================================================================================================
-// Backward (K4).  Per ray-warp and K group:
-//   pass 1 (front to back): alpha stack only -> T_n kept in shared memory (N x 32 floats per warp);
-//   pass 2 (back to front): recompute both stacks with their intermediates in registers, compositing
-//   adjoint with the suffix sum S (Appendix A.2), flow adjoint step by step in reverse (Appendix A.1), and a
-//   shared-memory transpose-reduction of the 18F per-point parameter gradients over the 32 latent lanes.
+// Backward (K4).  One warp per ray, lane = latent sample k, ONE pass back to front:
+//   * the transmittance T_n in front of every sample comes from HBM (B,N,K): the training forward writes it for free
+//     (K2 `trans` output), or `trans_prepass_kernel` (alpha stack only) fills it when the caller has none.  Keeping it in
+//     shared memory (round 1: N x 32 floats per warp) capped the kernel at 8 warps per SM, and at ~1200 dependent
+//     instructions per point the kernel is latency bound: occupancy is what it needs;
+//   * per point both stacks are recomputed with their intermediates in registers, the compositing adjoint carries the
+//     suffix sum S (Appendix A.2), the flow adjoints run step by step in reverse (Appendix A.1);
+//   * the 18F per-point parameter gradients are reduced over the 32 latent lanes 16 rows at a time through a small
+//     double-buffered shared-memory scratch (16 x 36 floats: conflict-free column stores, two lanes per row read four
+//     float4 each, one shuffle joins the halves) — one __syncwarp per 16 rows, 4.5 KB per warp instead of 10 KB;
+//   * parameters are staged PB points at a time (coalesced loads, register prefetch of the next block) and the reduced
+//     gradient rows of a block leave through shared memory as contiguous stores.
 // Gradients w.r.t. the global latent parameters through z0 = eps*std + mean are summed per ray into
 // g_globals_partial (B,8) (deterministic; the host sums over rays).
 // =====================================================================================================
+constexpr int kBwdPB = 4;     // points per staged block
+constexpr int kBwdGLD = 36;   // row stride of the reduction scratch: 32 lanes + 4 (rows stay 16-byte aligned, no conflicts)
+
 template <int FT, bool FAST>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
+trans_prepass_kernel(int K, const float* __restrict__ globals, const float* __restrict__ flow_params,
+                     const float* __restrict__ z_vals, const float* __restrict__ rays_d, int rays_d_stride,
+                     const float* __restrict__ eps_alpha, int64_t eps_group_rays, int64_t B, int N,
+                     float* __restrict__ trans) {
+  constexpr int F = FT, PP = 18 * FT;
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const int64_t egrp = eps_group_rays > 0 ? b / eps_group_rays : 0;
+  eps_alpha += egrp * K;
+  const float* d = rays_d + b * rays_d_stride;
+  const float norm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  const float a_mean = globals[0], a_std = globals[1];
+  const float* prow = flow_params + (b * N) * PP;
+  const float* zrow = z_vals + b * N;
+  for (int k = lane; k < K; k += 32) {
+    const float za0 = eps_alpha[k] * a_std + a_mean;
+    float T = 1.0f;
+    float zn = __ldg(zrow);
+    for (int n = 0; n < N; ++n) {
+      const float* P = prow + (int64_t)n * PP;   // warp-uniform address: one broadcast transaction
+      const float znext = (n < N - 1) ? __ldg(zrow + n + 1) : 0.f;
+      const float dist = ((n < N - 1) ? (znext - zn) : 10.0f) * norm;
+      zn = znext;
+      float za = za0;
+#pragma unroll
+      for (int f = 0; f < F; ++f) za += __ldg(P + f) * tanh_<FAST>(__ldg(P + F + f) * za + __ldg(P + 2 * F + f));
+      const float alpha = 1.0f - exp_<FAST>(-softplus_<FAST>(za) * dist);
+      trans[(b * N + n) * K + k] = T;
+      T = T * ((1.0f - alpha) + 1e-10f);
+    }
+  }
+}
+
+// sum v[0..NV) over the 32 lanes, 16 rows per round; row r of round g0 lands in out[g0 + r]
+template <int NV>
+__device__ __forceinline__ void reduce_rows_over_lanes(const float (&v)[NV], float* __restrict__ sG, int& buf,
+                                                       float* __restrict__ out, int lane) {
+  const int row = lane >> 1, half = lane & 1;
+#pragma unroll
+  for (int g0 = 0; g0 < NV; g0 += 16) {
+    constexpr int kRows = 16;
+    const int cnt = (NV - g0 < kRows) ? (NV - g0) : kRows;
+    float* S = sG + buf * (16 * kBwdGLD);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (g0 + i < NV) S[i * kBwdGLD + lane] = v[g0 + i];
+    __syncwarp();
+    float acc = 0.f;
+    if (row < cnt) {
+      const float4* r4 = reinterpret_cast<const float4*>(S + row * kBwdGLD + half * 16);
+      const float4 a = r4[0], b4 = r4[1], c = r4[2], d = r4[3];
+      acc = ((a.x + a.y) + (a.z + a.w)) + ((b4.x + b4.y) + (b4.z + b4.w)) + (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (half == 0 && row < cnt) out[g0 + row] = acc;
+    buf ^= 1;   // the buffer written two rounds ago is free again: every lane passed a __syncwarp after reading it
+  }
+}
+
+template <int FT, bool FAST>
+__global__ void __launch_bounds__(128, 4)
 flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float* __restrict__ flow_params,
                           const float* __restrict__ z_vals, const float* __restrict__ rays_d, int rays_d_stride,
-                          const float* __restrict__ eps_alpha, const float* __restrict__ eps_rgb, int64_t B, int N,
-                          int white_bkgd, const float* __restrict__ g_rgb_map, const float* __restrict__ g_depth_map,
-                          float gl_a_host, float gl_c_host, const float* __restrict__ g_ld_dev,
+                          const float* __restrict__ eps_alpha, const float* __restrict__ eps_rgb, int64_t eps_group_rays,
+                          int64_t B, int N, int white_bkgd, const float* __restrict__ g_rgb_map,
+                          const float* __restrict__ g_depth_map, float gl_a_host, float gl_c_host,
+                          const float* __restrict__ g_ld_dev, const float* __restrict__ trans,
                           float* __restrict__ g_flow_params, float* __restrict__ g_globals_partial) {
-  // gradient seeds of the two log-det sums: by value, or (g_ld_dev != nullptr) read from the device so that the host
-  // never has to wait for the loss graph before it can issue the backward
-  const float gl_a = g_ld_dev ? g_ld_dev[0] : gl_a_host;
-  const float gl_c = g_ld_dev ? g_ld_dev[1] : gl_c_host;
   constexpr int F = FT;
   constexpr int PP = 18 * F;
+  constexpr int PB = kBwdPB;
+  constexpr int NPRE = (PB * PP + 31) / 32;
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int GLD = 36;               // row stride of the transpose scratch: 32 lanes + 4 (rows stay 16-byte aligned)
-  const int per_warp = ((2 * N + 3) & ~3) + N * 32 + PP * GLD + ((PP + 3) & ~3);   // every region 16-byte aligned
+  const int zd = (2 * N + 3) & ~3;
+  const int per_warp = zd + 2 * PB * PP + 2 * 16 * kBwdGLD;   // every region 16-byte aligned (PB * PP is a multiple of 4)
   float* sz = smem + warp * per_warp;   // z
-  float* sd = sz + N;                   // dists
-  float* sT = sz + ((2 * N + 3) & ~3);  // T_n per lane      [N][32]
-  float* sG = sT + N * 32;              // gradient transpose scratch [PP][GLD]
-  float* sP = sG + PP * GLD;            // parameters of the current point [PP]
+  float* sd = sz + N;                   // dists * |d|
+  float* sP = sz + zd;                  // parameters of the current block [PB][PP]
+  float* sO = sP + PB * PP;             // reduced gradient rows of the block [PB][PP]
+  float* sG = sO + PB * PP;             // reduction scratch [2][16][GLD]
   const int64_t b = (int64_t)blockIdx.x * 4 + warp;
   if (b >= B) return;
+  // gradient seeds of the two log-det sums of THIS ray: by value (host scalars), or read from the device (B,2) so that
+  // the host never waits for the loss graph and rays of different network calls / loss terms can carry different seeds
+  const float gl_a = g_ld_dev ? g_ld_dev[b * 2 + 0] : gl_a_host;
+  const float gl_c = g_ld_dev ? g_ld_dev[b * 2 + 1] : gl_c_host;
+  const int64_t egrp = eps_group_rays > 0 ? b / eps_group_rays : 0;
+  eps_alpha += egrp * K;
+  eps_rgb += egrp * K * 3;
 
   for (int n = lane; n < N; n += 32) sz[n] = z_vals[b * N + n];
   const float* d = rays_d + b * rays_d_stride;
@@ -317,8 +404,11 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
   const float c_std[3] = {globals[5], globals[6], globals[7]};
   const float* prow = flow_params + (b * N) * PP;
   float* grow = g_flow_params + (b * N) * PP;
+  const float* trow = trans + (b * N) * K;
   const int KG = (K + 31) / 32;
+  const int n_blocks = (N + PB - 1) / PB;
   float gg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d/d[a_mean, a_std, c_mean(3), c_std(3)]
+  int rbuf = 0;
 
   for (int kg = 0; kg < KG; ++kg) {
     const int k = kg * 32 + lane;
@@ -339,159 +429,161 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
       if (g_depth_map) gD = g_depth_map[b * K + k];
     }
     const float gA = white_bkgd ? -(gC[0] + gC[1] + gC[2]) : 0.f;
+    const float gla = active ? gl_a : 0.f, glc = active ? gl_c : 0.f;
 
-    // ---- pass 1: alpha stack, transmittance ----
-    {
-      float T = 1.0f;
-      for (int n = 0; n < N; ++n) {
-        const float* P = prow + (int64_t)n * PP;   // warp-uniform address: one broadcast transaction
-        float za = za0;
-#pragma unroll
-        for (int f = 0; f < F; ++f) za += __ldg(P + f) * tanh_<FAST>(__ldg(P + F + f) * za + __ldg(P + 2 * F + f));
-        const float alpha = 1.0f - exp_<FAST>(-softplus_<FAST>(za) * sd[n]);
-        sT[n * 32 + lane] = T;
-        T = T * ((1.0f - alpha) + 1e-10f);
-      }
-    }
-    __syncwarp();
-
-    // ---- pass 2: back to front ----
     float S = 0.f;
-    // the parameters of point n-1 are requested while point n is processed (PP <= 144: at most 5 values per lane)
-    constexpr int NPRE = (PP + 31) / 32;
-    float pre[NPRE];
+    // register prefetch of the next block's parameters and transmittances while the current block is processed
+    float pre[NPRE], tpre[PB];
+    {
+      const int c = n_blocks - 1, n0 = c * PB, cnt = (N - n0) * PP;
 #pragma unroll
-    for (int u = 0; u < NPRE; ++u) pre[u] = (lane + 32 * u < PP) ? __ldg(prow + (int64_t)(N - 1) * PP + lane + 32 * u) : 0.f;
-    for (int n = N - 1; n >= 0; --n) {
-      // stage the point's parameters (PP floats) into shared memory
+      for (int u = 0; u < NPRE; ++u) pre[u] = (lane + 32 * u < cnt) ? __ldg(prow + (int64_t)n0 * PP + lane + 32 * u) : 0.f;
 #pragma unroll
-      for (int u = 0; u < NPRE; ++u) if (lane + 32 * u < PP) sP[lane + 32 * u] = pre[u];
+      for (int i = 0; i < PB; ++i) tpre[i] = (active && n0 + i < N) ? __ldg(trow + (int64_t)(n0 + i) * K + k) : 0.f;
+    }
+    for (int c = n_blocks - 1; c >= 0; --c) {
+      const int n0 = c * PB;
+      const int npts = min(PB, N - n0);
+      float tcur[PB];
+#pragma unroll
+      for (int u = 0; u < NPRE; ++u) if (lane + 32 * u < PB * PP) sP[lane + 32 * u] = pre[u];
+#pragma unroll
+      for (int i = 0; i < PB; ++i) tcur[i] = tpre[i];
       __syncwarp();
-      if (n > 0) {
+      if (c > 0) {
+        const int m0 = n0 - PB;   // full block
 #pragma unroll
-        for (int u = 0; u < NPRE; ++u) pre[u] = (lane + 32 * u < PP) ? __ldg(prow + (int64_t)(n - 1) * PP + lane + 32 * u) : 0.f;
+        for (int u = 0; u < NPRE; ++u) pre[u] = (lane + 32 * u < PB * PP) ? __ldg(prow + (int64_t)m0 * PP + lane + 32 * u) : 0.f;
+#pragma unroll
+        for (int i = 0; i < PB; ++i) tpre[i] = active ? __ldg(trow + (int64_t)(m0 + i) * K + k) : 0.f;
       }
-      // recompute alpha stack with intermediates
-      float za_in[F], ta[F];
-      float za = za0;
 #pragma unroll
-      for (int f = 0; f < F; ++f) {
-        za_in[f] = za;
-        ta[f] = tanh_<FAST>(sP[F + f] * za + sP[2 * F + f]);
-        za += sP[f] * ta[f];
-      }
-      // recompute rgb stack with intermediates
-      float zp[F][3], tc[F][3];
-      float z[3] = {zc0[0], zc0[1], zc0[2]};
+      for (int i = PB - 1; i >= 0; --i) {
+        if (i < npts) {
+          const int n = n0 + i;
+          const float* Pn = sP + i * PP;
+          float* On = sO + i * PP;
+          // recompute alpha stack with intermediates
+          float za_in[F], ta[F];
+          float za = za0;
 #pragma unroll
-      for (int f = 0; f < F; ++f) {
-        const float* Q = sP + 3 * F + kRgbFlowRec * f;
-        const bool odd = f & 1;
-        zp[f][0] = odd ? z[2] : z[0]; zp[f][1] = z[1]; zp[f][2] = odd ? z[0] : z[2];
-        tc[f][0] = tanh_<FAST>(Q[6] * zp[f][0] + Q[7] * zp[f][1] + Q[8] * zp[f][2] + Q[12]);
-        tc[f][1] = tanh_<FAST>(Q[9] * zp[f][1] + Q[10] * zp[f][2] + Q[13]);
-        tc[f][2] = tanh_<FAST>(Q[11] * zp[f][2] + Q[14]);
-        const float s0 = Q[0] * tc[f][0] + Q[1] * tc[f][1] + Q[2] * tc[f][2];
-        const float s1 = Q[3] * tc[f][1] + Q[4] * tc[f][2];
-        const float s2 = Q[5] * tc[f][2];
-        z[0] += odd ? s2 : s0; z[1] += s1; z[2] += odd ? s0 : s2;
-      }
-      // ---- compositing adjoint (Appendix A.2) ----
-      const float T = sT[n * 32 + lane];
-      const float alpha = 1.0f - exp_<FAST>(-softplus_<FAST>(za) * sd[n]);
-      const float w = alpha * T;
-      const float q = (1.0f - alpha) + 1e-10f;
-      float col[3];
+          for (int f = 0; f < F; ++f) {
+            za_in[f] = za;
+            ta[f] = tanh_<FAST>(Pn[F + f] * za + Pn[2 * F + f]);
+            za += Pn[f] * ta[f];
+          }
+          // recompute rgb stack with intermediates
+          float zp[F][3], tc[F][3];
+          float z[3] = {zc0[0], zc0[1], zc0[2]};
 #pragma unroll
-      for (int c = 0; c < 3; ++c) col[c] = sigmoid_<FAST>(z[c]);
-      const float v = gC[0] * col[0] + gC[1] * col[1] + gC[2] * col[2] + gD * sz[n] + gA;
-      const float g_alpha = v * T - S / q;
-      S += v * w;
-      // d alpha / d raw_sigma = (1-alpha) * delta * sigmoid(raw_sigma);  entropy activation term (models.py:263)
-      float g_za = g_alpha * (1.0f - alpha) * sd[n] * sigmoid_<FAST>(za) + gl_a * (1.0f - sigmoid_<FAST>(za));
-      float gz[3];
+          for (int f = 0; f < F; ++f) {
+            const float* Q = Pn + 3 * F + kRgbFlowRec * f;
+            const bool odd = f & 1;
+            zp[f][0] = odd ? z[2] : z[0]; zp[f][1] = z[1]; zp[f][2] = odd ? z[0] : z[2];
+            tc[f][0] = tanh_<FAST>(Q[6] * zp[f][0] + Q[7] * zp[f][1] + Q[8] * zp[f][2] + Q[12]);
+            tc[f][1] = tanh_<FAST>(Q[9] * zp[f][1] + Q[10] * zp[f][2] + Q[13]);
+            tc[f][2] = tanh_<FAST>(Q[11] * zp[f][2] + Q[14]);
+            const float s0 = Q[0] * tc[f][0] + Q[1] * tc[f][1] + Q[2] * tc[f][2];
+            const float s1 = Q[3] * tc[f][1] + Q[4] * tc[f][2];
+            const float s2 = Q[5] * tc[f][2];
+            z[0] += odd ? s2 : s0; z[1] += s1; z[2] += odd ? s0 : s2;
+          }
+          // ---- compositing adjoint (Appendix A.2) ----
+          const float T = tcur[i];
+          const float sig_za = sigmoid_<FAST>(za);
+          const float alpha = 1.0f - exp_<FAST>(-softplus_<FAST>(za) * sd[n]);
+          const float w = alpha * T;
+          const float q = (1.0f - alpha) + 1e-10f;
+          float col[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        gz[c] = w * gC[c] * col[c] * (1.0f - col[c]) + gl_c * (1.0f - 2.0f * col[c]);  // models.py:278
-      if (!active) { g_za = 0.f; gz[0] = gz[1] = gz[2] = 0.f; }
-      const float gla = active ? gl_a : 0.f, glc = active ? gl_c : 0.f;
+          for (int cc = 0; cc < 3; ++cc) col[cc] = sigmoid_<FAST>(z[cc]);
+          const float v = gC[0] * col[0] + gC[1] * col[1] + gC[2] * col[2] + gD * sz[n] + gA;
+          const float g_alpha = v * T - S / q;
+          S += v * w;
+          // d alpha / d raw_sigma = (1-alpha) * delta * sigmoid(raw_sigma);  entropy activation term (models.py:263)
+          float g_za = g_alpha * (1.0f - alpha) * sd[n] * sig_za + gl_a * (1.0f - sig_za);
+          float gz[3];
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc)
+            gz[cc] = w * gC[cc] * col[cc] * (1.0f - col[cc]) + gl_c * (1.0f - 2.0f * col[cc]);  // models.py:278
+          if (!active) { g_za = 0.f; gz[0] = gz[1] = gz[2] = 0.f; }
 
-      // ---- alpha stack adjoint (Appendix A.1 with z_size 1) ----
+          // ---- alpha stack adjoint (Appendix A.1 with z_size 1) ----
+          float ga[3 * F];
 #pragma unroll
-      for (int f = F - 1; f >= 0; --f) {
-        const float d1 = sP[f], d2 = sP[F + f];
-        const float t = ta[f], omt2 = 1.0f - t * t;
-        const float u = omt2 * (d1 * d2) + 1.0f;
-        const float sgn = (u > 0.f) ? 1.f : ((u < 0.f) ? -1.f : 0.f);
-        const float sl = gla * sgn / (fabsf(u) + 1e-8f);
-        const float g_d1 = g_za * t + sl * omt2 * d2;
-        const float gt = d1 * g_za + sl * (-2.0f * t * d1 * d2);
-        const float gpre = gt * omt2;
-        const float g_d2 = gpre * za_in[f] + sl * omt2 * d1;
-        g_za = g_za + d2 * gpre;
-        sG[(f)*GLD + lane] = g_d1;
-        sG[(F + f) * GLD + lane] = g_d2;
-        sG[(2 * F + f) * GLD + lane] = gpre;
+          for (int f = F - 1; f >= 0; --f) {
+            const float d1 = Pn[f], d2 = Pn[F + f];
+            const float t = ta[f], omt2 = 1.0f - t * t;
+            const float u = omt2 * (d1 * d2) + 1.0f;
+            const float sgn = (u > 0.f) ? 1.f : ((u < 0.f) ? -1.f : 0.f);
+            const float sl = gla * sgn / (fabsf(u) + 1e-8f);
+            const float g_d1 = g_za * t + sl * omt2 * d2;
+            const float gt = d1 * g_za + sl * (-2.0f * t * d1 * d2);
+            const float gpre = gt * omt2;
+            const float g_d2 = gpre * za_in[f] + sl * omt2 * d1;
+            g_za = g_za + d2 * gpre;
+            ga[f] = g_d1; ga[F + f] = g_d2; ga[2 * F + f] = gpre;
+          }
+          reduce_rows_over_lanes<3 * F>(ga, sG, rbuf, On, lane);
+          // ---- rgb stack adjoint ----
+#pragma unroll
+          for (int f = F - 1; f >= 0; --f) {
+            const float* Q = Pn + 3 * F + kRgbFlowRec * f;
+            float G[kRgbFlowRec];
+            const bool odd = f & 1;
+            // gy = P g'
+            const float gy0 = odd ? gz[2] : gz[0], gy1 = gz[1], gy2 = odd ? gz[0] : gz[2];
+            const float t0 = tc[f][0], t1 = tc[f][1], t2 = tc[f][2];
+            const float o0 = 1.0f - t0 * t0, o1 = 1.0f - t1 * t1, o2 = 1.0f - t2 * t2;
+            const float dd0 = Q[0] * Q[6], dd1 = Q[3] * Q[9], dd2 = Q[5] * Q[11];
+            const float u0 = o0 * dd0 + 1.0f, u1 = o1 * dd1 + 1.0f, u2 = o2 * dd2 + 1.0f;
+            const float sl0 = glc * ((u0 > 0.f) ? 1.f : ((u0 < 0.f) ? -1.f : 0.f)) / (fabsf(u0) + 1e-8f);
+            const float sl1 = glc * ((u1 > 0.f) ? 1.f : ((u1 < 0.f) ? -1.f : 0.f)) / (fabsf(u1) + 1e-8f);
+            const float sl2 = glc * ((u2 > 0.f) ? 1.f : ((u2 < 0.f) ? -1.f : 0.f)) / (fabsf(u2) + 1e-8f);
+            // gR1 = gy t^T (upper), diagonal gets the log-det term
+            G[0] = gy0 * t0 + sl0 * o0 * Q[6];
+            G[1] = gy0 * t1;
+            G[2] = gy0 * t2;
+            G[3] = gy1 * t1 + sl1 * o1 * Q[9];
+            G[4] = gy1 * t2;
+            G[5] = gy2 * t2 + sl2 * o2 * Q[11];
+            // gt = R1^T gy + log-det term
+            const float gt0 = Q[0] * gy0 + sl0 * (-2.0f * t0 * dd0);
+            const float gt1 = Q[1] * gy0 + Q[3] * gy1 + sl1 * (-2.0f * t1 * dd1);
+            const float gt2 = Q[2] * gy0 + Q[4] * gy1 + Q[5] * gy2 + sl2 * (-2.0f * t2 * dd2);
+            const float gp0 = gt0 * o0, gp1 = gt1 * o1, gp2 = gt2 * o2;
+            // gR2 = gpre zp^T (upper), diagonal gets the log-det term
+            G[6] = gp0 * zp[f][0] + sl0 * o0 * Q[0];
+            G[7] = gp0 * zp[f][1];
+            G[8] = gp0 * zp[f][2];
+            G[9] = gp1 * zp[f][1] + sl1 * o1 * Q[3];
+            G[10] = gp1 * zp[f][2];
+            G[11] = gp2 * zp[f][2] + sl2 * o2 * Q[5];
+            G[12] = gp0;
+            G[13] = gp1;
+            G[14] = gp2;
+            // gz = g' + P (R2^T gpre)
+            const float r0 = Q[6] * gp0;
+            const float r1 = Q[7] * gp0 + Q[9] * gp1;
+            const float r2 = Q[8] * gp0 + Q[10] * gp1 + Q[11] * gp2;
+            gz[0] += odd ? r2 : r0;
+            gz[1] += r1;
+            gz[2] += odd ? r0 : r2;
+            reduce_rows_over_lanes<kRgbFlowRec>(G, sG, rbuf, On + 3 * F + kRgbFlowRec * f, lane);
+          }
+          // gradients of the base samples z0 = eps*std + mean
+          gg[0] += g_za; gg[1] += ea * g_za;
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) { gg[2 + cc] += gz[cc]; gg[5 + cc] += ec[cc] * gz[cc]; }
+        }
       }
-      // ---- rgb stack adjoint ----
-#pragma unroll
-      for (int f = F - 1; f >= 0; --f) {
-        const float* Q = sP + 3 * F + kRgbFlowRec * f;
-        float* G = sG + (3 * F + kRgbFlowRec * f) * GLD + lane;
-        const bool odd = f & 1;
-        // gy = P g'
-        const float gy0 = odd ? gz[2] : gz[0], gy1 = gz[1], gy2 = odd ? gz[0] : gz[2];
-        const float t0 = tc[f][0], t1 = tc[f][1], t2 = tc[f][2];
-        const float o0 = 1.0f - t0 * t0, o1 = 1.0f - t1 * t1, o2 = 1.0f - t2 * t2;
-        const float dd0 = Q[0] * Q[6], dd1 = Q[3] * Q[9], dd2 = Q[5] * Q[11];
-        const float u0 = o0 * dd0 + 1.0f, u1 = o1 * dd1 + 1.0f, u2 = o2 * dd2 + 1.0f;
-        const float sl0 = glc * ((u0 > 0.f) ? 1.f : ((u0 < 0.f) ? -1.f : 0.f)) / (fabsf(u0) + 1e-8f);
-        const float sl1 = glc * ((u1 > 0.f) ? 1.f : ((u1 < 0.f) ? -1.f : 0.f)) / (fabsf(u1) + 1e-8f);
-        const float sl2 = glc * ((u2 > 0.f) ? 1.f : ((u2 < 0.f) ? -1.f : 0.f)) / (fabsf(u2) + 1e-8f);
-        // gR1 = gy t^T (upper), diagonal gets the log-det term
-        G[0 * GLD] = gy0 * t0 + sl0 * o0 * Q[6];
-        G[1 * GLD] = gy0 * t1;
-        G[2 * GLD] = gy0 * t2;
-        G[3 * GLD] = gy1 * t1 + sl1 * o1 * Q[9];
-        G[4 * GLD] = gy1 * t2;
-        G[5 * GLD] = gy2 * t2 + sl2 * o2 * Q[11];
-        // gt = R1^T gy + log-det term
-        const float gt0 = Q[0] * gy0 + sl0 * (-2.0f * t0 * dd0);
-        const float gt1 = Q[1] * gy0 + Q[3] * gy1 + sl1 * (-2.0f * t1 * dd1);
-        const float gt2 = Q[2] * gy0 + Q[4] * gy1 + Q[5] * gy2 + sl2 * (-2.0f * t2 * dd2);
-        const float gp0 = gt0 * o0, gp1 = gt1 * o1, gp2 = gt2 * o2;
-        // gR2 = gpre zp^T (upper), diagonal gets the log-det term
-        G[6 * GLD] = gp0 * zp[f][0] + sl0 * o0 * Q[0];
-        G[7 * GLD] = gp0 * zp[f][1];
-        G[8 * GLD] = gp0 * zp[f][2];
-        G[9 * GLD] = gp1 * zp[f][1] + sl1 * o1 * Q[3];
-        G[10 * GLD] = gp1 * zp[f][2];
-        G[11 * GLD] = gp2 * zp[f][2] + sl2 * o2 * Q[5];
-        G[12 * GLD] = gp0;
-        G[13 * GLD] = gp1;
-        G[14 * GLD] = gp2;
-        // gz = g' + P (R2^T gpre)
-        const float r0 = Q[6] * gp0;
-        const float r1 = Q[7] * gp0 + Q[9] * gp1;
-        const float r2 = Q[8] * gp0 + Q[10] * gp1 + Q[11] * gp2;
-        gz[0] += odd ? r2 : r0;
-        gz[1] += r1;
-        gz[2] += odd ? r0 : r2;
-      }
-      // gradients of the base samples z0 = eps*std + mean
-      gg[0] += g_za; gg[1] += ea * g_za;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { gg[2 + c] += gz[c]; gg[5 + c] += ec[c] * gz[c]; }
-
-      // ---- reduce the PP per-point parameter gradients over the 32 latent lanes ----
+      // the block's reduced gradient rows leave as contiguous stores
       __syncwarp();
-      for (int j = lane; j < PP; j += 32) {
-        const float4* row = reinterpret_cast<const float4*>(sG + j * GLD);
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { const float4 q4 = row[i]; acc += (q4.x + q4.y) + (q4.z + q4.w); }
-        float* dst = grow + (int64_t)n * PP + j;
-        if (kg == 0) *dst = acc; else *dst += acc;
+      {
+        float* dst = grow + (int64_t)n0 * PP;
+        const int cnt = npts * PP;
+        if (kg == 0) { for (int j = lane; j < cnt; j += 32) dst[j] = sO[j]; }
+        else { for (int j = lane; j < cnt; j += 32) dst[j] += sO[j]; }
       }
       __syncwarp();
     }
@@ -508,23 +600,30 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
 
 int launch_flow_composite_bwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
-                              int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
-                              float g_ld_alpha, float g_ld_rgb, const float* g_ld_dev, float* g_flow_params,
-                              float* g_globals_partial,
+                              int64_t eps_group_rays, int64_t B, int N, int white_bkgd, const float* g_rgb_map,
+                              const float* g_depth_map, float g_ld_alpha, float g_ld_rgb, const float* g_ld_dev,
+                              float* trans, int trans_valid, float* g_flow_params, float* g_globals_partial,
                               cudaStream_t s) {
   if (B == 0) return CFN_OK;
   CFN_CHECK_ARG(F >= 1 && F <= kMaxF, "flow_composite_bwd: n_flows=%d unsupported (1..%d)", F, kMaxF);
-  CFN_CHECK_ARG(N >= 2 && N <= 320 && K >= 1, "flow_composite_bwd: unsupported N=%d (<=320) K=%d", N, K);
+  CFN_CHECK_ARG(N >= 2 && N <= 4096 && K >= 1, "flow_composite_bwd: unsupported N=%d (2..4096) K=%d", N, K);
+  CFN_CHECK_ARG(trans != nullptr, "flow_composite_bwd: the transmittance buffer (B,N,K) is required");
   const int PP = 18 * F;
-  size_t smem = (size_t)4 * (((2 * N + 3) & ~3) + N * 32 + PP * 36 + ((PP + 3) & ~3)) * sizeof(float);
+  size_t smem = (size_t)4 * (((2 * N + 3) & ~3) + 2 * kBwdPB * PP + 2 * 16 * kBwdGLD) * sizeof(float);
   unsigned grid = (unsigned)((B + 3) / 4);
+  unsigned grid_pre = (unsigned)((B * 32 + 255) / 256);
 #define CFN_BWD_CASE(FF)                                                                                             \
   case FF: {                                                                                                         \
+    if (!trans_valid) {                                                                                              \
+      auto pre = fast_math ? trans_prepass_kernel<FF, true> : trans_prepass_kernel<FF, false>;                       \
+      pre<<<grid_pre, 256, 0, s>>>(K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_group_rays, \
+                                   B, N, trans);                                                                     \
+    }                                                                                                                \
     auto kern = fast_math ? flow_composite_bwd_kernel<FF, true> : flow_composite_bwd_kernel<FF, false>;              \
-    CFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
-    kern<<<grid, 128, smem, s>>>(K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, B, N,   \
-                                 white_bkgd, g_rgb_map, g_depth_map, g_ld_alpha, g_ld_rgb, g_ld_dev, g_flow_params,  \
-                                 g_globals_partial);                                                                 \
+    if (smem > 48 * 1024) CFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, 128, smem, s>>>(K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb,         \
+                                 eps_group_rays, B, N, white_bkgd, g_rgb_map, g_depth_map, g_ld_alpha, g_ld_rgb,     \
+                                 g_ld_dev, trans, g_flow_params, g_globals_partial);                                 \
   } break;
   switch (F) {
     CFN_BWD_CASE(1) CFN_BWD_CASE(2) CFN_BWD_CASE(3) CFN_BWD_CASE(4) CFN_BWD_CASE(5) CFN_BWD_CASE(6) CFN_BWD_CASE(7)

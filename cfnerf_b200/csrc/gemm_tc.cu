@@ -541,24 +541,16 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, in
 
 bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return device_num_sms(); }   // per device (common.cuh)
 
 template <int CG, bool A_MN, bool B_MN, int EPI, int DT = 0, bool CBF = false>
 int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const TgParams& p, size_t smem, cudaStream_t s) {
-  static bool attr_set = false;
+  // function attributes are PER DEVICE: one once-flag per device ordinal (a process may drive several GPUs)
+  static PerDeviceOnce attr_set;
   auto kern = tgemm_kernel<CG, A_MN, B_MN, EPI, DT, CBF>;
-  if (!attr_set) {
+  if (!attr_set.done()) {
     CFN_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_set.mark();
   }
   int64_t units = num_sms() / CG;
   if (units > p.n_work) units = p.n_work;

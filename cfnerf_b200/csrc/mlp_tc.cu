@@ -196,8 +196,9 @@ template <bool FP16, bool RELU>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   uint32_t d;
   if (FP16) {
-    if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    // .satfinite: an activation beyond the fp16 range (65504) saturates instead of becoming inf -> NaN downstream
+    if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   } else {
     if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
@@ -723,7 +724,7 @@ __global__ void pack_stream_kernel(PackSrcTable srcs, const int* __restrict__ bl
       v = (c == bias_col) ? hi : (bv - hi);
     }
     uint16_t o;
-    if (FP16) o = __half_as_ushort(__float2half_rn(v));
+    if (FP16) o = __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f)));   // saturate, never inf
     else o = __bfloat16_as_ushort(__float2bfloat16_rn(v));
     stream[(stream_row + r) * 64 + c] = o;
   }

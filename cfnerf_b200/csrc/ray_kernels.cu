@@ -307,16 +307,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__global__ void kde_nll_kernel(const float* __restrict__ rgb_map, const float* __restrict__ target, int64_t B, int K,
-                               float bw_factor, float grad_scale, float* __restrict__ partial, float* __restrict__ g) {
-  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (b >= B) return;
-  float nll_sum = 0.f, mse_sum = 0.f;
+// one ray's KDE term (warp-wide): returns [sum_c nll_c, sum_c (mean_c - t_c)^2] and writes g (3,K) when g != nullptr
+__device__ __forceinline__ void kde_nll_ray(const float* __restrict__ x3, const float* __restrict__ t3, int K, float bw_factor,
+                                            float grad_scale, float* __restrict__ g3, int lane, float& nll_sum, float& mse_sum) {
+  nll_sum = 0.f; mse_sum = 0.f;
   const float c_norm = 0.06349363593424097f;   // (2*pi)^(-1.5)
   for (int c = 0; c < 3; ++c) {
-    const float* x = rgb_map + (b * 3 + c) * K;
-    const float t = target[b * 3 + c];
+    const float* x = x3 + c * K;
+    const float t = t3[c];
     float s = 0.f;
     for (int k = lane; k < K; k += 32) s += x[k];
     const float m = warp_sum(s) / (float)K;
@@ -331,14 +329,23 @@ __global__ void kde_nll_kernel(const float* __restrict__ rgb_map, const float* _
     const float pm = warp_sum(ps) / (float)K;
     nll_sum += -logf(pm + 1e-5f);
     mse_sum += (m - t) * (m - t);
-    if (g) {
+    if (g3) {
       const float coef = grad_scale / ((pm + 1e-5f) * (float)K * h * h);
       for (int k = lane; k < K; k += 32) {
         const float dlt = x[k] - t;
-        g[(b * 3 + c) * K + k] = coef * expf(-(dlt * dlt) * inv2h2) * (c_norm / h) * dlt;
+        g3[c * K + k] = coef * expf(-(dlt * dlt) * inv2h2) * (c_norm / h) * dlt;
       }
     }
   }
+}
+
+__global__ void kde_nll_kernel(const float* __restrict__ rgb_map, const float* __restrict__ target, int64_t B, int K,
+                               float bw_factor, float grad_scale, float* __restrict__ partial, float* __restrict__ g) {
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float nll_sum, mse_sum;
+  kde_nll_ray(rgb_map + b * 3 * K, target + b * 3, K, bw_factor, grad_scale, g ? g + b * 3 * K : nullptr, lane, nll_sum, mse_sum);
   if (lane == 0) { partial[b * 2 + 0] = nll_sum; partial[b * 2 + 1] = mse_sum; }
 }
 
@@ -349,6 +356,81 @@ int launch_kde_nll(const float* rgb_map, const float* target, int64_t B, int K, 
   const float bw = (float)pow(0.8 / (double)K, -1.0 / 7.0);
   int64_t threads = B * 32;
   kde_nll_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(rgb_map, target, B, K, bw, grad_scale, partial, g);
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// F1, the whole trainer loss of the shipped recipe (colmap_depth, run_nerf_uncertainty_NF.py:1018-1055) in one launch
+// over the concatenated batch [B_rgb colour rays | B_depth depth rays] (main:1009-1011):
+//   colour rays: K-mean + KDE-NLL as above (the gradient seed w.r.t. rgb_map; their depth gets no gradient);
+//   depth rays : depth = mean_K depth_map (main:1020), squared error against the COLMAP depth (img2mse, main:1053);
+//                d/d depth_map[b,k] = depth_scale * 2 * err / K; their colours get no gradient (rgbs[:N_batch], main:1021).
+// partial (B,3) = [sum_c nll_c, sum_c (mean_c - t_c)^2, (mean_K depth - target_depth)^2]; the caller takes
+// loss_nll = sum(partial[:,0]) / (3 B_rgb), depth_loss = sum(partial[:,2]) / B_depth.
+// ------------------------------------------------------------------------------------------------
+__global__ void trainer_loss_kernel(const float* __restrict__ rgb_map, const float* __restrict__ depth_map,
+                                    const float* __restrict__ target_rgb, const float* __restrict__ target_depth,
+                                    int64_t B_rgb, int64_t B_depth, int K, float bw_factor, float nll_scale, float depth_scale,
+                                    float* __restrict__ partial, float* __restrict__ g_rgb, float* __restrict__ g_depth) {
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B_rgb + B_depth) return;
+  if (b < B_rgb) {
+    float nll_sum, mse_sum;
+    kde_nll_ray(rgb_map + b * 3 * K, target_rgb + b * 3, K, bw_factor, nll_scale, g_rgb ? g_rgb + b * 3 * K : nullptr, lane,
+                nll_sum, mse_sum);
+    if (g_depth) for (int k = lane; k < K; k += 32) g_depth[b * K + k] = 0.f;
+    if (lane == 0) { partial[b * 3 + 0] = nll_sum; partial[b * 3 + 1] = mse_sum; partial[b * 3 + 2] = 0.f; }
+  } else {
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s += depth_map[b * K + k];
+    const float err = warp_sum(s) / (float)K - target_depth[b - B_rgb];
+    const float gk = depth_scale * 2.0f * err / (float)K;
+    if (g_depth) for (int k = lane; k < K; k += 32) g_depth[b * K + k] = gk;
+    if (g_rgb) for (int i = lane; i < 3 * K; i += 32) g_rgb[b * 3 * K + i] = 0.f;
+    if (lane == 0) { partial[b * 3 + 0] = 0.f; partial[b * 3 + 1] = 0.f; partial[b * 3 + 2] = err * err; }
+  }
+}
+
+int launch_trainer_loss(const float* rgb_map, const float* depth_map, const float* target_rgb, const float* target_depth,
+                        int64_t B_rgb, int64_t B_depth, int K, float nll_scale, float depth_scale, float* partial, float* g_rgb,
+                        float* g_depth, cudaStream_t s) {
+  if (B_rgb + B_depth == 0) return CFN_OK;
+  CFN_CHECK_ARG(K >= 2, "trainer_loss: K_samples must be >= 2 (unbiased std)");
+  const float bw = (float)pow(0.8 / (double)K, -1.0 / 7.0);
+  int64_t threads = (B_rgb + B_depth) * 32;
+  trainer_loss_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(rgb_map, depth_map, target_rgb, target_depth, B_rgb,
+                                                                         B_depth, K, bw, nll_scale, depth_scale, partial, g_rgb,
+                                                                         g_depth);
+  CFN_LAUNCH_CHECK();
+  return CFN_OK;
+}
+
+// gradients of the four global latent parameters (models.py:44-48): the per-ray partial sums of K4 (through
+// z0 = eps * std + mean), summed over the rays in a fixed order (deterministic), plus the base log-density of the
+// entropy term: -log(std) per latent dimension, i.e. -ent_coef / alpha_std and -ent_coef / (3 rgb_std) (models.py:268,
+// 283, 286; the eps^2 part is constant).  out (8) = d/d[alpha_mean, alpha_std, rgb_mean(3), rgb_std(3)].
+__global__ void globals_grad_kernel(const float* __restrict__ partial, int64_t B, const float* __restrict__ globals8,
+                                    float ent_coef, float* __restrict__ out) {
+  __shared__ float red[8][8];
+  const int j = threadIdx.x & 7, part = threadIdx.x >> 3;   // 64 threads: 8 columns x 8 row slices
+  float s = 0.f;
+  for (int64_t b = part; b < B; b += 8) s += partial[b * 8 + j];
+  red[part][j] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) t += red[p][j];
+    if (j == 1) t -= ent_coef / globals8[1];
+    if (j >= 5) t -= ent_coef / (3.0f * globals8[j]);
+    out[j] = t;
+  }
+}
+
+int launch_globals_grad(const float* partial, int64_t B, const float* globals8, float ent_coef, float* out, cudaStream_t s) {
+  globals_grad_kernel<<<1, 64, 0, s>>>(partial, B, globals8, ent_coef, out);
   CFN_LAUNCH_CHECK();
   return CFN_OK;
 }

@@ -81,15 +81,17 @@ class GradBucket:
 
 
 def train_step(network_fn, optimizer, ray_batch, target, bucket: GradBucket | None = None, beta1: float = 0.01,
-               **render_kwargs):
+               depth_rays=None, target_depth=None, depth_lambda: float = 0.0, **render_kwargs):
     """One data-parallel optimisation step on this rank's shard (the trainer body of main:1014-1067 with the
     DataParallel wrapper replaced by one gradient all-reduce).  Equal shard sizes make the averaged gradient equal
-    to the global-batch gradient of the mean-reduced loss."""
+    to the global-batch gradient of the mean-reduced loss.  `depth_rays` (Bd,11) / `target_depth` (Bd) add the
+    depth-supervised rays of the shipped recipe (--colmap_depth, main:965-977, 1009-1011, 1018-1023, 1053-1054)."""
     from . import api
 
-    out = api.render_rays(ray_batch, network_fn, None, 128, True, False, perturb=1., raw_noise_std=1., **render_kwargs)
+    rays = ray_batch if depth_rays is None else torch.cat([ray_batch, depth_rays], 0)             # main:1009-1011
+    out = api.render_rays(rays, network_fn, None, 128, True, False, perturb=1., raw_noise_std=1., **render_kwargs)
     K = out["rgb_map"].shape[-1]
-    losses = api.kde_nll_loss(out["rgb_map"], target, out["loss_entropy"], K, beta1)
+    losses = api.trainer_loss(out, target, K, beta1, target_depth=target_depth, depth_lambda=depth_lambda)
     optimizer.zero_grad(set_to_none=True)
     losses["loss"].backward()
     if bucket is not None:
@@ -99,15 +101,23 @@ def train_step(network_fn, optimizer, ray_batch, target, bucket: GradBucket | No
 
 
 class FusedTrainStep:
-    """The trainer body (main:1014-1067: render in train mode -> K-mean + KDE-NLL + beta1 * entropy -> backward -> Adam)
-    as a straight chain of C-ABI calls, without an autograd graph: cfn_zvals -> cfn_network_fwd(save) ->
-    cfn_flow_composite_fwd -> cfn_kde_nll (loss + gradient seed) -> cfn_flow_composite_bwd_dev -> cfn_network_bwd ->
-    [one all-reduce of the flat gradient] -> cfn_adam_step.  Same kernels and numbers as `train_step`; the host cost per
-    step drops from ~3 ms (torch autograd engine + Python glue) to well under 1 ms, which is what bounds the reference's
-    own batch size (N_rand = 512 rays).  Gradients live in ONE flat fp32 buffer (the all-reduce bucket itself)."""
+    """The trainer body (main:1014-1067: render in train mode -> K-mean + KDE-NLL + beta1 * entropy [+ depth_lambda *
+    depth MSE on the depth rays] -> backward -> Adam with the reference's lr decay) as a straight chain of C-ABI calls,
+    without an autograd graph: cfn_zvals -> cfn_network_fwd(save) -> cfn_flow_composite_fwd (also writes the
+    transmittances the backward reads) -> cfn_trainer_loss (loss + gradient seeds) -> cfn_flow_composite_bwd_dev ->
+    cfn_network_bwd -> cfn_globals_grad -> [one all-reduce of the flat gradient] -> cfn_adam_step_dev -> cfn_pack_weights.
+
+    Same kernels and numbers as `train_step`.  Parameters, gradients and Adam moments each live in ONE flat fp32 buffer
+    (the module's Parameters are re-pointed at views of it: the gradient buffer is the all-reduce bucket, the weight
+    re-pack is a single copy).  With `use_graph=True` the chain is captured once per batch shape into CUDA graphs and
+    replayed: at the reference's own batch size (N_rand = 512 rays) a step is ~200 launches and ~80 tensor-map encodes
+    of host work for ~1.5 ms of device work, so launch overhead is what bounds it.  The optimiser clock (step count,
+    decayed learning rate) lives on the device so that it advances inside the graph."""
 
     def __init__(self, network_fn, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, beta1: float = 0.01,
-                 precision: str | None = None, N_samples: int = 128, white_bkgd: bool = False, lindisp: bool = False):
+                 precision: str | None = None, N_samples: int = 128, white_bkgd: bool = False, lindisp: bool = False,
+                 depth_lambda: float = 0.0, netchunk: int | None = None, lrate_decay: float = 0.0,
+                 use_graph: bool = False):
         from . import api
         from .engine import _unwrap, engine_for
         self.module = _unwrap(network_fn)
@@ -115,78 +125,182 @@ class FusedTrainStep:
         self.eng = engine_for(network_fn, self.dev, precision or api.DEFAULT_TRAIN_PRECISION)
         self.lr, self.betas, self.eps, self.beta1 = lr, betas, eps, beta1
         self.N, self.white_bkgd, self.lindisp = N_samples, white_bkgd, lindisp
+        self.depth_lambda = float(depth_lambda)
+        self.netchunk = api.DEFAULT_NETCHUNK if netchunk is None else int(netchunk)
+        self.decay_steps = float(lrate_decay) * 1000.0            # args.lrate_decay is in thousands of steps (main:1074)
+        self.use_graph = bool(use_graph)
         ps = self.eng.params
         n = sum(p.numel() for p in ps)
         f32 = dict(dtype=torch.float32, device=self.dev)
+        self.flat_param = torch.empty(n, **f32)
         self.flat_grad, self.exp_avg, self.exp_avg_sq = (torch.zeros(n, **f32) for _ in range(3))
         self.grads, self._m, self._v, o = [], [], [], 0
-        for p in ps:
-            k = p.numel()
-            self.grads.append(self.flat_grad[o:o + k].view(p.shape))
-            self._m.append(self.exp_avg[o:o + k])
-            self._v.append(self.exp_avg_sq[o:o + k])
-            o += k
+        with torch.no_grad():
+            for p in ps:
+                k = p.numel()
+                view = self.flat_param[o:o + k].view(p.shape)
+                view.copy_(p.detach())
+                p.data = view                     # same Parameter object (optimizers / state_dict keep working)
+                self.grads.append(self.flat_grad[o:o + k].view(p.shape))
+                self._m.append(self.exp_avg[o:o + k])
+                self._v.append(self.exp_avg_sq[o:o + k])
+                o += k
         import ctypes as C
         arr = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
         self._arrs = (arr(ps), arr(self.grads), arr(self._m), arr(self._v), (C.c_int64 * len(ps))(*[p.numel() for p in ps]))
+        self.adam_state = torch.zeros(4, **f32)    # [step, lr, 1 - b1^t, sqrt(1 - b2^t)] — advanced on the device
         self.step_count = 0
-        self._g_ld = {}
+        self._shapes = {}
+
+    # ---- static per-shape state -------------------------------------------------------------------------------
+    def _buffers(self, B_rgb: int, B_depth: int):
+        key = (B_rgb, B_depth)
+        st = self._shapes.get(key)
+        if st is not None:
+            return st
+        from . import api
+        B, N, K, dev = B_rgb + B_depth, self.N, self.eng.K, self.dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        group_rays, G = api.latent_groups(B, N, self.netchunk)
+        st = dict(B=B, B_rgb=B_rgb, B_depth=B_depth, group_rays=group_rays, G=G,
+                  rays=torch.empty(B, 11, **f32), target=torch.empty(B_rgb, 3, **f32),
+                  target_depth=torch.empty(max(B_depth, 1), **f32), t_rand=torch.empty(B, N, **f32),
+                  eps_a=torch.empty(G, K, **f32), eps_c=torch.empty(G, K, 3, **f32),
+                  partial=torch.empty(B, 3, **f32), g_rgb=torch.empty(B, 3, K, **f32), g_depth=torch.empty(B, K, **f32),
+                  graph_a=None, graph_b=None, out=None)
+        # d loss / d (per-ray sum of log-dets) (models.py:286): the entropy term is the point-weighted mean of the per-call
+        # scalars over ALL rows (main:1045) — or, with depth rays, over the first N_batch ROWS only (main:1023), which all
+        # belong to the first network call: only its rays carry a seed, normalised by that call's own point count
+        g_ld = torch.zeros(B, 2, **f32)
+        if B_depth > 0:
+            first = min(group_rays, B) if group_rays else B
+            g_ld[:first] = -self.beta1 / float(first * N * K)
+        else:
+            g_ld[:] = -self.beta1 / float(B * N * K)
+        st["g_ld"] = g_ld
+        self._shapes[key] = st
+        return st
+
+    # ---- the chain --------------------------------------------------------------------------------------------
+    def _forward_backward(self, st):
+        from ._lib import check
+        from .engine import _ptr, _stream
+        eng, N, K = self.eng, self.N, self.eng.K
+        B, rays = st["B"], st["rays"]
+        from . import api
+        t_vals = api.reference_t_schedule(N, self.dev)
+        z = eng.zvals(rays, t_vals, st["t_rand"], self.lindisp)
+        fp, ws = eng.network(B, N, rays=rays, z_vals=z, save=True)
+        out = eng.flow_composite(fp, z, rays[:, 3:6], 11, st["eps_a"], st["eps_c"], self.white_bkgd, train=True,
+                                 eps_group_rays=st["group_rays"], want_trans=True)
+        Bd = st["B_depth"]
+        check(eng.lib.cfn_trainer_loss_f32(_ptr(out["rgb_map"]), _ptr(out["depth_map"]), _ptr(st["target"]),
+                                           _ptr(st["target_depth"]) if Bd else None, st["B_rgb"], Bd, K,
+                                           1.0 / (3.0 * st["B_rgb"]), (self.depth_lambda / Bd) if Bd else 0.0,
+                                           _ptr(st["partial"]), _ptr(st["g_rgb"]), _ptr(st["g_depth"]), _stream()),
+              "cfn_trainer_loss_f32")
+        g_fp, g_glob = eng.flow_composite_bwd(fp, z, rays[:, 3:6], 11, st["eps_a"], st["eps_c"], self.white_bkgd,
+                                              st["g_rgb"], st["g_depth"] if Bd else None, st["g_ld"],
+                                              trans=out["trans"], eps_group_rays=st["group_rays"])
+        eng.network_bwd(g_fp, B, N, ws, grads=self.grads)
+        # parameters 0..3 (alpha_mean, alpha_std, rgb_mean, rgb_std) sit first in the flat gradient buffer
+        check(eng.lib.cfn_globals_grad_f32(eng.h, _ptr(g_glob), B, float(self.beta1), _ptr(self.flat_grad), _stream()),
+              "cfn_globals_grad_f32")
+        st["out"] = out
+
+    def _update(self, world: int):
+        from ._lib import check
+        from .engine import _ptr, _stream
+        eng = self.eng
+        p_arr, g_arr, m_arr, v_arr, numels = self._arrs
+        check(eng.lib.cfn_adam_step_dev_f32(len(eng.params), p_arr, g_arr, m_arr, v_arr, numels, _ptr(self.adam_state),
+                                            float(self.lr), 0.1, self.decay_steps, float(self.betas[0]),
+                                            float(self.betas[1]), float(self.eps), 1.0 / world, _stream()),
+              "cfn_adam_step_dev_f32")
+        eng.pack(force=True)        # the next forward reads the re-packed operand copies
 
     @torch.no_grad()
-    def step(self, ray_batch, target, t_rand=None, eps_alpha=None, eps_rgb=None, want_loss: bool = True):
-        from . import _lib, api
-        from ._lib import check
-        from .engine import _f32c, _ptr, _stream, bump_weights_epoch
-        import ctypes as C
+    def step(self, ray_batch, target, t_rand=None, eps_alpha=None, eps_rgb=None, want_loss: bool = True,
+             depth_rays=None, target_depth=None):
+        from .engine import _f32c, bump_weights_epoch
+        import math
         eng, dev, N, K = self.eng, self.dev, self.N, self.eng.K
-        rays, target = _f32c(ray_batch, dev), _f32c(target, dev)
-        B = rays.shape[0]
+        B_rgb = ray_batch.shape[0]
+        B_depth = 0 if depth_rays is None else depth_rays.shape[0]
+        rank, w = world()
         with torch.cuda.device(dev):
-            t_vals = api.reference_t_schedule(N, dev)
+            st = self._buffers(B_rgb, B_depth)
+            B, G = st["B"], st["G"]
+            st["rays"][:B_rgb].copy_(ray_batch, non_blocking=True)
+            st["target"].copy_(target, non_blocking=True)
+            if B_depth:
+                st["rays"][B_rgb:].copy_(depth_rays, non_blocking=True)                       # main:1009-1011
+                st["target_depth"][:B_depth].copy_(target_depth, non_blocking=True)
             if t_rand is None:
-                t_rand = torch.rand(B, N, device=dev)                                         # main:524
-            z = eng.zvals(rays, t_vals, _f32c(t_rand, dev), self.lindisp)
+                st["t_rand"].uniform_()                                                       # main:524
+            else:
+                st["t_rand"].copy_(t_rand, non_blocking=True)
             if eps_alpha is None:
-                eps_alpha = torch.empty([K, 1], device=dev).normal_()                         # models.py:234
-                eps_rgb = torch.empty([K, 3], device=dev).normal_()                           # models.py:246
-            ea, ec = _f32c(eps_alpha.reshape(-1), dev), _f32c(eps_rgb, dev)
-            fp, ws = eng.network(B, N, rays=rays, z_vals=z, save=True)
-            out = eng.flow_composite(fp, z, rays[:, 3:6], 11, ea, ec, self.white_bkgd, train=True)
-            rgb = out["rgb_map"]
-            partial = torch.empty(B, 2, dtype=torch.float32, device=dev)
-            g_rgb = torch.empty_like(rgb)
-            check(eng.lib.cfn_kde_nll_f32(_ptr(rgb), _ptr(target), B, K, 1.0 / (3.0 * B), _ptr(partial), _ptr(g_rgb),
-                                          _stream()), "cfn_kde_nll_f32")
-            cnt = float(B * N * K)
-            g_ld = self._g_ld.get(B)
-            if g_ld is None:        # d loss / d (sum of log-dets) = -beta1 / (B N K) for both stacks (models.py:286)
-                g_ld = self._g_ld[B] = torch.full((2,), -self.beta1 / cnt, dtype=torch.float32, device=dev)
-            g_fp, g_glob = eng.flow_composite_bwd(fp, z, rays[:, 3:6], 11, ea, ec, self.white_bkgd, g_rgb, None, g_ld)
-            eng.network_bwd(g_fp, B, N, ws, grads=self.grads)
-            # the four global latent parameters: through z0 = eps * std + mean (K4's per-ray partials) plus the base
-            # log-density of the entropy term, -log(std) per latent dimension (models.py:268/283; its eps^2 part is constant)
-            m = self.module
-            gg = g_glob.sum(0)
-            self.grads[0].copy_(gg[0:1])
-            self.grads[1].copy_(gg[1:2] - self.beta1 / m.alpha_std)
-            self.grads[2].copy_(gg[2:5])
-            self.grads[3].copy_(gg[5:8] - self.beta1 / (3.0 * m.rgb_std))
-            rank, w = world()
-            if w > 1:
-                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+                st["eps_a"].normal_()                                                         # models.py:234 (per call)
+                st["eps_c"].normal_()                                                         # models.py:246
+            else:
+                st["eps_a"].copy_(_f32c(eps_alpha, dev).reshape(G, K))
+                st["eps_c"].copy_(_f32c(eps_rgb, dev).reshape(G, K, 3))
+            if not self.use_graph:
+                self._forward_backward(st)
+                if w > 1:
+                    dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+                self._update(w)
+            elif st["graph_a"] is None:
+                # first step of this shape: run it eagerly (warm-up: function attributes, allocator), then capture the same
+                # calls for every later step.  The all-reduce stays outside the graphs (NCCL on the current stream).
+                self._forward_backward(st)
+                if w > 1:
+                    dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+                self._update(w)
+                torch.cuda.synchronize()
+                eager_out = st["out"]                # this step's results; the capture below re-binds st["out"]
+                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                state_backup = [t.clone() for t in (self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq,
+                                                    self.adam_state)]
+                with torch.cuda.graph(ga):
+                    self._forward_backward(st)
+                with torch.cuda.graph(gb, pool=ga.pool()):
+                    self._update(w)
+                for t, bck in zip((self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.adam_state),
+                                  state_backup):
+                    t.copy_(bck)          # capture does not execute, but keep the state provably untouched
+                st["graph_a"], st["graph_b"] = ga, gb
+                st["out_captured"], st["out"] = st["out"], eager_out
+            else:
+                if "out_captured" in st:
+                    st["out"] = st.pop("out_captured")      # static tensors the replayed graph writes
+                st["graph_a"].replay()
+                if w > 1:
+                    dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+                st["graph_b"].replay()
             self.step_count += 1
-            p_arr, g_arr, m_arr, v_arr, numels = self._arrs
-            check(eng.lib.cfn_adam_step_f32(len(eng.params), p_arr, g_arr, m_arr, v_arr, numels, float(self.lr),
-                                            float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                                            int(self.step_count), 1.0 / w, _stream()), "cfn_adam_step_f32")
-            bump_weights_epoch()
+            bump_weights_epoch()                          # other engines of this module re-pack on their next use ...
+            eng._packed_version = eng._version()          # ... this one was re-packed inside the step
             if not want_loss:
                 return {}
-            tot = partial.sum(0) / (3.0 * B)
-            nll, mse = tot[0], tot[1]
-            base_a, base_c = api._entropy_base_terms(m, ea, ec)
-            ld = out["logdet_sums"].sum(0)
-            ent = base_a - ld[0] / cnt + base_c - ld[1] / cnt
-            import math
-            return {"loss": nll + self.beta1 * ent, "loss_nll": nll, "mse": mse,
-                    "psnr": -10. * torch.log(mse) / math.log(10.)}
+            from . import api
+            out, partial = st["out"], st["partial"]
+            tot = partial.sum(0)
+            nll, mse = tot[0] / (3.0 * B_rgb), tot[1] / (3.0 * B_rgb)
+            ent_rows = api._entropy_rows(self.module, st["eps_a"] if G > 1 else st["eps_a"][0],
+                                         st["eps_c"] if G > 1 else st["eps_c"][0], out["logdet_sums"], B, N, K,
+                                         st["group_rays"])
+            ent = ent_rows[:B_rgb].mean() if B_depth else ent_rows.mean()                     # main:1023 / 1045
+            res = {"loss_nll": nll, "mse": mse, "psnr": -10. * torch.log(mse) / math.log(10.), "loss_entropy": ent}
+            loss = nll + self.beta1 * ent
+            if B_depth:
+                res["depth_loss"] = tot[2] / B_depth
+                loss = loss + self.depth_lambda * res["depth_loss"]
+            res["loss"] = loss
+            return res
+
+    def weights_checksum(self) -> torch.Tensor:
+        """fp64 sum and sum of squares of the flat parameter buffer (ranks of a data-parallel job must agree bit for bit)."""
+        p = self.flat_param.double()
+        return torch.stack([p.sum(), (p * p).sum()])

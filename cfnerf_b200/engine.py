@@ -122,7 +122,9 @@ class Engine:
         return (out, ws) if save else out
 
     def flow_composite(self, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, white_bkgd: bool,
-                       want_raw=False, want_weights=False, train=False, want_kstats=False):
+                       want_raw=False, want_weights=False, train=False, want_kstats=False, eps_group_rays: int = 0,
+                       want_trans=False):
+        """eps_alpha (K) / eps_rgb (K,3), or (G,K) / (G,K,3) with eps_group_rays = rays per latent-draw group."""
         self.pack()
         B, N = z_vals.shape
         K, dev = self.K, self.device
@@ -134,21 +136,27 @@ class Engine:
         w = torch.empty(B, N, K, **f32) if want_weights else None
         ld = torch.empty(B, 2, **f32) if train else None
         ks = torch.empty(B, 8, **f32) if want_kstats else None
+        tr = torch.empty(B, N, K, **f32) if (train and want_trans) else None
         check(self.lib.cfn_flow_composite_fwd(self.h, _ptr(flow_params), _ptr(z_vals), _ptr(rays_d), rays_d_stride,
-                                              _ptr(eps_alpha), _ptr(eps_rgb), B, N, int(white_bkgd), _ptr(rgb),
-                                              _ptr(disp), _ptr(depth), _ptr(raw), _ptr(w), _ptr(ld), _ptr(ks),
-                                              _stream()), "cfn_flow_composite_fwd")
-        return dict(rgb_map=rgb, disp_map=disp, depth_map=depth, raw=raw, weights=w, logdet_sums=ld, kstats=ks)
+                                              _ptr(eps_alpha), _ptr(eps_rgb), int(eps_group_rays), B, N, int(white_bkgd),
+                                              _ptr(rgb), _ptr(disp), _ptr(depth), _ptr(raw), _ptr(w), _ptr(ld), _ptr(ks),
+                                              _ptr(tr), _stream()), "cfn_flow_composite_fwd")
+        return dict(rgb_map=rgb, disp_map=disp, depth_map=depth, raw=raw, weights=w, logdet_sums=ld, kstats=ks, trans=tr)
 
     def flow_composite_bwd(self, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, white_bkgd,
-                           g_rgb, g_depth, g_ld):
-        """g_ld: device tensor (2,) = d loss / d (sum of the alpha / rgb log-dets); stays on the device (no host sync)."""
+                           g_rgb, g_depth, g_ld, trans=None, eps_group_rays: int = 0):
+        """g_ld: device tensor (B,2) = d loss / d (per-ray sums of the alpha / rgb log-dets); stays on the device (no
+        host sync).  trans: the (B,N,K) transmittance the training forward wrote (None: recomputed into scratch)."""
         B, N = z_vals.shape
         g_fp = torch.empty_like(flow_params)
         g_glob = torch.empty(B, 8, dtype=torch.float32, device=self.device)
+        valid = trans is not None
+        if trans is None:
+            trans = torch.empty(B, N, self.K, dtype=torch.float32, device=self.device)
         check(self.lib.cfn_flow_composite_bwd_dev(self.h, _ptr(flow_params), _ptr(z_vals), _ptr(rays_d), rays_d_stride,
-                                                  _ptr(eps_alpha), _ptr(eps_rgb), B, N, int(white_bkgd), _ptr(g_rgb),
-                                                  _ptr(g_depth), _ptr(g_ld), _ptr(g_fp), _ptr(g_glob), _stream()),
+                                                  _ptr(eps_alpha), _ptr(eps_rgb), int(eps_group_rays), B, N,
+                                                  int(white_bkgd), _ptr(g_rgb), _ptr(g_depth), _ptr(g_ld), _ptr(trans),
+                                                  int(valid), _ptr(g_fp), _ptr(g_glob), _stream()),
               "cfn_flow_composite_bwd_dev")
         return g_fp, g_glob
 

@@ -2,8 +2,9 @@
 
 It holds exactly the tensors of the reference `state_dict()` (same keys and shapes, so released checkpoints
 load with `load_state_dict`) plus the attributes the hot path reads off the module (`sample_alpha`,
-`sample_rgb`, `K_samples`, ...).  It has no PyTorch forward of its own: calling it routes through the CUDA
-library, like every other entry of this package (no fallback).
+`sample_rgb`, `K_samples`, ...).  It has no PyTorch arithmetic of its own: `forward` (the `network_fn(embedded,
+is_val, is_test)` surface of models.py:188) routes through the CUDA library like every other entry of this package
+(no fallback).
 """
 from __future__ import annotations
 
@@ -65,10 +66,25 @@ class NeRFFlowsParams(nn.Module):
         self.flows_rgb = _Amortised(self.h_rgb_size, 3, self.n_flows)
         self.flows_alpha = _Amortised(self.h_alpha_size, 1, self.n_flows)
 
-    def forward(self, embedded, is_val=False, is_test=False):
-        """`network_fn(embedded, is_val, is_test)` (models.py:188): the embedded (M,90) input cannot be inverted to
-        points, so the fused path needs points; use cfnerf_b200.api.run_network / render_rays instead."""
-        raise RuntimeError("NeRFFlowsParams has no PyTorch forward; query it through cfnerf_b200.api.run_network")
+    def forward(self, embedded, is_val=False, is_test=False, *, eps_alpha=None, eps_rgb=None, precision=None):
+        """`network_fn(embedded, is_val, is_test)` (models.py:188), the call `batchify` makes (main:55).
+
+        embedded (M, input_ch + input_ch_views) = [gamma(p) | gamma(d)] as `run_network` assembles it (main:70-80).
+        `get_embedder` keeps the raw input in front of the sin/cos blocks (`include_input: True`, helpers:59), so the
+        3-D point is columns 0:3 and the view direction columns input_ch : input_ch+3; the fused kernel re-encodes
+        them itself (the other columns are redundant).  Returns (raw (M,K,4) [rgb|sigma], zeros_like(raw)) in test mode
+        (models.py:223) and (raw, entropy scalar broadcast to (M,K,1)) otherwise (models.py:291).  Not differentiable:
+        training goes through cfnerf_b200.api.render_rays (one autograd node around network + flows + compositing)."""
+        from . import api
+        if embedded.dim() != 2 or embedded.shape[-1] != self.input_ch + self.input_ch_views:
+            raise ValueError(f"embedded must be (M,{self.input_ch + self.input_ch_views}) = [gamma(p)|gamma(d)] "
+                             f"(main:70-80), got {tuple(embedded.shape)}")
+        pts = embedded[:, 0:3]
+        dirs = embedded[:, self.input_ch:self.input_ch + 3]
+        # every row carries its own direction: M rays of one sample each
+        raw, ent = api.run_network(pts[:, None, :], dirs, self, is_val, is_test, eps_alpha=eps_alpha, eps_rgb=eps_rgb,
+                                   precision=precision)
+        return raw[:, 0], (ent[:, 0] if is_test else ent)
 
     @staticmethod
     def from_oracle_params(cfg, params: dict, sample_alpha=None, sample_rgb=None) -> "NeRFFlowsParams":

@@ -95,7 +95,9 @@ int cfn_rays_from_pose_f32(int H, int W, double focal, const float* c2w_host, do
 
 /* ---- A2-A5: positional encoding + MLP trunk/heads + flow conditioning ------------------------ */
 /* Bytes of caller-provided workspace cfn_network_fwd needs for n_points points.
- * save_for_backward != 0 sizes it for the training path (activations kept for cfn_network_bwd). */
+ * save_for_backward != 0 sizes it for the training path (activations kept for cfn_network_bwd).  Without saved
+ * activations the layer-by-layer chain walks the points in internal passes of at most 262144 points, so the answer
+ * is bounded whatever n_points is (the reference bounds its memory with netchunk, main:47-64). */
 int cfn_workspace_bytes(const CfnHandle* h, int64_t n_points, int save_for_backward, size_t* out);
 
 /* Points are either given explicitly (pts (B*N,3), run_network semantics, run_nerf_uncertainty_NF.py:67-85)
@@ -114,32 +116,43 @@ int cfn_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, 
                     size_t workspace_bytes, float* const* grads, int n_params, void* stream);
 
 /* ---- A6-A8 (+A11 partials): K-sample flows + alpha compositing --------------------------------- */
-/* eps_alpha (K), eps_rgb (K,3): base latent draws (models.py:198-206 / 233-251), shared by all points.
+/* eps_alpha (G,K), eps_rgb (G,K,3): base latent draws (models.py:198-206 / 233-251).  eps_group_rays = 0: G = 1, one
+ * set shared by all rays (test mode; a training call of at most netchunk points).  eps_group_rays = R > 0: ray b uses
+ * set b / R — the reference draws fresh noise in EVERY network call of netchunk points (batchify, main:47-64), i.e.
+ * every netchunk / N rays of a training batch (512 rays at the shipped netchunk = 65536, N = 128).
  * rays_d: pointer to the first direction, rays_d_stride floats between rays (11 when it points into a ray batch).
  * Outputs: rgb_map (B,3,K), disp_map (B,K), depth_map (B,K); optional raw (B,N,K,4) [rgb|sigma],
  * weights (B,N,K); optional logdet_sums (B,2): per-ray sums over (n,k) of the alpha / rgb log-det terms
- * (models.py:263,278) for the entropy loss; optional kstats (B,8): mean_k rgb (3), "uncertainty" std
- * (unbiased std * K/(K-1), main:1034/1130) (3), mean_k depth, mean_k disp.  Any optional pointer may be NULL. */
+ * (models.py:263,278) for the entropy loss (requesting them selects the training flavour); optional kstats (B,8):
+ * mean_k rgb (3), "uncertainty" std (unbiased std * K/(K-1), main:1034/1130) (3), mean_k depth, mean_k disp; optional
+ * trans (B,N,K) (training flavour only): the transmittance in front of every sample, which cfn_flow_composite_bwd
+ * reads instead of recomputing it.  Any optional pointer may be NULL. */
 int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, const float* z_vals, const float* rays_d,
-                           int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t B, int N,
-                           int white_bkgd, float* rgb_map, float* disp_map, float* depth_map, float* raw,
-                           float* weights, float* logdet_sums, float* kstats, void* stream);
+                           int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t eps_group_rays,
+                           int64_t B, int N, int white_bkgd, float* rgb_map, float* disp_map, float* depth_map,
+                           float* raw, float* weights, float* logdet_sums, float* kstats, float* trans, void* stream);
 
 /* Backward.  g_rgb_map (B,3,K) and g_depth_map (B,K) (NULL = zero) are upstream
  * gradients; g_logdet_alpha / g_logdet_rgb are d loss / d(sum of log-dets) (scalars, e.g. -beta1/(B*N*K)).
+ * trans (B,N,K) is REQUIRED device memory: with trans_valid != 0 it holds what cfn_flow_composite_fwd wrote for the
+ * same inputs; with trans_valid == 0 it is scratch that this call fills first (an alpha-stack-only pre-pass).
  * Writes g_flow_params (B*N,18F) and g_globals_partial (B,8): per-ray
  * partial sums of d/d[alpha_mean, alpha_std, rgb_mean(3), rgb_std(3)] through z0 = eps*std+mean only (the caller sums
- * over rays; kept per ray so the result is deterministic). */
+ * over rays; kept per ray so the result is deterministic, and per eps group when eps_group_rays > 0). */
 int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, const float* z_vals, const float* rays_d,
-                           int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t B, int N,
-                           int white_bkgd, const float* g_rgb_map, const float* g_depth_map, float g_logdet_alpha,
-                           float g_logdet_rgb, float* g_flow_params, float* g_globals_partial, void* stream);
-/* Same, with the two log-det gradient seeds read from DEVICE memory (g_logdet_dev[0] = alpha, [1] = rgb): the host
- * does not have to wait for the loss graph before it issues the backward (no device-to-host sync per step). */
+                           int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t eps_group_rays,
+                           int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
+                           float g_logdet_alpha, float g_logdet_rgb, float* trans, int trans_valid,
+                           float* g_flow_params, float* g_globals_partial, void* stream);
+/* Same, with PER-RAY log-det gradient seeds read from DEVICE memory: g_logdet_dev (B,2), [b][0] = alpha, [b][1] = rgb.
+ * The host does not have to wait for the loss graph before it issues the backward (no device-to-host sync per step),
+ * and rays of different network calls / loss terms can carry different seeds (the depth rays of the shipped recipe
+ * take no part in the entropy term, main:1018-1023, 1045). */
 int cfn_flow_composite_bwd_dev(CfnHandle* h, const float* flow_params, const float* z_vals, const float* rays_d,
-                               int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t B, int N,
-                               int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
-                               const float* g_logdet_dev, float* g_flow_params, float* g_globals_partial, void* stream);
+                               int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t eps_group_rays,
+                               int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
+                               const float* g_logdet_dev, float* trans, int trans_valid, float* g_flow_params,
+                               float* g_globals_partial, void* stream);
 
 /* ---- A8 stand-alone: raw2outputs (run_nerf_uncertainty_NF.py:411-454) ------------------------ */
 int cfn_raw2outputs_f32(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,
@@ -163,6 +176,17 @@ int cfn_mean_over_k_f32(const float* w, float* out, int64_t rows, int K, void* s
 int cfn_kde_nll_f32(const float* rgb_map, const float* target, int64_t B, int K, float grad_scale, float* partial,
                     float* g_rgb_map, void* stream);
 
+/* The whole loss of the shipped recipe (--colmap_depth, --depth_lambda; run_nerf_uncertainty_NF.py:1018-1055) over the
+ * concatenated batch [B_rgb colour rays | B_depth depth rays] (main:1009-1011) in one launch.  rgb_map (B,3,K),
+ * depth_map (B,K) with B = B_rgb + B_depth; target_rgb (B_rgb,3); target_depth (B_depth) (may be NULL when B_depth = 0).
+ * partial (B,3) = per-ray [sum_c nll_c, sum_c (mean_k rgb - target)^2, (mean_k depth - target_depth)^2] (colour rays fill
+ * columns 0-1, depth rays column 2).  g_rgb_map (B,3,K) = nll_scale * d(sum_c nll_c)/d rgb_map on colour rays, 0 on
+ * depth rays (rgbs[:N_batch], main:1021); g_depth_map (B,K) = depth_scale * d(err^2)/d depth_map on depth rays, 0 on
+ * colour rays.  Pass nll_scale = 1/(3 B_rgb) and depth_scale = depth_lambda / B_depth to seed the backward directly. */
+int cfn_trainer_loss_f32(const float* rgb_map, const float* depth_map, const float* target_rgb, const float* target_depth,
+                         int64_t B_rgb, int64_t B_depth, int K, float nll_scale, float depth_scale, float* partial,
+                         float* g_rgb_map, float* g_depth_map, void* stream);
+
 /* ---- F3: fused optimiser step (torch.optim.Adam, run_nerf_uncertainty_NF.py:339, 1065-1077) ------------------- */
 /* One launch over all n_tensors parameter tensors.  The four pointer arrays and numels live in HOST memory and hold
  * DEVICE pointers / element counts; `step` is the 1-based step count (bias correction), `lr` the already decayed
@@ -170,6 +194,22 @@ int cfn_kde_nll_f32(const float* rgb_map, const float* target, int64_t B, int K,
 int cfn_adam_step_f32(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                       float* const* exp_avg_sq, const int64_t* numels, float lr, float beta1, float beta2, float eps,
                       int step, float grad_scale, void* stream);
+
+/* Same update with the optimiser clock in DEVICE memory, so that a whole training step can be replayed as one CUDA
+ * graph: state_dev (4 floats: step count, learning rate of this step, 1 - beta1^step, sqrt(1 - beta2^step); zero it
+ * before the first step) is advanced by one thread and then read by the update kernel.  The learning rate follows the
+ * reference's schedule (main:1073-1077, applied after optimizer.step() with a global_step that lags by one):
+ * lr(t) = lr0 * decay_rate^(max(t - 2, 0) / decay_steps); decay_steps <= 0 keeps lr0. */
+int cfn_adam_step_dev_f32(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                          float* const* exp_avg_sq, const int64_t* numels, float* state_dev, float lr0, float decay_rate,
+                          float decay_steps, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* Gradients of the four global latent parameters (models.py:44-48): out8 = sum over rays of g_globals_partial (B,8)
+ * (fixed order: deterministic) plus the base log-density part of entropy_coef * loss_entropy
+ * (-entropy_coef / alpha_std, -entropy_coef / (3 rgb_std); models.py:268, 283, 286).  out8 = d/d[alpha_mean,
+ * alpha_std, rgb_mean(3), rgb_std(3)], i.e. exactly parameter tensors 0..3 when they are stored back to back. */
+int cfn_globals_grad_f32(const CfnHandle* h, const float* g_globals_partial, int64_t B, float entropy_coef, float* out8,
+                         void* stream);
 
 /* ---- diagnostics ---------------------------------------------------------------------------------- */
 /* When CFN_TC_PROFILE=1 is set in the environment at cfn_create time, the tensor-core network kernel records

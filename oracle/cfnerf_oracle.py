@@ -297,8 +297,12 @@ def run_network(p: dict, cfg: CfnConfig, pts: torch.Tensor, viewdirs: torch.Tens
     dirs = viewdirs[:, None].expand(B, N, 3).reshape(-1, 3)                                  # main:74-78
     emb = torch.cat([emb, positional_encoding(dirs, cfg.L_dir)], -1)                         # main:79-80
     raws, ents = [], []
-    for i in range(0, emb.shape[0], netchunk):
-        r, e = nerf_flows_forward(p, cfg, emb[i:i + netchunk], eps_alpha, eps_rgb, train, faithful)
+    for ci, i in enumerate(range(0, emb.shape[0], netchunk)):
+        # the reference draws fresh noise inside EVERY network call in train mode (models:233-251): a leading axis on
+        # the eps arguments, (G,K,1) / (G,K,3), gives call ci its own draw; plain (K,1) / (K,3) are shared by all calls
+        ea = eps_alpha[ci] if eps_alpha.dim() == 3 else eps_alpha
+        er = eps_rgb[ci] if eps_rgb.dim() == 3 else eps_rgb
+        r, e = nerf_flows_forward(p, cfg, emb[i:i + netchunk], ea, er, train, faithful)
         raws.append(r)
         ents.append((e, min(netchunk, emb.shape[0] - i)))
     return torch.cat(raws, 0).reshape(B, N, cfg.K, 4), ents
@@ -357,20 +361,23 @@ def z_from_t(t_vals, near, far, lindisp: bool, t_rand=None):
 
 
 def render_rays(p: dict, cfg: CfnConfig, ray_batch: torch.Tensor, eps_alpha, eps_rgb, train: bool,
-                t_rand=None, lindisp: bool = False, white_bkgd: bool = False, faithful: bool = True):
-    """ray_batch (B,11)=[o d near far viewdir] -> dict like main:542-547 (loss_entropy as the scalar)."""
+                t_rand=None, lindisp: bool = False, white_bkgd: bool = False, faithful: bool = True,
+                netchunk: int = 1024 * 64):
+    """ray_batch (B,11)=[o d near far viewdir] -> dict like main:542-547 (loss_entropy as the scalar; the per-call
+    scalars and their point counts, i.e. the rows of the reference's (B*N,K,1) tensor, under "entropy_calls")."""
     rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
     viewdirs = ray_batch[:, -3:]
     near, far = ray_batch[:, 6:7], ray_batch[:, 7:8]
     z_vals = z_from_t(reference_t_schedule(ray_batch.dtype), near, far, lindisp, t_rand)
     pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]                 # main:534
-    raw, ents = run_network(p, cfg, pts, viewdirs, eps_alpha, eps_rgb, train, faithful=faithful)
+    raw, ents = run_network(p, cfg, pts, viewdirs, eps_alpha, eps_rgb, train, netchunk=netchunk, faithful=faithful)
     rgb_map, disp_map, weights, depth_map = raw2outputs(raw, z_vals, rays_d, white_bkgd)
     ret = {"rgb_map": rgb_map, "disp_map": disp_map, "depth_map": depth_map, "weights": weights,
            "z_vals": z_vals}
     if train:
         ret["raw"] = raw
         ret["loss_entropy"] = entropy_mean(ents)
+        ret["entropy_calls"] = ents
         ret["pts"] = pts
     return ret
 
@@ -508,6 +515,33 @@ def kde_nll_loss(rgb_map: torch.Tensor, target: torch.Tensor, loss_entropy: torc
     nll = -torch.log((p1 * p2).mean(-1) + eps).mean()                                        # main:1040-1042
     loss = nll + beta1 * loss_entropy if beta1 else nll                                      # main:1047-1050
     return {"loss": loss, "loss_nll": nll, "mse": mse, "psnr": psnr}
+
+
+def trainer_loss(out: dict, target_s: torch.Tensor, K: int, beta1: float = 0.01, target_depth=None,
+                 depth_lambda: float = 0.0):
+    """The loss of the trainer body, main:1018-1055, on `render_rays(cat[colour rays, depth rays], train=True)`.
+
+    With --colmap_depth the batch is [N_batch colour rays | depth rays] (main:1009-1011): `depth = mean_K depth_map`,
+    colours keep the first N_batch rays (main:1020-1022), and `extras[x][:N_batch]` (main:1023) slices the first
+    N_batch ROWS of the (B*N,K,1) entropy tensor — rows are points, so with N_batch <= netchunk that is the FIRST network
+    call's scalar only.  `depth_loss = img2mse(depth_col, target_depth)` enters with weight depth_lambda (main:1053-1054).
+    """
+    B = out["rgb_map"].shape[0]
+    B_depth = 0 if target_depth is None else int(target_depth.shape[0])
+    N_batch = B - B_depth
+    ents = out["entropy_calls"]
+    if B_depth:
+        assert N_batch <= ents[0][1], "the first N_batch rows must lie inside the first network call"
+        ent = ents[0][0]
+    else:
+        ent = entropy_mean(ents)                                                             # main:1045
+    res = kde_nll_loss(out["rgb_map"][:N_batch], target_s, ent, K, beta1)
+    res["loss_entropy"] = ent
+    if B_depth:
+        depth_col = out["depth_map"].mean(-1)[N_batch:]                                      # main:1020, 1022
+        res["depth_loss"] = torch.mean((depth_col - target_depth) ** 2)                      # main:1053
+        res["loss"] = res["loss"] + depth_lambda * res["depth_loss"]                         # main:1054
+    return res
 
 
 # --------------------------------------------------------------------------------------------

@@ -5,10 +5,12 @@ Imports ``/root/reference/run_nerf_uncertainty_NF.py`` without touching it by pr
 top level but never uses on the render/train hot path:
 ``imageio, kornia, skimage.metrics, matplotlib.{pyplot,colors}, configargparse``.
 
-The reference tree does not exist on the GPU box.  Nothing under ``tests/ -m gpu``, ``smoke()``
-or ``bench.py`` may import this module; it is used here only by ``oracle/make_golden.py`` (fixture
-generation) and by the container-side test that pins ``oracle/cfnerf_oracle.py`` to the live
-reference (skipped when ``/root/reference`` is absent).
+``/root/reference`` does not exist on the GPU box; there the loader falls back to ``oracle/_ref/``, the
+byte-identical copy of the reference's ``*.py`` files staged by ``oracle/build_ref.py`` (git-ignored,
+travels with the snapshot).  Users: ``oracle/make_golden.py`` (fixture generation), the container-side
+tests that pin ``oracle/cfnerf_oracle.py`` to the live reference, the ``-m gpu`` tests that put
+``cfnerf_b200.install()`` behind the real module, and the CPU legs of ``bench.py`` (kind "reference").
+Never imported by the product package.
 """
 from __future__ import annotations
 
@@ -16,7 +18,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CFNERF_REFERENCE_ROOT", "/root/reference")
+def _find_root() -> str:
+    """$CFNERF_REFERENCE_ROOT, else the read-only tree of the build container, else the byte-identical copy that
+    oracle/build_ref.py staged under oracle/_ref/ (git-ignored; it travels to the GPU box)."""
+    env = os.environ.get("CFNERF_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/run_nerf_uncertainty_NF.py"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

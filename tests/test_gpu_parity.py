@@ -184,6 +184,7 @@ def _network_case(cf, dev, name, precision, tol_params, tol_raw):
     with torch.no_grad():
         ref = oracle_flow_params(p, cfg, emb)
     err = (fp.cpu() - ref).abs().max().item()
+    print(f"{name}[{precision}] flow-parameter max|err| = {err:.3e} (tol {tol_params})")
     assert err <= tol_params, f"flow params err {err}"
     raw, zeros = cf.run_network(pts.to(dev)[:, None, :], dirs.to(dev), net, False, True, precision=precision)
     # conditioning-aware bar: the flows amplify rounding (the "stressed" fixture moves by 1e-3 between the
@@ -195,6 +196,7 @@ def _network_case(cf, dev, name, precision, tol_params, tol_raw):
         raw64, _ = O.nerf_flows_forward(p64, cfg, emb.double(), ea.double(), er.double(), False, faithful=False)
     ref_noise = (T(g["out_raw"]).double() - raw64).abs().max().item()
     err = (raw.cpu()[:, 0].double() - raw64).abs().max().item()
+    print(f"{name}[{precision}] raw max|err| vs fp64 = {err:.3e} (tol {max(tol_raw, 3 * ref_noise):.3e}, reference fp32 noise {ref_noise:.3e})")
     assert err <= max(tol_raw, 3 * ref_noise), f"raw err {err} (reference's own fp32 noise {ref_noise})"
     assert float(zeros.abs().max()) == 0.0 and zeros.shape == raw.shape
 
@@ -317,9 +319,12 @@ def test_render_rays_test_mode_tensor_core(cf, dev, name, precision):
     _render_test_case(cf, dev, name, precision, TOL_TC)
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp16", "tf32"])
-def test_network_tensor_core_vs_golden(cf, dev, precision):
-    _network_case(cf, dev, "network_canonical", precision, 3e-2, 3e-2)
+@pytest.mark.parametrize("precision,tol", [("bf16", 6e-3), ("fp16", TOL_TC), ("tf32", TOL_TC)])
+def test_network_tensor_core_vs_golden(cf, dev, precision, tol):
+    """Flow-parameter records and raw (B,K,4) of the network stage against the reference's golden: the 11-bit modes at the
+    2e-3 bar (observed 2e-4 on the records, 5e-4 on raw); bf16 (8-bit significand through ten layers) at its measured
+    level (1.8e-3 / 3.4e-3)."""
+    _network_case(cf, dev, "network_canonical", precision, tol, tol)
 
 
 def test_tensor_core_full_image_tile_properties(cf, dev):
@@ -486,24 +491,76 @@ def test_config5_white_background_k128(cf, dev, precision, tol):
     assert (ks[:, 6] - dm).abs().max().item() <= tol
 
 
-def test_stressed_heads_precision_report(cf, dev):
-    """SURVEY §8(d) 'stressed heads' variant (amortisation x8, heads x4): default init hides GEMM rounding.  fp16
-    operands (11-bit significand) must stay inside the 2e-3 bar where bf16 may not; both are reported."""
+def _bench_dtype():
+    import bench
+    return bench.RENDER_PRECISION
+
+
+def test_bench_dtype_meets_the_bar_on_the_stressed_heads_fixture(cf, dev):
+    """SURVEY §8(d) 'stressed heads' variant (amortisation x8, heads x4, biases ~ N(0,1)): default init leaves the flows
+    near identity and hides GEMM rounding.  The precision mode the driver's bench line reports (bench.RENDER_PRECISION)
+    must keep predictive mean, 'uncertainty' std and mean depth within the 2e-3 bar of the reference path there — against
+    the oracle on the host AND against the library's own fp32 check mode.  bf16 operands (same speed) do not: their drift
+    is pinned at its measured level so that a regression (or an improvement) is noticed, and it is NOT the bench dtype."""
+    prec = _bench_dtype()
+    assert prec in ("fp16", "tf32", "fp32"), "the bench must render in a mode that passes this fixture"
     cfg = O.CfnConfig()
     p = O.make_params(cfg, 2, "stressed")
     sa, sr = O.make_latents(cfg, 2)
     net = make_net(cf, cfg, p, sa, sr, dev)
-    rays = O.synthetic_rays(64, 21).to(dev)
-    ref = cf.render_rays(rays, net, None, 128, False, False, precision="fp32", want_kstats=True)
+    rays = O.synthetic_rays(64, 21)
+    ea, er = O.test_latents(sa, sr)
+    with torch.no_grad():
+        o = O.render_rays(p, cfg, rays, ea, er, False, faithful=False)
+    m, s, dm = O.k_reduce(o["rgb_map"], o["depth_map"], cfg.K)
+    oracle = torch.cat([m, s, dm[:, None]], -1)
+    ref = cf.render_rays(rays.to(dev), net, None, 128, False, False, precision="fp32", want_kstats=True)["kstats"][:, :7].cpu()
+    assert (ref - oracle).abs().max().item() <= 2e-4     # the check mode itself (ill-conditioned fixture: fp32 noise)
     errs = {}
-    for prec in ("bf16", "fp16"):
-        out = cf.render_rays(rays, net, None, 128, False, False, precision=prec, want_kstats=True)
-        errs[prec] = {"rgb_mean": (out["kstats"][:, 0:3] - ref["kstats"][:, 0:3]).abs().max().item(),
-                      "rgb_std": (out["kstats"][:, 3:6] - ref["kstats"][:, 3:6]).abs().max().item(),
-                      "depth_mean": (out["kstats"][:, 6] - ref["kstats"][:, 6]).abs().max().item()}
-    print("stressed-heads drift vs fp32 check mode:", errs)
-    assert errs["fp16"]["rgb_mean"] <= TOL_TC and errs["fp16"]["depth_mean"] <= TOL_TC
-    assert errs["fp16"]["rgb_mean"] <= errs["bf16"]["rgb_mean"] * 1.5 + 1e-4
+    for pr in sorted({prec, "bf16", "fp16", "tf32"}):
+        ks = cf.render_rays(rays.to(dev), net, None, 128, False, False, precision=pr, want_kstats=True)["kstats"][:, :7].cpu()
+        errs[pr] = {"rgb_mean": max((ks[:, 0:3] - r[:, 0:3]).abs().max().item() for r in (ref, oracle)),
+                    "rgb_std": max((ks[:, 3:6] - r[:, 3:6]).abs().max().item() for r in (ref, oracle)),
+                    "depth_mean": max((ks[:, 6] - r[:, 6]).abs().max().item() for r in (ref, oracle))}
+    print("stressed-heads drift vs fp32 check mode / oracle:", errs)
+    for k, v in errs[prec].items():
+        assert v <= TOL_TC, (prec, k, v)
+    for k, v in errs["tf32"].items():
+        assert v <= TOL_TC, ("tf32", k, v)
+    # bf16: outside the bar on this fixture (9.7e-3 / 1.7e-2 / 7.5e-4 measured in round 1)
+    assert errs["bf16"]["rgb_mean"] <= 2.5e-2 and errs["bf16"]["rgb_std"] <= 4e-2 and errs["bf16"]["depth_mean"] <= TOL_TC
+
+
+def test_bench_dtype_network_stage_on_the_stressed_golden(cf, dev):
+    """The network stage in the bench dtype on the golden the unmodified reference wrote for the stressed weights.  The
+    flow-parameter records (what K1 produces) are held to 3e-3 on values of magnitude ~10 (observed 1.1e-3).  The raw
+    (M,K,4) flow outputs are NOT comparable on this fixture — the amplified flows turn a 1e-6 parameter difference into
+    1e-3 of raw (the reference's own fp32 result is that far from an fp64 evaluation) and a 1e-3 one into 0.3 — so what
+    is compared downstream is what the renderer consumes: colour = sigmoid(raw rgb) and the opacity of a sample of
+    length 0.05, alpha = 1 - exp(-softplus(raw sigma) * 0.05), against an fp64 evaluation."""
+    prec = _bench_dtype()
+    g, cfg, p = load_golden("network_stressed")
+    sa, sr = T(g["in_sample_alpha"]), T(g["in_sample_rgb"])
+    net = make_net(cf, cfg, p, sa, sr, dev)
+    pts, dirs = T(g["in_pts"]), T(g["in_dirs"])
+    eng = cf.engine_for(net, dev, prec)
+    fp = eng.network(pts.shape[0], 1, pts=pts.to(dev).contiguous(), viewdirs=dirs.to(dev).contiguous())
+    with torch.no_grad():
+        ref = oracle_flow_params(p, cfg, T(g["out_embedded"]))
+    err = (fp.cpu() - ref).abs().max().item()
+    print(f"network_stressed[{prec}] flow-parameter max|err| = {err:.3e} (max |value| {ref.abs().max().item():.1f})")
+    assert err <= 3e-3, err
+    raw, _ = cf.run_network(pts.to(dev)[:, None, :], dirs.to(dev), net, False, True, precision=prec)
+    with torch.no_grad():
+        p64 = {k: v.double() for k, v in p.items()}
+        ea, er = O.test_latents(sa, sr)
+        raw64, _ = O.nerf_flows_forward(p64, cfg, T(g["out_embedded"]).double(), ea.double(), er.double(), False,
+                                        faithful=False)
+    act = lambda r: torch.cat([torch.sigmoid(r[..., :3]), 1 - torch.exp(-torch.nn.functional.softplus(r[..., 3:]) * 0.05)], -1)  # noqa: E731
+    e_mine = (act(raw.cpu()[:, 0].double()) - act(raw64)).abs().max().item()
+    e_ref = (act(T(g["out_raw"]).double()) - act(raw64)).abs().max().item()
+    print(f"network_stressed[{prec}] activated outputs: max|err| vs fp64 = {e_mine:.3e} (the reference's fp32: {e_ref:.3e})")
+    assert e_mine <= max(5e-2, 100 * e_ref)      # per-(point, k) values; the rendered statistics carry the 2e-3 bar above
 
 
 # ------------------------------------------------------------------------------------------------

@@ -112,3 +112,30 @@ def test_sample_pdf_sequential_oracle_agrees_with_upstream_formulation():
     # deterministic u is sorted -> samples sorted
     s, _ = O.sample_pdf(bins.numpy(), w.numpy(), torch.linspace(0, 1, Nf).expand(B, Nf).numpy())
     assert np.all(np.diff(s, axis=-1) >= 0)
+
+
+def test_depth_supervised_trainer_body_golden():
+    """The shipped recipe's loss (--colmap_depth, main:1009-1055) from the unmodified reference: colour rays in the first
+    network call, depth rays in the second (own noise), entropy = the first call's scalar, depth MSE on mean_K depth."""
+    g, cfg, p = load_golden("train_depth_small")
+    n_rgb = int(g["in_n_rgb"])
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    out = O.render_rays(pr, cfg, T(g["in_rays"]), T(g["in_eps_alpha"]), T(g["in_eps_rgb"]), True,
+                        t_rand=T(g["in_t_rand"]), faithful=True, netchunk=int(g["in_netchunk"]))
+    np.testing.assert_allclose(out["rgb_map"].detach().numpy(), g["out_rgb_map"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(out["depth_map"].detach().numpy(), g["out_depth_map"], rtol=0, atol=2e-5)
+    assert len(out["entropy_calls"]) == 2 and out["entropy_calls"][0][1] == n_rgb * 128
+    res = O.trainer_loss(out, T(g["in_target"]), cfg.K, float(g["in_beta1"]), target_depth=T(g["in_target_depth"]),
+                         depth_lambda=float(g["in_depth_lambda"]))
+    for k in ("loss_entropy", "loss_nll", "depth_loss", "loss", "psnr"):
+        np.testing.assert_allclose(float(res[k]), float(g["out_" + k]), rtol=2e-5, err_msg=k)
+    res["loss"].backward()
+    names = [str(n) for n in g["out_grad_names"]]
+    for n, ref_norm in zip(names, g["out_grad_norms"]):
+        gr = pr[n].grad
+        mine = 0.0 if gr is None else float(gr.double().pow(2).sum().sqrt())
+        assert abs(mine - ref_norm) <= 1e-3 * max(ref_norm, 1e-7) + 1e-9, (n, mine, ref_norm)
+    for k in g:
+        if k.startswith("grad__"):
+            np.testing.assert_allclose(pr[k[6:]].grad.numpy(), g[k], rtol=1e-3, atol=1e-3 * np.abs(g[k]).max() + 1e-9,
+                                       err_msg=k)
