@@ -19,6 +19,7 @@ SYMBOLS = {
     "cfn_version": (_i32, []),
     "cfn_create": (_i32, [C.POINTER(CfnConfigC), C.POINTER(_vp)]),
     "cfn_destroy": (_i32, [_vp]),
+    "cfn_set_deterministic": (_i32, [_vp, _i32]),
     "cfn_param_count": (_i32, [_vp]),
     "cfn_param_name": (C.c_char_p, [_vp, _i32]),
     "cfn_param_numel": (_i64, [_vp, _i32]),

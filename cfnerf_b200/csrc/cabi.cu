@@ -57,6 +57,10 @@ extern "C" int cfn_create(const CfnConfig* cfg, CfnHandle** out) {
   h->n_floats = 0;
   h->packed = false;
   h->tc = nullptr;
+  h->tc_dirty = 0;
+  h->deterministic = 0;
+  h->det_scratch = nullptr;
+  h->det_floats = 0;
   h->gemm_tc = (cfg->precision != CFN_PREC_FP32) ? 1 : 0;
   if (const char* e = getenv("CFN_TRAIN_GEMM")) {   // experiments: "fp32" forces the CUDA-core GEMMs, "tf32" the tensor cores
     if (!strcmp(e, "fp32")) h->gemm_tc = 0;
@@ -177,6 +181,7 @@ extern "C" int cfn_create(const CfnConfig* cfg, CfnHandle** out) {
 extern "C" int cfn_destroy(CfnHandle* h) {
   if (!h) return CFN_OK;
   if (h->tc) tc_destroy(h);
+  cudaFree(h->det_scratch);
   cudaFree(h->w32);
   cudaFree(h->wg);
   if (h->amA_g != h->amA) cudaFree(h->amA_g);
@@ -211,10 +216,9 @@ extern "C" int cfn_pack_weights(CfnHandle* h, const float* const* params, int n_
   cudaStream_t s = (cudaStream_t)stream;
   int rc = pack_fp32(h, params, s);
   if (rc != CFN_OK) return rc;
-  if (h->tc) {
-    rc = tc_pack(h, s);
-    if (rc != CFN_OK) return rc;
-  }
+  // the tensor-core weight stream of the fused render kernel (K1) is rebuilt lazily, by the first cfn_network_fwd that
+  // needs it: a training loop that re-packs after every optimiser step never pays for it (0.12 ms of a 1.9 ms step)
+  if (h->tc) h->tc_dirty = 1;
   h->packed = true;
   return CFN_OK;
 }
@@ -263,8 +267,14 @@ extern "C" int cfn_network_fwd(CfnHandle* h, const float* rays, const float* z_v
     return CFN_ENOMEM;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (h->tc && !save_for_backward)
+  if (h->tc && !save_for_backward) {
+    if (h->tc_dirty) {
+      int rc = tc_pack(h, s);
+      if (rc != CFN_OK) return rc;
+      h->tc_dirty = 0;
+    }
     return tc_network_fwd(h, rays, z_vals, pts, viewdirs, B, N, flow_params, workspace, workspace_bytes, s);
+  }
   if (save_for_backward || B * N <= kChainPassPoints)
     return chain_network_fwd(h, rays, z_vals, pts, viewdirs, B, N, flow_params, (float*)workspace, save_for_backward, s);
   // bounded-memory passes over whole rays (results are independent of the split: every point is independent)
@@ -468,4 +478,33 @@ extern "C" int cfn_globals_grad_f32(const CfnHandle* h, const float* g_globals_p
     return CFN_ESTATE;
   }
   return launch_globals_grad(g_globals_partial, B, h->globals, entropy_coef, out8, (cudaStream_t)stream);
+}
+
+extern "C" int cfn_set_deterministic(CfnHandle* h, int on) {
+  CFN_CHECK_ARG(h != nullptr, "cfn_set_deterministic: null handle");
+  if (on && !h->det_scratch) {
+    // the largest (splits x (out x in + out)) over every weight gradient the backward chain issues; the split count is
+    // bounded by one K slice per CTA (tensor-core engine) or 8 per SM (CUDA-core engine), whichever engine runs
+    int64_t need = 0;
+    auto account = [&](int64_t out_f, int64_t in_f) {
+      const int cg = out_f <= 128 ? 1 : 2;
+      const int64_t bn = in_f >= 256 ? 256 : ((in_f + 15) / 16) * 16;
+      const int64_t tiles_tc = ((out_f + 128 * cg - 1) / (128 * cg)) * ((in_f + bn - 1) / bn);
+      const int64_t tiles_cc = ((out_f + 127) / 128) * ((in_f + 127) / 128);
+      int64_t split = (148 / cg) / tiles_tc;
+      const int64_t split_cc = (148 * 8 + tiles_cc - 1) / tiles_cc;
+      if (split_cc > split) split = split_cc;
+      if (split < 2) split = 2;
+      const int64_t n = split * (out_f * in_f + out_f);
+      if (n > need) need = n;
+    };
+    for (size_t i = 0; i < h->slots.size(); ++i)
+      if (h->wv[i].ld) account(h->slots[i].rows, h->wv[i].ld);
+    account(3 * h->cfg.F, (h->cfg.h_alpha + 7) & ~7);
+    account(15 * h->cfg.F, (h->cfg.h_rgb + 7) & ~7);
+    CFN_CUDA(cudaMalloc(&h->det_scratch, (size_t)need * sizeof(float)));
+    h->det_floats = need;
+  }
+  h->deterministic = on ? 1 : 0;
+  return CFN_OK;
 }

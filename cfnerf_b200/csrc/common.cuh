@@ -68,6 +68,8 @@ template <bool FAST> __device__ __forceinline__ float softplus_(float x) {
   if (FAST) return x > 20.0f ? x : __logf(1.0f + __expf(x));
   return x > 20.0f ? x : log1pf(expf(x));
 }
+// log of the log-det terms (arguments in (1e-8, ~2]): one MUFU.LG2 in the fast flavour (absolute error ~2e-7)
+template <bool FAST> __device__ __forceinline__ float log_(float x) { return FAST ? __logf(x) : logf(x); }
 template <bool FAST> __device__ __forceinline__ float tanh_(float x) {
   if (FAST) { const float t = __expf(2.0f * x); return 1.0f - __fdividef(2.0f, t + 1.0f); }
   return tanhf(x);
@@ -139,7 +141,14 @@ struct GemmArgs {
   // tensor-core engine only: bf16 STORAGE.  ab_bf16: A and B point to __nv_bfloat16 (strides in elements, tcgen05
   // kind::f16 with bf16 operands); c_bf16: C is written as bf16 (else fp32).  Accumulation is fp32 either way.
   int ab_bf16, c_bf16;
+  // split_k > 1 only, opt-in determinism: instead of fp32 atomics into C every split stores its partial product as a
+  // dense (M x N) slab in `partials` (capacity partials_floats; the row sums follow the slabs) and a second pass adds the
+  // slabs in split order — bitwise run-to-run stable weight gradients.  C need not be pre-zeroed then.
+  float* partials; int64_t partials_floats;
 };
+// C(m,n) = sum_z partials[z][m][n] (fixed order), rowsum_out[m] = sum_z rowsum_partials[z][m] when given
+int reduce_split_partials(const float* partials, int split, int64_t M, int N, float* C, int64_t c_rs,
+                          const float* rowsum_partials, float* rowsum_out, cudaStream_t s);
 int launch_sgemm(const GemmArgs& g, cudaStream_t s);
 // same contract on the tensor cores (tcgen05.mma kind::tf32, TMA-fed; gemm_tc.cu).  round_out: round the stored
 // outputs to the tf32 grid (they are the next GEMM's operands).

@@ -137,7 +137,7 @@ flow_composite_fwd_kernel(int F_rt, int K, const float* __restrict__ globals, co
           const float d1 = P[f], d2 = P[F + f], bb = P[2 * F + f];
           const float t = tanh_<FAST>(d2 * za + bb);
           za += d1 * t;
-          if (TRAIN) lda += logf(fabsf((1.0f - t * t) * (d1 * d2) + 1.0f) + 1e-8f);
+          if (TRAIN) lda += log_<FAST>(fabsf((1.0f - t * t) * (d1 * d2) + 1.0f) + 1e-8f);
         }
         // ---- rgb stack (z_size 3; components reversed on odd flows, models.py:404-408) ----
         float z0 = zc00, z1 = zc01, z2 = zc02, ldc = 0.f;
@@ -156,9 +156,9 @@ flow_composite_fwd_kernel(int F_rt, int K, const float* __restrict__ globals, co
           z1 += s1;
           z2 += odd ? s0 : s2;
           if (TRAIN) {
-            ldc += logf(fabsf((1.0f - t0 * t0) * (Q[0] * Q[6]) + 1.0f) + 1e-8f) +
-                   logf(fabsf((1.0f - t1 * t1) * (Q[3] * Q[9]) + 1.0f) + 1e-8f) +
-                   logf(fabsf((1.0f - t2 * t2) * (Q[5] * Q[11]) + 1.0f) + 1e-8f);
+            ldc += log_<FAST>(fabsf((1.0f - t0 * t0) * (Q[0] * Q[6]) + 1.0f) + 1e-8f) +
+                   log_<FAST>(fabsf((1.0f - t1 * t1) * (Q[3] * Q[9]) + 1.0f) + 1e-8f) +
+                   log_<FAST>(fabsf((1.0f - t2 * t2) * (Q[5] * Q[11]) + 1.0f) + 1e-8f);
           }
         }
         if (TRAIN && active) {
@@ -432,35 +432,34 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
     const float gla = active ? gl_a : 0.f, glc = active ? gl_c : 0.f;
 
     float S = 0.f;
-    // register prefetch of the next block's parameters and transmittances while the current block is processed
-    float pre[NPRE], tpre[PB];
+    // register prefetch of the next block's parameters (and of the next point's transmittance) while the current one is
+    // processed
+    float pre[NPRE];
     {
       const int c = n_blocks - 1, n0 = c * PB, cnt = (N - n0) * PP;
 #pragma unroll
       for (int u = 0; u < NPRE; ++u) pre[u] = (lane + 32 * u < cnt) ? __ldg(prow + (int64_t)n0 * PP + lane + 32 * u) : 0.f;
-#pragma unroll
-      for (int i = 0; i < PB; ++i) tpre[i] = (active && n0 + i < N) ? __ldg(trow + (int64_t)(n0 + i) * K + k) : 0.f;
     }
+    float t_next = active ? __ldg(trow + (int64_t)(N - 1) * K + k) : 0.f;
     for (int c = n_blocks - 1; c >= 0; --c) {
       const int n0 = c * PB;
       const int npts = min(PB, N - n0);
-      float tcur[PB];
 #pragma unroll
       for (int u = 0; u < NPRE; ++u) if (lane + 32 * u < PB * PP) sP[lane + 32 * u] = pre[u];
-#pragma unroll
-      for (int i = 0; i < PB; ++i) tcur[i] = tpre[i];
       __syncwarp();
       if (c > 0) {
         const int m0 = n0 - PB;   // full block
 #pragma unroll
         for (int u = 0; u < NPRE; ++u) pre[u] = (lane + 32 * u < PB * PP) ? __ldg(prow + (int64_t)m0 * PP + lane + 32 * u) : 0.f;
-#pragma unroll
-        for (int i = 0; i < PB; ++i) tpre[i] = active ? __ldg(trow + (int64_t)(m0 + i) * K + k) : 0.f;
       }
-#pragma unroll
-      for (int i = PB - 1; i >= 0; --i) {
-        if (i < npts) {
+      // NOT unrolled: one point is ~1200 instructions; four copies of the body fell out of the instruction cache (the
+      // first capture showed two instruction-fetch stalls per issued instruction, profiles/r02_prof_k2k4_summary.csv)
+#pragma unroll 1
+      for (int i = npts - 1; i >= 0; --i) {
+        {
           const int n = n0 + i;
+          const float T = t_next;
+          if (n > 0) t_next = active ? __ldg(trow + (int64_t)(n - 1) * K + k) : 0.f;
           const float* Pn = sP + i * PP;
           float* On = sO + i * PP;
           // recompute alpha stack with intermediates
@@ -489,7 +488,6 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
             z[0] += odd ? s2 : s0; z[1] += s1; z[2] += odd ? s0 : s2;
           }
           // ---- compositing adjoint (Appendix A.2) ----
-          const float T = tcur[i];
           const float sig_za = sigmoid_<FAST>(za);
           const float alpha = 1.0f - exp_<FAST>(-softplus_<FAST>(za) * sd[n]);
           const float w = alpha * T;

@@ -28,6 +28,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace cfn {
 namespace {
@@ -55,55 +56,15 @@ struct TgParams {
   int64_t n_work;      // m_tiles * n_tiles * split_k
   int stages; int stage_bytes;
   float* rowsum;       // optional (atomic GEMMs): rowsum[m] += sum_k A(m,k)
+  int64_t partial_stride;   // split-K without atomics (deterministic mode): split z STORES its tile at C + z * partial_stride
+                            // (and its row sums at rowsum + z * M); the caller adds the slabs in a fixed order afterwards
   uint32_t* mask_out;  // optional (EPI_RELU): word [m][n / 32], bit 8 * (n % 4) + (n % 32) / 4 = output (m, n) > 0
   const uint32_t* aux_bits;   // optional (EPI_RELU_MASK_MUL): the same words, read instead of the fp32 aux
   int64_t bits_ld;     // words per row of either
 };
 
-// ---- PTX wrappers (same idioms as mlp_tc.cu) -----------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
-  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(bar_cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" :: "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+using namespace ptx;   // mbarrier / cluster / TMA / tcgen05 wrappers shared with mlp_tc.cu (ptx_sm100.cuh)
 
-template <int CG>
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  if (CG == 1)
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-  else   // both CTAs of the pair issue; the peer bit of the barrier address is cleared: bytes land on the leader's barrier
-    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu) : "memory");
-}
 // DT = 0: fp32 storage, kind::tf32 (K = 8 per instruction); DT = 1: bf16 storage, kind::f16 (K = 16)
 template <int CG, int DT>
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -124,28 +85,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-template <int CG>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  if (CG == 1)
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-  else
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 :: "r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
-  uint32_t r; asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory"); return r;
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // round-to-nearest (ties away) onto the 10-bit tf32 significand: the tensor core TRUNCATES fp32 operands, which is
 // a one-sided error that accumulates over the layers; operands written through this are read back exactly
 __device__ __forceinline__ float round_tf32(float x) {
@@ -398,7 +337,8 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             float x[4] = {a4.x, a4.y, a4.z, a4.w};
             float* cp = p.C + gm * p.c_rs + gn;
             if (EPI == TG_ATOMIC) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(cp), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+              if (p.partial_stride) *reinterpret_cast<float4*>(cp + (int64_t)z * p.partial_stride) = make_float4(x[0], x[1], x[2], x[3]);
+              else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(cp), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
               continue;
             }
             uint32_t keep = 0x01010101u;   // relu'(h) of column slot i at bit 8 * i
@@ -463,7 +403,10 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 if (gn + i >= p.N) continue;
-                if (EPI == TG_ATOMIC) { atomicAdd(cp + i, x[i]); continue; }
+                if (EPI == TG_ATOMIC) {
+                  if (p.partial_stride) cp[(int64_t)z * p.partial_stride + i] = x[i]; else atomicAdd(cp + i, x[i]);
+                  continue;
+                }
                 float y = x[i] + b4[i];
                 if (EPI == TG_MASK && p.accumulate) y += cp[i];
                 if (EPI == TG_RELU) y = fmaxf(y, 0.f);
@@ -490,7 +433,10 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t sum = tmem_ld1(tmem_row + 256u);
         tmem_ld_wait();
         const int64_t gm = tile_m0 + q * 32 + lane;
-        if (gm < p.M) atomicAdd(p.rowsum + gm, __uint_as_float(sum));
+        if (gm < p.M) {
+          if (p.partial_stride) p.rowsum[(int64_t)z * p.M + gm] = __uint_as_float(sum);
+          else atomicAdd(p.rowsum + gm, __uint_as_float(sum));
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -655,6 +601,20 @@ int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s) {
   plan_tgemm(g, p, CG, a_mn, b_mn, smem);
   p.round_out = round_out;
   p.rowsum = g.rowsum;
+  // deterministic split-K: the splits store dense (M x N) slabs into the caller's scratch, added in a fixed order below
+  const bool det = p.atomic && g.partials != nullptr;
+  float* const c_final = g.C;
+  const int64_t c_rs_final = g.c_rs;
+  float* const rowsum_final = g.rowsum;
+  if (det) {
+    const int64_t slab = g.M * (int64_t)g.N;
+    CFN_CHECK_ARG((int64_t)p.split_k * (slab + (g.rowsum ? g.M : 0)) <= g.partials_floats,
+                  "tgemm: deterministic split-K scratch too small (%lld floats needed)",
+                  (long long)((int64_t)p.split_k * (slab + g.M)));
+    p.C = g.partials; p.c_rs = g.N; p.partial_stride = slab;
+    p.vec_ok = (g.N % 4 == 0) && aligned16(g.partials);
+    if (g.rowsum) p.rowsum = g.partials + (int64_t)p.split_k * slab;
+  }
   p.mask_out = (g.epilogue == EPI_RELU && !p.atomic) ? g.mask_out : nullptr;
   p.aux_bits = (g.epilogue == EPI_RELU_MASK_MUL) ? g.aux_bits : nullptr;
   p.bits_ld = g.bits_ld;
@@ -678,10 +638,15 @@ int launch_tgemm(const GemmArgs& g, int round_out, cudaStream_t s) {
   else if (g.epilogue == EPI_RELU) epi = TG_RELU;
   else if (g.epilogue == EPI_TANH_MASK) epi = TG_TANH;
   else if (g.epilogue == EPI_RELU_MASK_MUL || g.accumulate) epi = TG_MASK;
-#define TG_LAUNCH(cg, am, bm, e) return launch_variant<cg, am, bm, e>(tmA, tmB, p, smem, s)
+  auto finish = [&](int rc_launch) -> int {
+    if (rc_launch != CFN_OK || !det) return rc_launch;
+    return reduce_split_partials(g.partials, p.split_k, g.M, g.N, c_final, c_rs_final,
+                                 rowsum_final ? p.rowsum : nullptr, rowsum_final, s);
+  };
+#define TG_LAUNCH(cg, am, bm, e) return finish(launch_variant<cg, am, bm, e>(tmA, tmB, p, smem, s))
 #define TG_BY_CG(am, bm, e) do { if (CG == 1) TG_LAUNCH(1, am, bm, e); else TG_LAUNCH(2, am, bm, e); } while (0)
-#define TG_BF(am, bm, e, cbf) do { if (CG == 1) return launch_variant<1, am, bm, e, 1, cbf>(tmA, tmB, p, smem, s); \
-                                   else return launch_variant<2, am, bm, e, 1, cbf>(tmA, tmB, p, smem, s); } while (0)
+#define TG_BF(am, bm, e, cbf) do { if (CG == 1) return finish(launch_variant<1, am, bm, e, 1, cbf>(tmA, tmB, p, smem, s)); \
+                                   else return finish(launch_variant<2, am, bm, e, 1, cbf>(tmA, tmB, p, smem, s)); } while (0)
   if (bf) {
     if (!a_mn && !b_mn && epi == TG_PLAIN && g.c_bf16) TG_BF(false, false, TG_PLAIN, true);
     if (!a_mn && !b_mn && epi == TG_RELU && g.c_bf16) TG_BF(false, false, TG_RELU, true);

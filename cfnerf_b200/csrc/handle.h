@@ -63,7 +63,12 @@ struct CfnHandle {
   std::vector<int64_t> wg_offset;   // in 4-byte slots
   float* amA_g; float* amC_g;   // operand copies of amA / amC (tf32-rounded when gemm_tc, else aliases)
 
+  // opt-in deterministic weight gradients (cfn_set_deterministic): scratch for the split-K slabs of one wgrad
+  int deterministic;
+  float* det_scratch; int64_t det_floats;
+
   cfn::TcPlan* tc;   // nullptr in fp32 mode
+  int tc_dirty;      // the fp32 copies changed since K1's weight stream was built (rebuilt lazily by cfn_network_fwd)
 };
 
 namespace cfn {

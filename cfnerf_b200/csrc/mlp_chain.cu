@@ -379,7 +379,30 @@ __global__ void colsum_kernel(const float* __restrict__ g, int64_t ld, int64_t M
   }
 }
 
-static int colsum(const float* g, int64_t ld, int64_t M, int N, float* out, cudaStream_t s) {
+// deterministic variant: 32 columns x 8 row lanes per block, every thread adds its rows in order, the 8 lanes are joined
+// in a fixed order (no atomics)
+__global__ void colsum_det_kernel(const float* __restrict__ g, int64_t ld, int64_t M, int N, float* __restrict__ out) {
+  __shared__ float red[8][32];
+  const int c = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + c;
+  float s = 0.f;
+  if (n < N) for (int64_t m = rl; m < M; m += 8) s += g[m * ld + n];
+  red[rl][c] = s;
+  __syncthreads();
+  if (rl == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][c];
+    out[n] = t;
+  }
+}
+
+static int colsum(const float* g, int64_t ld, int64_t M, int N, float* out, cudaStream_t s, bool deterministic = false) {
+  if (deterministic) {
+    colsum_det_kernel<<<(unsigned)((N + 31) / 32), 256, 0, s>>>(g, ld, M, N, out);
+    CFN_LAUNCH_CHECK();
+    return CFN_OK;
+  }
   CFN_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), s));
   const int rows = 256;
   colsum_kernel<<<(unsigned)((M + rows - 1) / rows), N < 256 ? ((N + 31) / 32) * 32 : 256, 0, s>>>(g, ld, M, N, out, rows);
@@ -391,7 +414,7 @@ static int colsum(const float* g, int64_t ld, int64_t M, int N, float* out, cuda
 // db (optional): the bias gradient = column sums of G, fused into the tensor-core GEMM when possible
 static int wgrad(const CfnHandle* h, const float* G, int64_t ldg, int out_f, const float* X, int64_t ldx, int in_f, int64_t M,
                  float* dW, float* db, cudaStream_t s) {
-  CFN_CUDA(cudaMemsetAsync(dW, 0, (size_t)out_f * in_f * sizeof(float), s));
+  if (!h->deterministic) CFN_CUDA(cudaMemsetAsync(dW, 0, (size_t)out_f * in_f * sizeof(float), s));
   GemmArgs g{};
   g.A = G; g.a_rs = 1; g.a_cs = ldg;        // A(m=o, k=pt) = G[pt*ldg + o]
   g.B = X; g.b_rs = ldx; g.b_cs = 1;        // B(k=pt, n=i) = X[pt*ldx + i]
@@ -416,15 +439,16 @@ static int wgrad(const CfnHandle* h, const float* G, int64_t ldg, int out_f, con
   }
   if (split < 2) split = 2;                 // split_k > 1 selects the atomic accumulate path
   g.split_k = (int)split;
+  if (h->deterministic) { g.partials = h->det_scratch; g.partials_floats = h->det_floats; }
   if (db) {
     if (h->gemm_tc && tgemm_can_rowsum(g)) {
-      CFN_CUDA(cudaMemsetAsync(db, 0, (size_t)out_f * sizeof(float), s));
+      if (!h->deterministic) CFN_CUDA(cudaMemsetAsync(db, 0, (size_t)out_f * sizeof(float), s));
       g.rowsum = db;
     } else if (h->chain_bf16) {
       set_error("bf16 chain: the bias gradient could not be fused into the wgrad (out %d in %d)", out_f, in_f);
       return CFN_ESTATE;
     } else {
-      int rc = colsum(G, ldg, M, out_f, db, s);
+      int rc = colsum(G, ldg, M, out_f, db, s, h->deterministic != 0);
       if (rc) return rc;
     }
   }

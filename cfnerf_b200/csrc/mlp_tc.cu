@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include "handle.h"
+#include "ptx_sm100.cuh"
 
 namespace cfn {
 
@@ -48,6 +49,13 @@ struct TcStep {
   int out_col;    // kind 2: first column in the flow-parameter record
   int n_valid;    // kind 2: valid output columns
   int row0;       // first row of this step's blocks in the weight stream (rows of 64 elements)
+  // Two-part steps whose output overwrites the activation tile in place (kind 0/1, n_parts == 2, natural part order): the
+  // accumulator of the FIRST part (columns 0..n_part-1 = output chunks 0..n_part/64-1) is committed on its own and
+  // drained while the second part's MMAs run.  Output chunk x may only be stored once the second part has read INPUT
+  // chunk x: afree_pos byte x = the K position of the second part after which that is the case (0 if the step does not
+  // read activation chunk x at all).
+  int split_commit;
+  unsigned int afree_pos;
 };
 
 struct TcPlanDev {
@@ -74,7 +82,6 @@ struct TcPlan {
   void* stream_dev;             // packed weight stream (2-byte elements)
   int64_t stream_rows;
   float* table_dev;             // biases + flags
-  std::vector<float> table_host_flags;   // unused placeholder for symmetry
   float* compA; float* compA_b; // composed alpha conditioning (3F x W), (3F)
   float* compC; float* compC_b; // composed rgb conditioning (15F x W/2), (15F)
   CUtensorMap tm_big, tm_small, tm_bias;
@@ -95,60 +102,7 @@ struct TcPlan {
 // ======================================================================================================
 // PTX wrappers
 // ======================================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
-  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-// arrive on a barrier addressed in the shared::cluster window (own CTA or the pair's leader)
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  // default .release.cta semantics, as cutlass::arch::ClusterBarrier::arrive: a cluster-scope release costs a
-  // MEMBAR.ALL.GPU per arrival; the generic->async proxy fence issued before it is what orders the smem writes
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(bar_cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      // default .acquire.cta: a cluster-scope acquire makes ptxas emit CCTL.IVALL (L1 invalidate) after every wait,
-      // which round 1's first profile showed to be the single largest stall of the MMA-issuing thread
-      // the suspend-time hint lets the warp SLEEP in hardware until the phase completes (woken by the arrival) instead of
-      // re-issuing the probe every few hundred ns: spinning waiters steal issue slots from the MMA-issuing warp
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" :: "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <int CG>
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  if (CG == 1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-  } else {
-    // executed by both CTAs of the pair; the peer bit of the barrier address is cleared so the transaction bytes land
-    // on the leader CTA's barrier
-    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu) : "memory");
-  }
-}
+using namespace ptx;   // mbarrier / cluster / TMA / tcgen05 wrappers shared with gemm_tc.cu (ptx_sm100.cuh)
 
 template <int CG>
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -161,35 +115,6 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t 
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-
-// tcgen05.commit: the barrier receives one arrival when every MMA issued so far by this thread has completed.
-template <int CG>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  if (CG == 1)
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-  else
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 :: "r"(bar), "h"((uint16_t)3) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // two fp32 -> packed 16-bit pair (lo = element c, hi = element c+1), optional fused ReLU
 template <bool FP16, bool RELU>
@@ -238,11 +163,14 @@ struct Prof {
 // ======================================================================================================
 // the kernel
 // ======================================================================================================
-struct TcBarriers {
+struct alignas(16) TcBarriers {   // the fp32 bias staging area follows it and is read as float4
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
   uint64_t act_ready[8];
-  uint64_t acc_full;
+  uint64_t a_free[4];
+  uint64_t acc_full;    // the step's accumulator (or its FIRST part in split-commit steps) is complete
+  uint64_t acc_full2;   // split-commit steps: the second part is complete (its own barrier: the two commits of a short
+                        // layer can be a few hundred cycles apart, and a waiter must never miss a phase)
   uint64_t out_done;
   uint64_t in_ready;
   uint32_t tmem_ptr;
@@ -310,7 +238,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(bar_local(&bars->full[s]), CG); mbar_init(bar_local(&bars->empty[s]), 1); }
     for (int j = 0; j < 8; ++j) mbar_init(bar_local(&bars->act_ready[j]), 4 * CG);
+    for (int j = 0; j < 4; ++j) mbar_init(bar_local(&bars->a_free[j]), 1);
     mbar_init(bar_local(&bars->acc_full), 1);
+    mbar_init(bar_local(&bars->acc_full2), 1);
     mbar_init(bar_local(&bars->out_done), 8 * CG);
     mbar_init(bar_local(&bars->in_ready), 8 * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -346,6 +276,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
         const int rows = st.n_part / CG;           // rows of each weight block this CTA stages
         const int n_blk = st.n_parts * st.n_k;
         for (int blk = 0; blk < n_blk; ++blk) {
+          // (sleeping wait: polling this barrier with short probes instead cost 6 % of the kernel, round-2 A/B)
           mbar_wait(bar_local(&bars->empty[stage]), phase ^ 1u);
           prof.stamp();
           const bool bias_tile = (st.kinfo[blk % st.n_k] >> 24) & 1u;
@@ -386,18 +317,20 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
       // consumed completely before the next one is produced, so one counter replaces per-chunk bookkeeping:
       // chunks [0, ready_upto) of generation act_gen are known to be written (and their TMEM columns drained).
       int ready_upto = 0;
+      // Split-commit steps hand the first output chunks over while their second part is still running: those hand-overs
+      // (generation act_gen + 1) are observed by probes overlapped with the second part's MMA issue, so that the next
+      // step starts without a chain of ~300-cycle barrier round trips (1.4 k cycles per layer in the first timeline).
+      int next_upto = 0;
       const uint32_t act_bar0 = bar_local(&bars->act_ready[0]);
-      auto wait_act = [&](int j) {
-        if (act_gen == 0) return;
-        while (ready_upto <= j) { mbar_wait(act_bar0 + 8u * ready_upto, (act_gen - 1u) & 1u); ++ready_upto; }
-      };
       // non-blocking probe (no suspend hint): issued BEFORE the MMAs of the current chunk so that its ~90-cycle
       // latency overlaps their issue; the blocking wait afterwards is only taken when the probe failed
-      auto probe = [&](uint32_t bar, uint32_t parity) -> bool {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        return ok != 0;
+      auto probe = [&](uint32_t bar, uint32_t parity) -> bool { return mbar_probe(bar, parity); };
+      auto wait_act = [&](int j) {
+        if (act_gen == 0) return;
+        while (ready_upto <= j) {
+          mbar_wait(act_bar0 + 8u * ready_upto, (act_gen - 1u) & 1u);
+          ++ready_upto;
+        }
       };
       const uint32_t full_bar0 = bar_local(&bars->full[0]), empty_bar0 = bar_local(&bars->empty[0]);
       const uint64_t desc_sw32 = ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61) | ((uint64_t)1 << 16);
@@ -445,22 +378,42 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
               const bool next_full = (blocks_left > 0) ? probe(full_bar0 + 8u * nstage, nphase) : false;
               const bool can_probe_act = act_gen > 0 && ready_upto < act_chunks;
               const bool next_act = can_probe_act ? probe(act_bar0 + 8u * ready_upto, (act_gen - 1u) & 1u) : false;
+              // last K chunk of the second part of a split-commit step: the first output chunks (the NEXT generation) were
+              // handed over while this part ran; four non-blocking tests here save the next step a chain of barrier
+              // round trips (~340 cycles each) in front of its first MMA
+              if (st.split_commit && pi == 1 && kc == st.n_k - 1) {
+                const uint32_t npar = act_gen & 1u;
+                const uint32_t m = (mbar_test(act_bar0, npar) ? 1u : 0u) | (mbar_test(act_bar0 + 8u, npar) ? 2u : 0u) |
+                                   (mbar_test(act_bar0 + 16u, npar) ? 4u : 0u) | (mbar_test(act_bar0 + 24u, npar) ? 8u : 0u);
+                const int lead = (m == 15u) ? 4 : ((m & 7u) == 7u ? 3 : ((m & 3u) == 3u ? 2 : (int)(m & 1u)));
+                next_upto = lead < st.n_part / 64 ? lead : st.n_part / 64;
+              }
               if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                   if (ks < nks) umma<CG>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
                 umma_commit<CG>(empty_bar0 + 8u * stage);
+                if (st.split_commit && pi == 1) {
+                  // input chunk x has now been read for the last time: the epilogue may overwrite it with output chunk x
+#pragma unroll
+                  for (int x = 0; x < 4; ++x)
+                    if ((int)((st.afree_pos >> (8 * x)) & 0xffu) == kc) umma_commit<CG>(bar_local(&bars->a_free[x]));
+                }
               }
               __syncwarp();
               if (next_act) ++ready_upto;          // that phase has been observed complete: consumed
               cur_full_ready = next_full;
               stage = nstage; phase = nphase;
             }
+            if (st.split_commit && pi == 0) {     // the first part's accumulator is complete: its drain starts now
+              if (elect_one()) umma_commit<CG>(bar_local(&bars->acc_full));
+              __syncwarp();
+            }
           }
-          if (elect_one()) umma_commit<CG>(bar_local(&bars->acc_full));
+          if (elect_one()) umma_commit<CG>(bar_local(st.split_commit ? &bars->acc_full2 : &bars->acc_full));
           __syncwarp();
           prof.stamp();
-          if (st.kind == 2) { pending_out = true; ++out_cnt; } else { ++act_gen; ready_upto = 0; }
+          if (st.kind == 2) { pending_out = true; ++out_cnt; } else { ++act_gen; ready_upto = next_upto; next_upto = 0; }
         }
       }
     }
@@ -485,7 +438,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
     const int tid_e = threadIdx.x;
     const int row = q * 32 + lane;                         // TMEM lane == row of the tile owned by this thread
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t acc_cnt = 0;
+    uint32_t acc_cnt = 0, split_cnt = 0;
     Prof prof{(a.prof && blockIdx.x == 0 && warp == 0 && lane == 0) ? a.prof : nullptr, 0};
     Prof prof2{nullptr, 0};   // (role 3 of the profile buffer is used by the TMA-landing watcher in warp 3)
     float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + sizeof(TcBarriers));   // 512 floats
@@ -641,8 +594,6 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
           // software pipeline over this warp's (chunk, half) pieces: the next TMEM load is in flight while the
           // current 32 columns are biased, activated, packed and stored
           uint32_t va[32], vb[32];
-          const int n_mine = (n_out_chunks > hh) ? ((n_out_chunks - hh + 1) / 2) * 2 : 0;   // pieces = chunks * 2 halves
-          if (n_mine > 0) tmem_ld32(tmem_row + (uint32_t)(hh * 64), va);
           auto process = [&](uint32_t (&v)[32], int j, int half) {
             const uint32_t chunk = act_base + j * TC_CHUNK_BYTES;
 #pragma unroll
@@ -663,21 +614,37 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
                            :: "r"(chunk + swz(row, half * 4 + u)), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
             }
           };
-          for (int j = hh; j < act_chunks; j += 2) {
-            if (j < n_out_chunks) {
-              tmem_ld_wait();                                                            // va = (j, half 0)
-              tmem_ld32(tmem_row + (uint32_t)(j * 64 + 32), vb);
-              process(va, j, 0);
-              tmem_ld_wait();                                                            // vb = (j, half 1)
-              if (j + 2 < n_out_chunks) tmem_ld32(tmem_row + (uint32_t)((j + 2) * 64), va);
-              process(vb, j, 1);
-              fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
-              tc_fence_before();
+          // chunks [j0, j1) of this warp's parity; wait_free: output chunk j overwrites input chunk j, which the second
+          // part's MMAs may still be reading (split-commit steps)
+          auto drain = [&](int j0, int j1, bool wait_free) {
+            const int j_end = j1 < n_out_chunks ? j1 : n_out_chunks;
+            if (j0 < j_end) tmem_ld32(tmem_row + (uint32_t)(j0 * 64), va);
+            for (int j = j0; j < j1; j += 2) {
+              if (j < n_out_chunks) {
+                tmem_ld_wait();                                                          // va = (j, half 0)
+                tmem_ld32(tmem_row + (uint32_t)(j * 64 + 32), vb);
+                if (wait_free) mbar_wait(bar_local(&bars->a_free[j]), split_cnt & 1u);
+                process(va, j, 0);
+                tmem_ld_wait();                                                          // vb = (j, half 1)
+                if (j + 2 < j_end) tmem_ld32(tmem_row + (uint32_t)((j + 2) * 64), va);
+                process(vb, j, 1);
+                fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                tc_fence_before();
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->act_ready[j]));
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->act_ready[j]));
+          };
+          if (st.split_commit) {
+            const int n_first = st.n_part / 64;      // even: the warp keeps its chunk parity across the two parts
+            drain(hh, n_first, true);
+            mbar_wait(bar_local(&bars->acc_full2), split_cnt & 1u);              // the second part's accumulator
+            tc_fence_after();
+            drain(n_first + hh, act_chunks, false);
+            ++split_cnt;
+          } else {
+            drain(hh, act_chunks, false);
           }
-          (void)n_mine;
         }
         if (st.kind == 2) epi_sync();                 // everyone is done with this step's bias (and the staged outputs)
         {
@@ -802,6 +769,9 @@ int tc_create(CfnHandle* h) {
   int64_t stream_row = 0;
   int table_off = 0;
 
+  // CFN_TC_SPLIT_DRAIN=0 keeps the round-1 schedule (one accumulator commit per layer) for A/B timing
+  bool split_drain = true;
+  if (const char* e = getenv("CFN_TC_SPLIT_DRAIN")) split_drain = atoi(e) != 0;
   struct KCh { int src, kstart, ksteps, col0, cols_valid, with_bias; };
   // every kind 0/1 step multiplies the ones columns (62, 63) of the gamma(d) tile by the (hi, lo) split of its fp32
   // bias, so the epilogue is a pure convert-and-store; kind 2 steps add their (tiny) bias in the epilogue
@@ -826,6 +796,16 @@ int tc_create(CfnHandle* h) {
       const int idx = kch[i].src == TC_SRC_GP ? AC : (kch[i].src == TC_SRC_GD ? AC + 1 : kch[i].src);
       st.kinfo[i] = (unsigned)idx | ((unsigned)kch[i].kstart << 8) | ((unsigned)kch[i].ksteps << 16) |
                     ((unsigned)(kch[i].with_bias == 2 ? 1 : 0) << 24);
+    }
+    st.split_commit = 0;
+    st.afree_pos = 0;
+    if (kind != 2 && st.n_parts == 2 && !st.order_rev && (st.n_part % 128) == 0 && st.n_part / 64 <= 4 && split_drain) {
+      st.split_commit = 1;
+      for (int x = 0; x < st.n_part / 64; ++x) {
+        int pos = 0;                                  // not read by this step: free right after the first K chunk
+        for (int i = 0; i < st.n_k; ++i) if (kch[i].src == x) pos = i;
+        st.afree_pos |= (unsigned)pos << (8 * x);
+      }
     }
     st.bias_off = table_off;
     st.out_col = out_col;

@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g, int64_t k_per_sp
       float* cp = g.C + gm * g.c_rs + gn;
       float v = acc[i][j];
       if (g.split_k > 1) {
-        atomicAdd(cp, v);
+        if (g.partials) g.partials[(int64_t)blockIdx.z * g.M * g.N + gm * g.N + gn] = v;   // deterministic mode: dense slab
+        else atomicAdd(cp, v);
         continue;
       }
       if (g.bias) v += g.bias[gn];
@@ -96,7 +97,39 @@ int launch_sgemm(const GemmArgs& g, cudaStream_t s) {
   if (kps == 0) kps = BK;
   dim3 grid((unsigned)((g.M + BM - 1) / BM), (unsigned)((g.N + BN - 1) / BN), (unsigned)split);
   CFN_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "sgemm: grid too large");
+  if (split > 1 && g.partials)
+    CFN_CHECK_ARG((int64_t)split * g.M * g.N <= g.partials_floats, "sgemm: deterministic split-K scratch too small");
   sgemm_kernel<<<grid, 256, 0, s>>>(g, kps);
+  CFN_LAUNCH_CHECK();
+  if (split > 1 && g.partials) return reduce_split_partials(g.partials, split, g.M, g.N, g.C, g.c_rs, nullptr, nullptr, s);
+  return CFN_OK;
+}
+
+// ---- second pass of the deterministic split-K: add the slabs in split order --------------------------------------
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int split, int64_t M, int N, float* __restrict__ C,
+                                       int64_t c_rs, const float* __restrict__ rs_part, float* __restrict__ rs_out) {
+  const int64_t total = M * (int64_t)N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total + (rs_out ? M : 0);
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < total) {
+      float acc = 0.f;
+      for (int z = 0; z < split; ++z) acc += partials[(int64_t)z * total + i];
+      C[(i / N) * c_rs + (i % N)] = acc;
+    } else {
+      const int64_t m = i - total;
+      float acc = 0.f;
+      for (int z = 0; z < split; ++z) acc += rs_part[(int64_t)z * M + m];
+      rs_out[m] = acc;
+    }
+  }
+}
+
+int reduce_split_partials(const float* partials, int split, int64_t M, int N, float* C, int64_t c_rs,
+                          const float* rowsum_partials, float* rowsum_out, cudaStream_t s) {
+  const int64_t n = M * (int64_t)N + (rowsum_out ? M : 0);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  reduce_partials_kernel<<<(unsigned)blocks, 256, 0, s>>>(partials, split, M, N, C, c_rs, rowsum_partials, rowsum_out);
   CFN_LAUNCH_CHECK();
   return CFN_OK;
 }

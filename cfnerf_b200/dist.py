@@ -117,7 +117,7 @@ class FusedTrainStep:
     def __init__(self, network_fn, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, beta1: float = 0.01,
                  precision: str | None = None, N_samples: int = 128, white_bkgd: bool = False, lindisp: bool = False,
                  depth_lambda: float = 0.0, netchunk: int | None = None, lrate_decay: float = 0.0,
-                 use_graph: bool = False):
+                 use_graph: bool = False, deterministic: bool = False):
         from . import api
         from .engine import _unwrap, engine_for
         self.module = _unwrap(network_fn)
@@ -129,6 +129,8 @@ class FusedTrainStep:
         self.netchunk = api.DEFAULT_NETCHUNK if netchunk is None else int(netchunk)
         self.decay_steps = float(lrate_decay) * 1000.0            # args.lrate_decay is in thousands of steps (main:1074)
         self.use_graph = bool(use_graph)
+        if deterministic:       # two-pass split-K weight gradients: bitwise identical steps for identical inputs
+            self.eng.set_deterministic(True)
         ps = self.eng.params
         n = sum(p.numel() for p in ps)
         f32 = dict(dtype=torch.float32, device=self.dev)

@@ -81,6 +81,12 @@ class Engine:
         self._packed_version = None
         self._ws = None
 
+    def set_deterministic(self, on: bool = True):
+        """Bitwise run-to-run stable weight gradients (two-pass split-K instead of fp32 atomics; cfn_set_deterministic)."""
+        with torch.cuda.device(self.device):
+            check(self.lib.cfn_set_deterministic(self.h, int(bool(on))), "cfn_set_deterministic")
+        return self
+
     # ---- weights --------------------------------------------------------------------------------------
     def _version(self):
         return (_WEIGHTS_EPOCH,) + tuple(p._version for p in self.params) + tuple(p.data_ptr() for p in self.params)

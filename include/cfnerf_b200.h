@@ -65,6 +65,13 @@ int cfn_version(void);
 int cfn_create(const CfnConfig* cfg, CfnHandle** out);
 int cfn_destroy(CfnHandle* h);
 
+/* Opt-in bitwise run-to-run stable training gradients.  By default the split-K weight-gradient GEMMs of
+ * cfn_network_bwd add their partial products with fp32 atomics, whose order varies between runs (differences ~1e-7
+ * relative).  With on != 0 every K split stores its partial product into handle-owned scratch (allocated by this call,
+ * like cfn_create / cfn_pack_weights: up to ~0.3 GB for the canonical network) and a second pass adds the slabs in split
+ * order; the bias-gradient column sums use a fixed-order reduction as well.  Costs a few percent of a training step. */
+int cfn_set_deterministic(CfnHandle* h, int on);
+
 /* The parameter tensors the path reads, in the order cfn_pack_weights / cfn_network_bwd expect them.
  * Names are the keys of NeRF_Flows.state_dict() (model/models.py:38-67, 339-350); the two dead heads
  * alpha_linear / alpha_std_linear (models.py:59-60) are not part of the list. */
@@ -73,7 +80,8 @@ const char* cfn_param_name(const CfnHandle* h, int i);
 int64_t cfn_param_numel(const CfnHandle* h, int i);
 
 /* Copy/convert the fp32 master parameters into the handle's packed device layouts (fp32 gathered flow
- * conditioning matrices; for the tensor-core modes also the bf16/fp16 pre-swizzled UMMA weight stream).
+ * conditioning matrices and GEMM operand copies; the bf16/fp16 pre-swizzled UMMA weight stream of the fused render
+ * kernel is rebuilt from them by the next cfn_network_fwd that needs it, on that call's stream).
  * Call after every optimizer step.  params[i] is a device pointer to tensor i (fp32, contiguous). */
 int cfn_pack_weights(CfnHandle* h, const float* const* params, int n_params, void* stream);
 

@@ -390,7 +390,9 @@ def test_one_real_trainer_body_iteration_behind_install(cf, dev):
         extras_ = {x: extras[x][:N_batch] for x in extras}
         rgb_mean = torch.mean(rgbs_, -1)
         ts, td = target_s.to(dev), target_depth.to(dev)
-        psnr_train = R.mse2psnr(R.img2mse(rgb_mean, ts))
+        # mse2psnr (helpers:16) builds torch.Tensor([10.]) on the DEFAULT device (the host script sets it to CUDA,
+        # main:1201): same expression with the constant on the device
+        psnr_train = -10. * torch.log(R.img2mse(rgb_mean, ts)) / torch.log(torch.tensor([10.], device=dev))
         rgb_std = torch.std(rgbs_, -1) * K / (K - 1)
         H_sqrt = (rgb_std.detach() * (0.8 / K) ** (-1 / 7) + 1e-05)[..., None]
         r1 = torch.exp(-((rgbs_ - ts[..., None]) ** 2) / (2 * H_sqrt * H_sqrt))
@@ -480,3 +482,32 @@ def test_second_device_in_the_same_process(cf):
     for a, b in zip(outs[:3], outs[3:]):
         assert torch.equal(a, b)
     assert abs(losses[0] - losses[1]) <= 1e-4 * max(1.0, abs(losses[0]))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_deterministic_mode_gives_bitwise_identical_gradients(cf, dev, precision):
+    """cfn_set_deterministic: two-pass split-K weight gradients (no fp32 atomics).  The same training step twice gives
+    bit-identical gradient buffers; the default (atomic) mode agrees with it to fp32 summation-order noise."""
+    from cfnerf_b200 import dist as D
+    cfg = O.CfnConfig()
+    p = O.make_params(cfg, 4, "lively")
+    sa, sr = O.make_latents(cfg, 4)
+    B = 96
+    rays = O.synthetic_rays(B, 6).to(dev)
+    g = torch.Generator().manual_seed(9)
+    target = torch.rand(B, 3, generator=g).to(dev)
+    t_rand = torch.rand(B, 128, generator=g).to(dev)
+    ea, er = torch.randn(cfg.K, 1, generator=g).to(dev), torch.randn(cfg.K, 3, generator=g).to(dev)
+    grads = []
+    for det in (True, True, False):
+        net = make_net(cf, cfg, p, sa, sr, dev)
+        tr = D.FusedTrainStep(net, lr=0.0, precision=precision, deterministic=det)
+        tr.eng.set_deterministic(det)       # engines are cached per (module, precision): set explicitly both ways
+        tr.step(rays, target, t_rand=t_rand, eps_alpha=ea, eps_rgb=er, want_loss=False)
+        torch.cuda.synchronize()
+        grads.append(tr.flat_grad.clone())
+        tr.eng.set_deterministic(False)
+    assert torch.equal(grads[0], grads[1]), "deterministic mode must be bitwise reproducible"
+    ref = grads[0].double()
+    assert (grads[2].double() - ref).norm().item() <= 1e-5 * ref.norm().item()
+    assert float(ref.abs().max()) > 0
