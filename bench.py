@@ -399,7 +399,7 @@ def streaming_kernel_rooflines(cf, dev, net, K, N, peaks):
     g_rgb = torch.randn(B2, 3, K, device=dev) * 1e-3
     g_ld = torch.full((B2, 2), -0.01 / (B2 * N * K), device=dev)
     ms_f = cuda_time_ms(lambda: eng.flow_composite(fp, zz, rays[:, 3:6], 11, ea, er, False, train=True, want_trans=True))
-    ms_b = cuda_time_ms(lambda: eng.flow_composite_bwd(fp, zz, rays[:, 3:6], 11, ea, er, False, g_rgb, None, g_ld, trans=o["trans"]))
+    ms_b = cuda_time_ms(lambda: eng.flow_composite_bwd(fp, zz, rays[:, 3:6], 11, ea, er, False, g_rgb, None, g_ld, trans=o["trans"], seg_sums=o["seg_sums"]))
     bpr_b = 2 * 72 * 4 * N + 4 * N * K + 4 * N + 44 + 12 * K + 32      # records in, record gradients out, transmittances in
     out.append({"kernel": "flow_composite_fwd_kernel<train> (K2, with log-dets + transmittance output)", "bound": "mufu",
                 "achieved": B2 / ms_f * 1e3, "unit": "rays/s", "ms": ms_f, "rays": B2})

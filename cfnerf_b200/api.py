@@ -150,7 +150,8 @@ class _RenderTrainFn(torch.autograd.Function):
         out = eng.flow_composite(fp, z_vals, rays[:, 3:6], 11, eps_a, eps_c, white_bkgd, want_raw=True,
                                  want_weights=want_weights, train=True, eps_group_rays=group_rays, want_trans=True)
         ctx.eng, ctx.white_bkgd, ctx.group_rays = eng, white_bkgd, group_rays
-        ctx.save_for_backward(rays, z_vals, eps_a, eps_c, fp, ws, out["trans"])
+        sg = out["seg_sums"] if out["seg_sums"] is not None else torch.empty(0, device=rays.device)
+        ctx.save_for_backward(rays, z_vals, eps_a, eps_c, fp, ws, out["trans"], sg)
         w = out["weights"] if want_weights else torch.empty(0, device=rays.device)
         ctx.mark_non_differentiable(out["disp_map"], out["raw"], w)
         # logdet_sums (B,2): per-ray sums of the alpha / rgb log-det terms (the entropy scalars are built from them)
@@ -159,7 +160,7 @@ class _RenderTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_rgb, g_disp, g_depth, g_raw, g_ld, g_w):
         eng = ctx.eng
-        rays, z_vals, eps_a, eps_c, fp, ws, trans = ctx.saved_tensors
+        rays, z_vals, eps_a, eps_c, fp, ws, trans, sg = ctx.saved_tensors
         B, N = z_vals.shape
         dev = rays.device
         g_rgb = _f32c(g_rgb, dev) if g_rgb is not None else torch.zeros(B, 3, eng.K, device=dev)
@@ -168,7 +169,8 @@ class _RenderTrainFn(torch.autograd.Function):
         gl = _f32c(g_ld.detach(), dev) if g_ld is not None else torch.zeros(B, 2, device=dev)
         with torch.cuda.device(dev):
             g_fp, g_glob = eng.flow_composite_bwd(fp, z_vals, rays[:, 3:6], 11, eps_a, eps_c, ctx.white_bkgd, g_rgb,
-                                                  g_depth, gl, trans=trans, eps_group_rays=ctx.group_rays)
+                                                  g_depth, gl, trans=trans, eps_group_rays=ctx.group_rays,
+                                                  seg_sums=sg if sg.numel() else None)
             grads = eng.network_bwd(g_fp, B, N, ws)
         gg = g_glob.sum(0)
         grads[0], grads[1] = gg[0:1], gg[1:2]

@@ -58,6 +58,7 @@ extern "C" int cfn_create(const CfnConfig* cfg, CfnHandle** out) {
   h->packed = false;
   h->tc = nullptr;
   h->tc_dirty = 0;
+  h->zero_lo = h->zero_hi = nullptr;
   h->deterministic = 0;
   h->det_scratch = nullptr;
   h->det_floats = 0;
@@ -307,7 +308,10 @@ extern "C" int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, co
                                       const float* rays_d, int rays_d_stride, const float* eps_alpha,
                                       const float* eps_rgb, int64_t eps_group_rays, int64_t B, int N, int white_bkgd,
                                       float* rgb_map, float* disp_map, float* depth_map, float* raw, float* weights,
-                                      float* logdet_sums, float* kstats, float* trans, void* stream) {
+                                      float* logdet_sums, float* kstats, float* trans, float* seg_sums, int n_segments,
+                                      void* stream) {
+  CFN_CHECK_ARG(!seg_sums || (logdet_sums && n_segments >= 1 && n_segments <= 64 && N % n_segments == 0),
+                "cfn_flow_composite_fwd: seg_sums needs the training flavour and N %% n_segments == 0");
   CFN_CHECK_ARG(eps_group_rays >= 0, "cfn_flow_composite_fwd: negative eps_group_rays");
   CFN_CHECK_ARG(!trans || logdet_sums, "cfn_flow_composite_fwd: trans is written by the training flavour only (pass logdet_sums)");
   CFN_CHECK_ARG(h && B >= 0 && (B == 0 || (flow_params && z_vals && rays_d && eps_alpha && eps_rgb && rgb_map && disp_map && depth_map)),
@@ -321,14 +325,15 @@ extern "C" int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, co
   const int fast = (h->cfg.precision != CFN_PREC_FP32) ? 1 : 0;
   return launch_flow_composite_fwd(fast, h->cfg.F, h->cfg.K, h->globals, flow_params, z_vals, rays_d, rays_d_stride,
                                    eps_alpha, eps_rgb, eps_group_rays, B, N, white_bkgd, rgb_map, disp_map, depth_map, raw,
-                                   weights, logdet_sums, kstats, trans, (cudaStream_t)stream);
+                                   weights, logdet_sums, kstats, trans, seg_sums, n_segments, (cudaStream_t)stream);
 }
 
 static int flow_composite_bwd_impl(CfnHandle* h, const float* flow_params, const float* z_vals, const float* rays_d,
                                   int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t eps_group_rays,
                                   int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
                                   float g_logdet_alpha, float g_logdet_rgb, const float* g_logdet_dev, float* trans,
-                                  int trans_valid, float* g_flow_params, float* g_globals_partial, void* stream) {
+                                  int trans_valid, const float* seg_sums, int n_segments, float* g_flow_params,
+                                  float* g_globals_partial, void* stream) {
   CFN_CHECK_ARG(h && flow_params && z_vals && rays_d && eps_alpha && eps_rgb && g_rgb_map && g_flow_params &&
                     g_globals_partial && trans,
                 "cfn_flow_composite_bwd: null argument");
@@ -340,30 +345,30 @@ static int flow_composite_bwd_impl(CfnHandle* h, const float* flow_params, const
   return launch_flow_composite_bwd(h->cfg.precision != CFN_PREC_FP32 ? 1 : 0, h->cfg.F, h->cfg.K, h->globals, flow_params,
                                    z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, eps_group_rays, B, N, white_bkgd,
                                    g_rgb_map, g_depth_map, g_logdet_alpha, g_logdet_rgb, g_logdet_dev, trans, trans_valid,
-                                   g_flow_params, g_globals_partial, (cudaStream_t)stream);
+                                   seg_sums, n_segments, g_flow_params, g_globals_partial, (cudaStream_t)stream);
 }
 
 extern "C" int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, const float* z_vals,
                                       const float* rays_d, int rays_d_stride, const float* eps_alpha,
                                       const float* eps_rgb, int64_t eps_group_rays, int64_t B, int N, int white_bkgd,
                                       const float* g_rgb_map, const float* g_depth_map, float g_logdet_alpha,
-                                      float g_logdet_rgb, float* trans, int trans_valid, float* g_flow_params,
-                                      float* g_globals_partial, void* stream) {
+                                      float g_logdet_rgb, float* trans, int trans_valid, const float* seg_sums,
+                                      int n_segments, float* g_flow_params, float* g_globals_partial, void* stream) {
   return flow_composite_bwd_impl(h, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, eps_group_rays, B, N,
                                  white_bkgd, g_rgb_map, g_depth_map, g_logdet_alpha, g_logdet_rgb, nullptr, trans,
-                                 trans_valid, g_flow_params, g_globals_partial, stream);
+                                 trans_valid, seg_sums, n_segments, g_flow_params, g_globals_partial, stream);
 }
 
 extern "C" int cfn_flow_composite_bwd_dev(CfnHandle* h, const float* flow_params, const float* z_vals,
                                           const float* rays_d, int rays_d_stride, const float* eps_alpha,
                                           const float* eps_rgb, int64_t eps_group_rays, int64_t B, int N, int white_bkgd,
                                           const float* g_rgb_map, const float* g_depth_map, const float* g_logdet_dev,
-                                          float* trans, int trans_valid, float* g_flow_params, float* g_globals_partial,
-                                          void* stream) {
+                                          float* trans, int trans_valid, const float* seg_sums, int n_segments,
+                                          float* g_flow_params, float* g_globals_partial, void* stream) {
   CFN_CHECK_ARG(g_logdet_dev != nullptr, "cfn_flow_composite_bwd_dev: g_logdet_dev is null");
   return flow_composite_bwd_impl(h, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, eps_group_rays, B, N,
-                                 white_bkgd, g_rgb_map, g_depth_map, 0.f, 0.f, g_logdet_dev, trans, trans_valid,
-                                 g_flow_params, g_globals_partial, stream);
+                                 white_bkgd, g_rgb_map, g_depth_map, 0.f, 0.f, g_logdet_dev, trans, trans_valid, seg_sums,
+                                 n_segments, g_flow_params, g_globals_partial, stream);
 }
 
 extern "C" int cfn_raw2outputs_f32(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,

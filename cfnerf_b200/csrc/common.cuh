@@ -111,12 +111,13 @@ int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
                               int64_t eps_group_rays, int64_t B, int N, int white_bkgd, float* rgb_map, float* disp_map,
                               float* depth_map, float* raw, float* weights, float* logdet_sums, float* kstats, float* trans,
-                              cudaStream_t s);
+                              float* seg_sums, int n_seg, cudaStream_t s);
 int launch_flow_composite_bwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
                               int64_t eps_group_rays, int64_t B, int N, int white_bkgd, const float* g_rgb_map,
                               const float* g_depth_map, float g_ld_alpha, float g_ld_rgb, const float* g_ld_dev,
-                              float* trans, int trans_valid, float* g_flow_params, float* g_globals, cudaStream_t s);
+                              float* trans, int trans_valid, const float* seg_sums, int n_seg, float* g_flow_params,
+                              float* g_globals, cudaStream_t s);
 
 // C[m,n] = epi( sum_k A(m,k) * B(k,n) + bias[n] ) with arbitrary element strides (fp32 CUDA-core GEMM).
 enum Epilogue { EPI_NONE = 0, EPI_RELU = 1, EPI_TANH_MASK = 2, EPI_RELU_MASK_MUL = 3 };

@@ -39,14 +39,15 @@ __device__ __forceinline__ void chunk_store(float* dst, int n_floats, int lane, 
 // F <= 8 -> at most 18 float4 per lane.  We instantiate for F<=4 (MAXV=9) and F<=8 (MAXV=18).
 
 template <int MAXV, bool TRAIN, bool FAST, int FT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)   // 16 warps per SM: the kernel is latency / issue bound, occupancy is what it needs
 flow_composite_fwd_kernel(int F_rt, int K, const float* __restrict__ globals, const float* __restrict__ flow_params,
                           const float* __restrict__ z_vals, const float* __restrict__ rays_d, int rays_d_stride,
                           const float* __restrict__ eps_alpha, const float* __restrict__ eps_rgb,
                           int64_t eps_group_rays, int64_t B, int N,
                           int white_bkgd, float* __restrict__ rgb_map, float* __restrict__ disp_map,
                           float* __restrict__ depth_map, float* __restrict__ raw, float* __restrict__ weights,
-                          float* __restrict__ logdet_sums, float* __restrict__ kstats, float* __restrict__ trans) {
+                          float* __restrict__ logdet_sums, float* __restrict__ kstats, float* __restrict__ trans,
+                          float* __restrict__ seg_sums, int n_seg) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // FT > 0: the number of flows is a compile-time constant (the shipped recipe, F = 4): a point's 18F scalars are
@@ -99,6 +100,12 @@ flow_composite_fwd_kernel(int F_rt, int K, const float* __restrict__ globals, co
     const float zc00 = e0 * c_std0 + c_mean0, zc01 = e1 * c_std1 + c_mean1, zc02 = e2 * c_std2 + c_mean2;
 
     float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, depth = 0.f, acc = 0.f;
+    // TRAIN, n_seg > 1: sums of w*c (3), w*z, w over each of the n_seg equal sample ranges of the ray, written as
+    // seg_sums[b][seg][5][K].  The backward splits a ray into n_seg independent warps: the one that owns range s starts
+    // its suffix-sum recurrence from the (cancellation-free: all terms are non-negative) sums of the later ranges.
+    float sg0 = 0.f, sg1 = 0.f, sg2 = 0.f, sg3 = 0.f, sg4 = 0.f;
+    const int seg_len = (TRAIN && seg_sums && n_seg > 1) ? N / n_seg : 0;
+    int seg_left = seg_len, seg_idx = 0;
 
     float4 stage[MAXV];
     {
@@ -170,11 +177,23 @@ flow_composite_fwd_kernel(int F_rt, int K, const float* __restrict__ globals, co
         const float w = alpha * T;
         if (TRAIN && trans && active) trans[(b * N + n) * K + k] = T;   // transmittance in front of sample n (K4 reads it)
         T = T * ((1.0f - alpha) + 1e-10f);
-        cr += w * sigmoid_<FAST>(z0);
-        cg += w * sigmoid_<FAST>(z1);
-        cb += w * sigmoid_<FAST>(z2);
-        depth += w * sz[n];
+        const float wc0 = w * sigmoid_<FAST>(z0), wc1 = w * sigmoid_<FAST>(z1), wc2 = w * sigmoid_<FAST>(z2), wz = w * sz[n];
+        cr += wc0;
+        cg += wc1;
+        cb += wc2;
+        depth += wz;
         acc += w;
+        if (TRAIN && seg_len) {
+          sg0 += wc0; sg1 += wc1; sg2 += wc2; sg3 += wz; sg4 += w;
+          if (--seg_left == 0) {
+            if (active) {
+              float* o = seg_sums + ((b * n_seg + seg_idx) * 5) * K + k;
+              o[0] = sg0; o[K] = sg1; o[2 * K] = sg2; o[3 * K] = sg3; o[4 * K] = sg4;
+            }
+            sg0 = sg1 = sg2 = sg3 = sg4 = 0.f;
+            seg_left = seg_len; ++seg_idx;
+          }
+        }
         if (active) {
           if (raw) reinterpret_cast<float4*>(raw)[(b * N + n) * K + k] = make_float4(z0, z1, z2, za);
           if (weights) weights[(b * N + n) * K + k] = w;
@@ -252,8 +271,9 @@ int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
                               int64_t eps_group_rays, int64_t B, int N, int white_bkgd, float* rgb_map, float* disp_map,
                               float* depth_map, float* raw, float* weights, float* logdet_sums, float* kstats, float* trans,
-                              cudaStream_t s) {
+                              float* seg_sums, int n_seg, cudaStream_t s) {
   if (B == 0) return CFN_OK;
+  CFN_CHECK_ARG(!seg_sums || (n_seg >= 1 && N % n_seg == 0), "flow_composite: N=%d is not a multiple of n_segments=%d", N, n_seg);
   CFN_CHECK_ARG(F >= 1 && F <= kMaxF, "flow_composite: n_flows=%d unsupported (1..%d)", F, kMaxF);
   CFN_CHECK_ARG(N >= 1 && N <= 2048 && K >= 1, "flow_composite: unsupported N=%d K=%d (need 1 <= N <= 2048)", N, K);
   size_t smem = fwd_smem_bytes(F, N);
@@ -266,7 +286,7 @@ int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals,
     if (smem > 48 * 1024) CFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, 128, smem, s>>>(F, K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb,   \
                                  eps_group_rays, B, N, white_bkgd, rgb_map, disp_map, depth_map, raw, weights,    \
-                                 logdet_sums, kstats, trans);                                                     \
+                                 logdet_sums, kstats, trans, seg_sums, n_seg);                                    \
   } while (0)
   if (F <= 4) {
     if (train) CFN_FWD_LAUNCH(9, true); else CFN_FWD_LAUNCH(9, false);
@@ -367,6 +387,7 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
                           int64_t B, int N, int white_bkgd, const float* __restrict__ g_rgb_map,
                           const float* __restrict__ g_depth_map, float gl_a_host, float gl_c_host,
                           const float* __restrict__ g_ld_dev, const float* __restrict__ trans,
+                          const float* __restrict__ seg_sums, int n_seg,
                           float* __restrict__ g_flow_params, float* __restrict__ g_globals_partial) {
   constexpr int F = FT;
   constexpr int PP = 18 * F;
@@ -381,8 +402,14 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
   float* sP = sz + zd;                  // parameters of the current block [PB][PP]
   float* sO = sP + PB * PP;             // reduced gradient rows of the block [PB][PP]
   float* sG = sO + PB * PP;             // reduction scratch [2][16][GLD]
-  const int64_t b = (int64_t)blockIdx.x * 4 + warp;
+  // one warp per (ray, sample range): n_seg > 1 splits every ray into n_seg independent back-to-front walks (small
+  // batches — the reference trains on 512 rays — would otherwise leave most warp slots of the GPU empty)
+  const int64_t wid = (int64_t)blockIdx.x * 4 + warp;
+  const int64_t b = wid / n_seg;
+  const int seg = (int)(wid % n_seg);
   if (b >= B) return;
+  const int seg_len = N / n_seg;
+  const int n_lo = seg * seg_len, n_hi = n_lo + seg_len;
   // gradient seeds of the two log-det sums of THIS ray: by value (host scalars), or read from the device (B,2) so that
   // the host never waits for the loss graph and rays of different network calls / loss terms can carry different seeds
   const float gl_a = g_ld_dev ? g_ld_dev[b * 2 + 0] : gl_a_host;
@@ -406,7 +433,7 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
   float* grow = g_flow_params + (b * N) * PP;
   const float* trow = trans + (b * N) * K;
   const int KG = (K + 31) / 32;
-  const int n_blocks = (N + PB - 1) / PB;
+  const int n_blocks = (seg_len + PB - 1) / PB;             // blocks of this warp's range [n_lo, n_hi)
   float gg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d/d[a_mean, a_std, c_mean(3), c_std(3)]
   int rbuf = 0;
 
@@ -431,19 +458,25 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
     const float gA = white_bkgd ? -(gC[0] + gC[1] + gC[2]) : 0.f;
     const float gla = active ? gl_a : 0.f, glc = active ? gl_c : 0.f;
 
+    // suffix sum S = sum over the samples behind this range of v_m w_m: linear in the forward's range sums
     float S = 0.f;
+    if (active)
+      for (int s2 = seg + 1; s2 < n_seg; ++s2) {
+        const float* o = seg_sums + ((b * n_seg + s2) * 5) * K + k;
+        S += gC[0] * o[0] + gC[1] * o[K] + gC[2] * o[2 * K] + gD * o[3 * K] + gA * o[4 * K];
+      }
     // register prefetch of the next block's parameters (and of the next point's transmittance) while the current one is
     // processed
     float pre[NPRE];
     {
-      const int c = n_blocks - 1, n0 = c * PB, cnt = (N - n0) * PP;
+      const int c = n_blocks - 1, n0 = n_lo + c * PB, cnt = (n_hi - n0) * PP;
 #pragma unroll
       for (int u = 0; u < NPRE; ++u) pre[u] = (lane + 32 * u < cnt) ? __ldg(prow + (int64_t)n0 * PP + lane + 32 * u) : 0.f;
     }
-    float t_next = active ? __ldg(trow + (int64_t)(N - 1) * K + k) : 0.f;
+    float t_next = active ? __ldg(trow + (int64_t)(n_hi - 1) * K + k) : 0.f;
     for (int c = n_blocks - 1; c >= 0; --c) {
-      const int n0 = c * PB;
-      const int npts = min(PB, N - n0);
+      const int n0 = n_lo + c * PB;
+      const int npts = min(PB, n_hi - n0);
 #pragma unroll
       for (int u = 0; u < NPRE; ++u) if (lane + 32 * u < PB * PP) sP[lane + 32 * u] = pre[u];
       __syncwarp();
@@ -459,7 +492,7 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
         {
           const int n = n0 + i;
           const float T = t_next;
-          if (n > 0) t_next = active ? __ldg(trow + (int64_t)(n - 1) * K + k) : 0.f;
+          if (n > n_lo) t_next = active ? __ldg(trow + (int64_t)(n - 1) * K + k) : 0.f;
           const float* Pn = sP + i * PP;
           float* On = sO + i * PP;
           // recompute alpha stack with intermediates
@@ -592,7 +625,7 @@ flow_composite_bwd_kernel(int K, const float* __restrict__ globals, const float*
     for (int o = 16; o > 0; o >>= 1) gg[j] += __shfl_xor_sync(0xffffffffu, gg[j], o);
   if (lane == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g_globals_partial[b * 8 + j] = gg[j];
+    for (int j = 0; j < 8; ++j) g_globals_partial[wid * 8 + j] = gg[j];
   }
 }
 
@@ -600,15 +633,17 @@ int launch_flow_composite_bwd(int fast_math, int F, int K, const float* globals,
                               const float* rays_d, int rays_d_stride, const float* eps_alpha, const float* eps_rgb,
                               int64_t eps_group_rays, int64_t B, int N, int white_bkgd, const float* g_rgb_map,
                               const float* g_depth_map, float g_ld_alpha, float g_ld_rgb, const float* g_ld_dev,
-                              float* trans, int trans_valid, float* g_flow_params, float* g_globals_partial,
-                              cudaStream_t s) {
+                              float* trans, int trans_valid, const float* seg_sums, int n_seg, float* g_flow_params,
+                              float* g_globals_partial, cudaStream_t s) {
   if (B == 0) return CFN_OK;
+  if (!seg_sums || n_seg < 1) n_seg = 1;
+  CFN_CHECK_ARG(N % n_seg == 0 && (N / n_seg) >= 1, "flow_composite_bwd: N=%d is not a multiple of n_segments=%d", N, n_seg);
   CFN_CHECK_ARG(F >= 1 && F <= kMaxF, "flow_composite_bwd: n_flows=%d unsupported (1..%d)", F, kMaxF);
   CFN_CHECK_ARG(N >= 2 && N <= 4096 && K >= 1, "flow_composite_bwd: unsupported N=%d (2..4096) K=%d", N, K);
   CFN_CHECK_ARG(trans != nullptr, "flow_composite_bwd: the transmittance buffer (B,N,K) is required");
   const int PP = 18 * F;
   size_t smem = (size_t)4 * (((2 * N + 3) & ~3) + 2 * kBwdPB * PP + 2 * 16 * kBwdGLD) * sizeof(float);
-  unsigned grid = (unsigned)((B + 3) / 4);
+  unsigned grid = (unsigned)((B * n_seg + 3) / 4);
   unsigned grid_pre = (unsigned)((B * 32 + 255) / 256);
 #define CFN_BWD_CASE(FF)                                                                                             \
   case FF: {                                                                                                         \
@@ -621,7 +656,7 @@ int launch_flow_composite_bwd(int fast_math, int F, int K, const float* globals,
     if (smem > 48 * 1024) CFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, 128, smem, s>>>(K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb,         \
                                  eps_group_rays, B, N, white_bkgd, g_rgb_map, g_depth_map, g_ld_alpha, g_ld_rgb,     \
-                                 g_ld_dev, trans, g_flow_params, g_globals_partial);                                 \
+                                 g_ld_dev, trans, seg_sums, n_seg, g_flow_params, g_globals_partial);                \
   } break;
   switch (F) {
     CFN_BWD_CASE(1) CFN_BWD_CASE(2) CFN_BWD_CASE(3) CFN_BWD_CASE(4) CFN_BWD_CASE(5) CFN_BWD_CASE(6) CFN_BWD_CASE(7)

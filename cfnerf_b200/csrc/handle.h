@@ -63,6 +63,9 @@ struct CfnHandle {
   std::vector<int64_t> wg_offset;   // in 4-byte slots
   float* amA_g; float* amC_g;   // operand copies of amA / amC (tf32-rounded when gemm_tc, else aliases)
 
+  // transient, set by chain_network_bwd: the gradient range that one memset already zeroed (flat gradient buckets)
+  const float* zero_lo; const float* zero_hi;
+
   // opt-in deterministic weight gradients (cfn_set_deterministic): scratch for the split-K slabs of one wgrad
   int deterministic;
   float* det_scratch; int64_t det_floats;

@@ -414,7 +414,9 @@ static int colsum(const float* g, int64_t ld, int64_t M, int N, float* out, cuda
 // db (optional): the bias gradient = column sums of G, fused into the tensor-core GEMM when possible
 static int wgrad(const CfnHandle* h, const float* G, int64_t ldg, int out_f, const float* X, int64_t ldx, int in_f, int64_t M,
                  float* dW, float* db, cudaStream_t s) {
-  if (!h->deterministic) CFN_CUDA(cudaMemsetAsync(dW, 0, (size_t)out_f * in_f * sizeof(float), s));
+  // gradient tensors that sit in one flat buffer were zeroed by a single memset at the start of chain_network_bwd
+  auto prezeroed = [&](const float* q) { return h->zero_lo && q >= h->zero_lo && q < h->zero_hi; };
+  if (!h->deterministic && !prezeroed(dW)) CFN_CUDA(cudaMemsetAsync(dW, 0, (size_t)out_f * in_f * sizeof(float), s));
   GemmArgs g{};
   g.A = G; g.a_rs = 1; g.a_cs = ldg;        // A(m=o, k=pt) = G[pt*ldg + o]
   g.B = X; g.b_rs = ldx; g.b_cs = 1;        // B(k=pt, n=i) = X[pt*ldx + i]
@@ -442,7 +444,7 @@ static int wgrad(const CfnHandle* h, const float* G, int64_t ldg, int out_f, con
   if (h->deterministic) { g.partials = h->det_scratch; g.partials_floats = h->det_floats; }
   if (db) {
     if (h->gemm_tc && tgemm_can_rowsum(g)) {
-      if (!h->deterministic) CFN_CUDA(cudaMemsetAsync(db, 0, (size_t)out_f * sizeof(float), s));
+      if (!h->deterministic && !prezeroed(db)) CFN_CUDA(cudaMemsetAsync(db, 0, (size_t)out_f * sizeof(float), s));
       g.rowsum = db;
     } else if (h->chain_bf16) {
       set_error("bf16 chain: the bias gradient could not be fused into the wgrad (out %d in %d)", out_f, in_f);
@@ -550,10 +552,25 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
     return bits ? reinterpret_cast<const uint32_t*>(ws + L.MB) + (int64_t)layer * M * L.bw : nullptr;
   };
 
+  // Gradient tensors laid out back to back in slot order (cfnerf_b200.dist.FusedTrainStep's flat bucket): ONE memset
+  // replaces the ~40 per-tensor ones of the split-K wgrads (each a graph node / launch of its own at 512 rays per step)
+  h->zero_lo = h->zero_hi = nullptr;
+  {
+    bool flat = true;
+    for (size_t i = 5; i < h->slots.size(); ++i)
+      flat = flat && (grads[i] == grads[4] + (h->slots[i].offset - h->slots[4].offset));
+    if (flat) {
+      const int64_t n = h->n_floats - h->slots[4].offset;
+      CFN_CUDA(cudaMemsetAsync(grads[4], 0, (size_t)n * sizeof(float), s));
+      h->zero_lo = grads[4];
+      h->zero_hi = grads[4] + n;
+    }
+  }
   // zero every flow-conditioning gradient: rows the path never reads keep an exact 0
-  for (int base : {h->s_frgb, h->s_falpha})
-    for (int j = 0; j < 8; ++j)
-      CFN_CUDA(cudaMemsetAsync(grads[base + j], 0, h->slots[base + j].numel * sizeof(float), s));
+  if (!h->zero_lo)
+    for (int base : {h->s_frgb, h->s_falpha})
+      for (int j = 0; j < 8; ++j)
+        CFN_CUDA(cudaMemsetAsync(grads[base + j], 0, h->slots[base + j].numel * sizeof(float), s));
 
   // gradient pointers of every slot, handed to the scatter kernels by value
   GradPtrs table;

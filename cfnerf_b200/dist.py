@@ -203,10 +203,12 @@ class FusedTrainStep:
               "cfn_trainer_loss_f32")
         g_fp, g_glob = eng.flow_composite_bwd(fp, z, rays[:, 3:6], 11, st["eps_a"], st["eps_c"], self.white_bkgd,
                                               st["g_rgb"], st["g_depth"] if Bd else None, st["g_ld"],
-                                              trans=out["trans"], eps_group_rays=st["group_rays"])
+                                              trans=out["trans"], eps_group_rays=st["group_rays"],
+                                              seg_sums=out["seg_sums"])
         eng.network_bwd(g_fp, B, N, ws, grads=self.grads)
         # parameters 0..3 (alpha_mean, alpha_std, rgb_mean, rgb_std) sit first in the flat gradient buffer
-        check(eng.lib.cfn_globals_grad_f32(eng.h, _ptr(g_glob), B, float(self.beta1), _ptr(self.flat_grad), _stream()),
+        check(eng.lib.cfn_globals_grad_f32(eng.h, _ptr(g_glob), g_glob.shape[0], float(self.beta1), _ptr(self.flat_grad),
+                                           _stream()),
               "cfn_globals_grad_f32")
         st["out"] = out
 

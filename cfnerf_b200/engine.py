@@ -32,6 +32,13 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def backward_segments(B: int, N: int) -> int:
+    """Sample ranges per ray for the flow/compositing backward (one warp each).  A B200 holds 148 SMs x 16 warps of that
+    kernel: below ~16k rays the ray count alone leaves slots empty or a ragged last wave (512 rays, the reference's batch:
+    a fifth of the slots), so every ray is walked as 4 independent ranges."""
+    return 4 if (B < 16384 and N % 16 == 0) else 1
+
+
 _WEIGHTS_EPOCH = 0
 
 
@@ -130,7 +137,9 @@ class Engine:
     def flow_composite(self, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, white_bkgd: bool,
                        want_raw=False, want_weights=False, train=False, want_kstats=False, eps_group_rays: int = 0,
                        want_trans=False):
-        """eps_alpha (K) / eps_rgb (K,3), or (G,K) / (G,K,3) with eps_group_rays = rays per latent-draw group."""
+        """eps_alpha (K) / eps_rgb (K,3), or (G,K) / (G,K,3) with eps_group_rays = rays per latent-draw group.
+        want_trans (training): also returns what the backward reads — `trans` (B,N,K) and, for batches small enough to
+        leave warp slots empty, `seg_sums` (B,S,5,K) that let it walk S sample ranges of a ray in parallel."""
         self.pack()
         B, N = z_vals.shape
         K, dev = self.K, self.device
@@ -143,26 +152,31 @@ class Engine:
         ld = torch.empty(B, 2, **f32) if train else None
         ks = torch.empty(B, 8, **f32) if want_kstats else None
         tr = torch.empty(B, N, K, **f32) if (train and want_trans) else None
+        S = backward_segments(B, N) if tr is not None else 1
+        sg = torch.empty(B, S, 5, K, **f32) if S > 1 else None
         check(self.lib.cfn_flow_composite_fwd(self.h, _ptr(flow_params), _ptr(z_vals), _ptr(rays_d), rays_d_stride,
                                               _ptr(eps_alpha), _ptr(eps_rgb), int(eps_group_rays), B, N, int(white_bkgd),
                                               _ptr(rgb), _ptr(disp), _ptr(depth), _ptr(raw), _ptr(w), _ptr(ld), _ptr(ks),
-                                              _ptr(tr), _stream()), "cfn_flow_composite_fwd")
-        return dict(rgb_map=rgb, disp_map=disp, depth_map=depth, raw=raw, weights=w, logdet_sums=ld, kstats=ks, trans=tr)
+                                              _ptr(tr), _ptr(sg), S, _stream()), "cfn_flow_composite_fwd")
+        return dict(rgb_map=rgb, disp_map=disp, depth_map=depth, raw=raw, weights=w, logdet_sums=ld, kstats=ks, trans=tr,
+                    seg_sums=sg)
 
     def flow_composite_bwd(self, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, white_bkgd,
-                           g_rgb, g_depth, g_ld, trans=None, eps_group_rays: int = 0):
+                           g_rgb, g_depth, g_ld, trans=None, eps_group_rays: int = 0, seg_sums=None):
         """g_ld: device tensor (B,2) = d loss / d (per-ray sums of the alpha / rgb log-dets); stays on the device (no
-        host sync).  trans: the (B,N,K) transmittance the training forward wrote (None: recomputed into scratch)."""
+        host sync).  trans / seg_sums: what the training forward wrote (trans None: recomputed into scratch).
+        -> g_flow_params (B*N,18F), g_globals_partial (B*S,8) (sum the rows)."""
         B, N = z_vals.shape
+        S = seg_sums.shape[1] if seg_sums is not None else 1
         g_fp = torch.empty_like(flow_params)
-        g_glob = torch.empty(B, 8, dtype=torch.float32, device=self.device)
+        g_glob = torch.empty(B * S, 8, dtype=torch.float32, device=self.device)
         valid = trans is not None
         if trans is None:
             trans = torch.empty(B, N, self.K, dtype=torch.float32, device=self.device)
         check(self.lib.cfn_flow_composite_bwd_dev(self.h, _ptr(flow_params), _ptr(z_vals), _ptr(rays_d), rays_d_stride,
                                                   _ptr(eps_alpha), _ptr(eps_rgb), int(eps_group_rays), B, N,
                                                   int(white_bkgd), _ptr(g_rgb), _ptr(g_depth), _ptr(g_ld), _ptr(trans),
-                                                  int(valid), _ptr(g_fp), _ptr(g_glob), _stream()),
+                                                  int(valid), _ptr(seg_sums), S, _ptr(g_fp), _ptr(g_glob), _stream()),
               "cfn_flow_composite_bwd_dev")
         return g_fp, g_glob
 

@@ -134,24 +134,30 @@ int cfn_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, 
  * (models.py:263,278) for the entropy loss (requesting them selects the training flavour); optional kstats (B,8):
  * mean_k rgb (3), "uncertainty" std (unbiased std * K/(K-1), main:1034/1130) (3), mean_k depth, mean_k disp; optional
  * trans (B,N,K) (training flavour only): the transmittance in front of every sample, which cfn_flow_composite_bwd
- * reads instead of recomputing it.  Any optional pointer may be NULL. */
+ * reads instead of recomputing it; optional seg_sums (B, n_segments, 5, K) (training flavour only; N must be a multiple
+ * of n_segments): per equal sample range of every ray the sums of w*rgb (3), w*z and w — they let the backward walk the
+ * n_segments ranges of a ray in independent warps.  Any optional pointer may be NULL. */
 int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, const float* z_vals, const float* rays_d,
                            int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t eps_group_rays,
                            int64_t B, int N, int white_bkgd, float* rgb_map, float* disp_map, float* depth_map,
-                           float* raw, float* weights, float* logdet_sums, float* kstats, float* trans, void* stream);
+                           float* raw, float* weights, float* logdet_sums, float* kstats, float* trans, float* seg_sums,
+                           int n_segments, void* stream);
 
 /* Backward.  g_rgb_map (B,3,K) and g_depth_map (B,K) (NULL = zero) are upstream
  * gradients; g_logdet_alpha / g_logdet_rgb are d loss / d(sum of log-dets) (scalars, e.g. -beta1/(B*N*K)).
  * trans (B,N,K) is REQUIRED device memory: with trans_valid != 0 it holds what cfn_flow_composite_fwd wrote for the
  * same inputs; with trans_valid == 0 it is scratch that this call fills first (an alpha-stack-only pre-pass).
- * Writes g_flow_params (B*N,18F) and g_globals_partial (B,8): per-ray
+ * seg_sums / n_segments: what cfn_flow_composite_fwd wrote for the same inputs (NULL / 1: one warp walks the whole ray;
+ * n_segments > 1 gives small batches n_segments times the parallelism — the reference trains on 512 rays per step).
+ * Writes g_flow_params (B*N,18F) and g_globals_partial (B*n_segments,8): per ray and range the
  * partial sums of d/d[alpha_mean, alpha_std, rgb_mean(3), rgb_std(3)] through z0 = eps*std+mean only (the caller sums
- * over rays; kept per ray so the result is deterministic, and per eps group when eps_group_rays > 0). */
+ * the rows; kept apart so the result is deterministic). */
 int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, const float* z_vals, const float* rays_d,
                            int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t eps_group_rays,
                            int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
                            float g_logdet_alpha, float g_logdet_rgb, float* trans, int trans_valid,
-                           float* g_flow_params, float* g_globals_partial, void* stream);
+                           const float* seg_sums, int n_segments, float* g_flow_params, float* g_globals_partial,
+                           void* stream);
 /* Same, with PER-RAY log-det gradient seeds read from DEVICE memory: g_logdet_dev (B,2), [b][0] = alpha, [b][1] = rgb.
  * The host does not have to wait for the loss graph before it issues the backward (no device-to-host sync per step),
  * and rays of different network calls / loss terms can carry different seeds (the depth rays of the shipped recipe
@@ -159,8 +165,8 @@ int cfn_flow_composite_bwd(CfnHandle* h, const float* flow_params, const float* 
 int cfn_flow_composite_bwd_dev(CfnHandle* h, const float* flow_params, const float* z_vals, const float* rays_d,
                                int rays_d_stride, const float* eps_alpha, const float* eps_rgb, int64_t eps_group_rays,
                                int64_t B, int N, int white_bkgd, const float* g_rgb_map, const float* g_depth_map,
-                               const float* g_logdet_dev, float* trans, int trans_valid, float* g_flow_params,
-                               float* g_globals_partial, void* stream);
+                               const float* g_logdet_dev, float* trans, int trans_valid, const float* seg_sums,
+                               int n_segments, float* g_flow_params, float* g_globals_partial, void* stream);
 
 /* ---- A8 stand-alone: raw2outputs (run_nerf_uncertainty_NF.py:411-454) ------------------------ */
 int cfn_raw2outputs_f32(const float* raw, const float* z_vals, const float* rays_d, int rays_d_stride,

@@ -102,3 +102,58 @@ def test_tf32_gemm_layout_contract_is_checked_on_the_host(lib):
     assert call(1024, 64, 1, 2048, 32, 1, epi=1) == -1   # ReLU epilogue is only instantiated for K-major B
     assert call(1024, 64, 1, 2048, 1, 64, split=4) == -1  # split-K (wgrad) needs M-major A and N-major B
     assert lib.cfn_gemm_f32(2, None, 0, 0, None, 0, 0, None, 0, None, None, 0, 4, 4, 4, 0, 0, 1, 0, None) == -1   # engine id
+
+
+def test_latent_groups_follow_the_reference_batchify():
+    """One latent draw per `batchify` call of netchunk points (main:47-64, models.py:233-251)."""
+    from cfnerf_b200.api import latent_groups
+    assert latent_groups(512, 128, 65536) == (0, 1)              # the shipped N_rand: exactly one call
+    assert latent_groups(640, 128, 65536) == (512, 2)            # + 128 depth rays: a second call with its own noise
+    assert latent_groups(4096, 128, 65536) == (512, 8)
+    assert latent_groups(12, 128, 8 * 128) == (8, 2)
+    assert latent_groups(4096, 192, 65536) == (0, 1)             # 192 does not divide netchunk: treated as one call
+    # the oracle makes the same cut
+    cfg = O.CfnConfig(W=64, D=4, K=4, h_alpha=16, h_rgb=16)
+    p = O.make_params(cfg, 0, "lively")
+    g = torch.Generator().manual_seed(0)
+    ea, er = torch.randn(2, cfg.K, 1, generator=g), torch.randn(2, cfg.K, 3, generator=g)
+    out = O.render_rays(p, cfg, O.synthetic_rays(12, 1), ea, er, True, t_rand=torch.rand(12, 128, generator=g),
+                        faithful=False, netchunk=8 * 128)
+    assert [n for _, n in out["entropy_calls"]] == [8 * 128, 4 * 128]
+
+
+def test_backward_segments_and_defaults():
+    from cfnerf_b200 import api
+    from cfnerf_b200.engine import backward_segments
+    assert backward_segments(512, 128) == 4 and backward_segments(4096, 128) == 4
+    assert backward_segments(32768, 128) == 1 and backward_segments(512, 100) == 1
+    old = (api.DEFAULT_PRECISION, api.DEFAULT_TRAIN_PRECISION, api.DEFAULT_NETCHUNK)
+    try:
+        api.configure(precision="tf32", netchunk=1024)
+        assert api.DEFAULT_PRECISION == "tf32" and api.DEFAULT_NETCHUNK == 1024 and api.DEFAULT_TRAIN_PRECISION == old[1]
+    finally:
+        api.configure(*old)
+    assert (api.DEFAULT_PRECISION, api.DEFAULT_TRAIN_PRECISION, api.DEFAULT_NETCHUNK) == old
+
+
+def test_bench_workloads_and_flop_accounting():
+    """bench.py's config table: the canonical network is 4 708 864 FLOP per point; the three workloads have
+    the shapes BASELINE.json names; the bench renders in a precision that passes every parity fixture."""
+    import bench
+    assert bench.flop_per_point(O.CfnConfig()) == 4708864
+    assert bench.flop_per_point(O.CfnConfig(W=256, K=64, h_alpha=32)) == 1228544
+    assert bench.RENDER_PRECISION in ("fp16", "tf32", "fp32")
+    assert bench.image_rays_host("africa", 0).shape == (512 * 512, 11)
+    r = bench.image_rays_host("fern", 0)
+    assert r.shape == (1008 * 756, 11) and float(r[:, 6].max()) == 0.0 and float(r[:, 7].min()) == 1.0   # NDC near / far
+    assert abs(float(r[0, 2]) + 1.0) < 1e-5                                                            # origins on the near plane
+    p = bench.view_pose("lego", 50)
+    assert abs(float(p[:, 3].norm()) - 4.0) < 1e-4                                                     # radius of pose_spherical
+
+
+def test_oracle_ref_staging_is_byte_identical():
+    """oracle/_ref (git-ignored) is a byte-for-byte copy of the reference's *.py files when it exists."""
+    from oracle import build_ref
+    if not os.path.isfile(build_ref.MANIFEST):
+        pytest.skip("oracle/_ref not staged")
+    assert build_ref.check()
