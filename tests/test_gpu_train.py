@@ -511,3 +511,40 @@ def test_deterministic_mode_gives_bitwise_identical_gradients(cf, dev, precision
     ref = grads[0].double()
     assert (grads[2].double() - ref).norm().item() <= 1e-5 * ref.norm().item()
     assert float(ref.abs().max()) > 0
+
+
+@pytest.mark.parametrize("precision,n_rays,tol", [("fp32", 1024, 2e-5), ("bf16", 4096, 2e-3)])
+def test_global_batch_gradient_equals_mean_of_shard_gradients(cf, dev, precision, n_rays, tol):
+    """Data parallelism on one GPU (N-rank training == 1-rank global-batch training): the gradient of the
+    whole batch — 8 network calls of the reference, one latent draw each — equals the mean of the gradients of its 8
+    equal shards, each computed alone with its own draw, which is what the all-reduce of `FusedTrainStep` averages.  The
+    bf16 case runs at BASELINE configs[2]'s full size (4096-ray global batch, 512 rays per rank)."""
+    from cfnerf_b200 import dist as D
+    cfg = O.CfnConfig()
+    p = O.make_params(cfg, 4, "lively")
+    sa, sr = O.make_latents(cfg, 4)
+    shards = 8
+    per = n_rays // shards
+    rays = O.synthetic_rays(n_rays, 6).to(dev)
+    g = torch.Generator().manual_seed(9)
+    target = torch.rand(n_rays, 3, generator=g).to(dev)
+    t_rand = torch.rand(n_rays, 128, generator=g).to(dev)
+    ea, er = torch.randn(shards, cfg.K, 1, generator=g).to(dev), torch.randn(shards, cfg.K, 3, generator=g).to(dev)
+    net = make_net(cf, cfg, p, sa, sr, dev)
+    full = D.FusedTrainStep(net, lr=0.0, precision=precision, netchunk=per * 128)
+    lf = full.step(rays, target, t_rand=t_rand, eps_alpha=ea, eps_rgb=er)
+    assert full._shapes[(n_rays, 0)]["G"] == shards
+    g_full = full.flat_grad.clone()
+    net2 = make_net(cf, cfg, p, sa, sr, dev)
+    part = D.FusedTrainStep(net2, lr=0.0, precision=precision, netchunk=per * 128)
+    acc, losses = torch.zeros_like(g_full, dtype=torch.float64), []
+    for s in range(shards):
+        sl = slice(s * per, (s + 1) * per)
+        ls = part.step(rays[sl], target[sl], t_rand=t_rand[sl], eps_alpha=ea[s], eps_rgb=er[s])
+        acc += part.flat_grad.double()
+        losses.append(float(ls["loss"]))
+    g_mean = acc / shards
+    rel = (g_full.double() - g_mean).norm().item() / g_mean.norm().item()
+    print(f"global batch vs mean of {shards} shards [{precision}, {n_rays} rays]: relative gradient distance {rel:.2e}")
+    assert rel <= tol, rel
+    assert abs(float(lf["loss"]) - sum(losses) / shards) <= 1e-4 * max(1.0, abs(float(lf["loss"])))
