@@ -29,7 +29,8 @@ namespace cfn {
 constexpr int TC_MAX_STEPS = 20;
 constexpr int TC_MAX_KCH = 12;
 constexpr int TC_CHUNK_BYTES = 128 * 128;   // 128 rows x 64 columns x 2 bytes
-constexpr int TC_SRC_GP = 8, TC_SRC_GD = 9;   // host-side source ids; the device sees smem chunk indices AC / AC+1
+constexpr int TC_SRC_GP = 8, TC_SRC_GD = 9;   // host-side source ids; the device sees ONE shared-memory chunk index AC:
+                                              // gamma(p) and gamma(d) time-share one 16 KB tile (see TcPlanDev::gd_step)
 constexpr int TC_THREADS = 384;             // warps 0..7 encode/epilogue, 8 TMEM alloc, 9 (profiling), 10 TMA, 11 MMA
 constexpr int TC_W_ALLOC = 8, TC_W_WATCH = 9, TC_W_TMA = 10, TC_W_MMA = 11;   // the scheduler favours high warp ids
 constexpr int TC_MAX_STAGES = 8;
@@ -41,9 +42,12 @@ struct TcStep {
   int n_parts;
   int order_rev;  // issue the parts in reverse order (lets a pending drain of TMEM columns 0..63 finish)
   int n_k;        // K chunks
-  // per K chunk, packed: bits 0..7 shared-memory chunk index of the A operand (0..AC-1 activation chunk, AC = gamma(p),
-  // AC+1 = gamma(d)); bits 8..15 first K=16 slice of the 64-column chunk; bits 16..23 number of K=16 instructions; bit 24: bias entry
-  // (its B tile is a [rows][16] SWIZZLE_32B tile instead of a [rows][64] SWIZZLE_128B block)
+  // per K chunk, packed: bits 0..15 offset of the A operand from the activation tile in 16-byte descriptor units
+  // (chunk * 1024 + first K=16 slice * 2); bits 16..19 number of K=16 instructions; bits 20..23 shared-memory chunk
+  // index (0..AC-1 activation chunk, AC = the gamma tile); bit 24: bias entry (its B tile is a [rows][16] SWIZZLE_32B
+  // tile instead of a [rows][64] SWIZZLE_128B block); bit 25: the chunk reads gamma(d), which the epilogue warps write
+  // into the gamma tile after step gd_step (wait for gd_ready); bits 26..29: split-commit steps, second part: after this
+  // K chunk input chunk x (bit 26+x) has been read for the last time and may be overwritten by output chunk x
   unsigned int kinfo[TC_MAX_KCH];
   int bias_off;   // kind 2 only: floats into the table: bias[n_total] then tanh flags[n_total]
   int out_col;    // kind 2: first column in the flow-parameter record
@@ -52,16 +56,18 @@ struct TcStep {
   // Two-part steps whose output overwrites the activation tile in place (kind 0/1, n_parts == 2, natural part order): the
   // accumulator of the FIRST part (columns 0..n_part-1 = output chunks 0..n_part/64-1) is committed on its own and
   // drained while the second part's MMAs run.  Output chunk x may only be stored once the second part has read INPUT
-  // chunk x: afree_pos byte x = the K position of the second part after which that is the case (0 if the step does not
-  // read activation chunk x at all).
+  // chunk x (kinfo bits 26..29).
   int split_commit;
-  unsigned int afree_pos;
 };
 
 struct TcPlanDev {
   int n_steps;
   int act_chunks;
   int stage_out;   // 1: the last step's outputs are staged in shared memory and written to HBM coalesced
+  // ONE gamma tile: columns 0..62 hold gamma(p) and column 63 the constant 1 that multiplies every layer's bias row.
+  // gamma(p) is dead once step gd_step (the skip layer, or layer 0 without a skip) has been accumulated: its epilogue
+  // overwrites columns 0..31 with gamma(d) for the view layer.  The 16 KB this saves is a fifth weight stage.
+  int gd_step;
   TcStep steps[TC_MAX_STEPS];
 };
 
@@ -114,6 +120,27 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t 
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// The four K=16 instructions of one 64-column K chunk in ONE asm block: the descriptors differ only in the start
+// address field (+2 per 32 bytes of K), so the block takes the two low words and builds everything else itself.
+template <int CG>
+__device__ __forceinline__ void umma_k64(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                         uint32_t accumulate) {
+#define CFN_MMA4(GRP)                                                                                         \
+  asm volatile("{\n\t.reg .pred p, t;\n\t.reg .b64 da, db;\n\t.reg .b32 xa, xb;\n\t"                          \
+               "setp.ne.b32 p, %5, 0;\n\tsetp.eq.b32 t, %5, %5;\n\t"                                         \
+               "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"                                          \
+               "tcgen05.mma.cta_group::" GRP ".kind::f16 [%0], da, db, %4, p;\n\t"                            \
+               "add.u32 xa, %1, 2;\n\tadd.u32 xb, %2, 2;\n\tmov.b64 da, {xa, %3};\n\tmov.b64 db, {xb, %3};\n\t" \
+               "tcgen05.mma.cta_group::" GRP ".kind::f16 [%0], da, db, %4, t;\n\t"                            \
+               "add.u32 xa, %1, 4;\n\tadd.u32 xb, %2, 4;\n\tmov.b64 da, {xa, %3};\n\tmov.b64 db, {xb, %3};\n\t" \
+               "tcgen05.mma.cta_group::" GRP ".kind::f16 [%0], da, db, %4, t;\n\t"                            \
+               "add.u32 xa, %1, 6;\n\tadd.u32 xb, %2, 6;\n\tmov.b64 da, {xa, %3};\n\tmov.b64 db, {xb, %3};\n\t" \
+               "tcgen05.mma.cta_group::" GRP ".kind::f16 [%0], da, db, %4, t;\n\t}"                           \
+               :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory")
+  if (CG == 1) CFN_MMA4("1"); else CFN_MMA4("2");
+#undef CFN_MMA4
 }
 
 // two fp32 -> packed 16-bit pair (lo = element c, hi = element c+1), optional fused ReLU
@@ -173,24 +200,29 @@ struct alignas(16) TcBarriers {   // the fp32 bias staging area follows it and i
                         // layer can be a few hundred cycles apart, and a waiter must never miss a phase)
   uint64_t out_done;
   uint64_t in_ready;
+  uint64_t gd_ready;    // gamma(d) of the current tile has been written into the gamma tile
   uint32_t tmem_ptr;
   uint32_t pad;
 };
 
-template <bool FP16, bool ONES>
+// GD == false: gamma(p) of one row -> columns 0..62 of the gamma tile, column 63 = 1 (the bias column).
+// GD == true : gamma(d) of one row -> columns 0..31 (27 values, zero padded); the other columns are left alone.
+template <bool FP16, bool GD>
 __device__ __forceinline__ void encode_row(float x, float y, float z, int L, uint32_t chunk_base, int r) {
-  // [x, sin(2^l x), cos(2^l x)]_l in blocks of 3 (run_nerf_helpers.py:29-51), zero padded to 64 columns
-  float e[64];
+  // [x, sin(2^l x), cos(2^l x)]_l in blocks of 3 (run_nerf_helpers.py:29-51), zero padded
+  constexpr int NC = GD ? 32 : 64;
+  constexpr int NL = GD ? 4 : 10;
+  float e[NC];
 #pragma unroll
-  for (int i = 0; i < 64; ++i) e[i] = 0.f;
+  for (int i = 0; i < NC; ++i) e[i] = 0.f;
   e[0] = x; e[1] = y; e[2] = z;
-  if (ONES) { e[62] = 1.0f; e[63] = 1.0f; }   // multiplies the (hi, lo) split of the fp32 bias in the weight stream
+  if (!GD) e[63] = 1.0f;   // multiplies the bias row of the weight stream
   // sin/cos of 2^l x by the double-angle recurrence from one accurate sincosf per coordinate: the absolute error
   // grows to ~2^9 * 1e-7 = 5e-5 at the top octave, far below the operand rounding of this mode (bf16 2e-3, fp16 5e-4)
   float sx, cx, sy, cy, sz, cz;
   sincosf(x, &sx, &cx); sincosf(y, &sy, &cy); sincosf(z, &sz, &cz);
 #pragma unroll
-  for (int l = 0; l < 10; ++l) {
+  for (int l = 0; l < NL; ++l) {
     if (l < L) {
       e[3 + 6 * l + 0] = sx; e[3 + 6 * l + 1] = sy; e[3 + 6 * l + 2] = sz;
       e[3 + 6 * l + 3] = cx; e[3 + 6 * l + 4] = cy; e[3 + 6 * l + 5] = cz;
@@ -201,7 +233,7 @@ __device__ __forceinline__ void encode_row(float x, float y, float z, int L, uin
     }
   }
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
+  for (int u = 0; u < NC / 8; ++u) {
     uint32_t p0 = pack2<FP16, false>(e[8 * u + 0], e[8 * u + 1]);
     uint32_t p1 = pack2<FP16, false>(e[8 * u + 2], e[8 * u + 3]);
     uint32_t p2 = pack2<FP16, false>(e[8 * u + 4], e[8 * u + 5]);
@@ -223,11 +255,12 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
   const int act_chunks = plan.act_chunks;
   const uint32_t act_base = smem_base;
   const uint32_t gp_base = act_base + act_chunks * TC_CHUNK_BYTES;
-  const uint32_t gd_base = gp_base + TC_CHUNK_BYTES;
-  const uint32_t stage_base = gd_base + TC_CHUNK_BYTES;
+  const uint32_t stage_base = gp_base + TC_CHUNK_BYTES;
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_gen + (stage_base - smem_base) + (size_t)a.stages * a.stage_bytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the shuffle tells the compiler that `warp` is warp-uniform: the role branches below are then uniform branches and
+  // the schedule arithmetic of the producer / issuer warps lives in the uniform datapath (no R2UR in front of every MMA)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int64_t unit0 = blockIdx.x / CG, n_grid_units = gridDim.x / CG;
 
@@ -242,7 +275,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
     mbar_init(bar_local(&bars->acc_full), 1);
     mbar_init(bar_local(&bars->acc_full2), 1);
     mbar_init(bar_local(&bars->out_done), 8 * CG);
-    mbar_init(bar_local(&bars->in_ready), 8 * CG);
+    mbar_init(bar_local(&bars->in_ready), 4 * CG);
+    mbar_init(bar_local(&bars->gd_ready), 4 * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_W_ALLOC) {
@@ -306,114 +340,101 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
     }
   } else if (warp == TC_W_MMA) {
     // ================================= MMA issuer (leader CTA) =================================
-    // The WHOLE warp runs the schedule so that every descriptor is a warp-uniform value (uniform registers, no
-    // per-lane waterfall around the tcgen05 instructions); one elected lane issues.
+    // The WHOLE warp runs the schedule so that every descriptor is a warp-uniform value; one elected lane issues.
+    // Round-2 finding (profiles/README.md, "issuer timeline"): the loop below, not the tensor pipe or the weight ring,
+    // set the pace of the kernel - ~575 cycles of dependent scalar code per ring slot whatever the slot's N.  The hot
+    // path is therefore kept to: one table word per slot (host-packed descriptor offset / flags), one barrier test,
+    // one fence, ONE asm block that issues the slot's four MMAs, one commit.
     if (rank == 0) {
       int stage = 0; uint32_t phase = 0;
       uint32_t act_gen = 0, in_cnt = 0, out_cnt = 0;
-      bool pending_out = false;
+      bool pending_out = false, gd_seen = false;
       Prof prof{(a.prof && blockIdx.x == 0 && lane == 0) ? a.prof + 1 * TC_PROF_N : nullptr, 0};
       // Activation chunks of the current generation become ready in index order (0,1,2,...), and every generation is
       // consumed completely before the next one is produced, so one counter replaces per-chunk bookkeeping:
       // chunks [0, ready_upto) of generation act_gen are known to be written (and their TMEM columns drained).
       int ready_upto = 0;
-      // Split-commit steps hand the first output chunks over while their second part is still running: those hand-overs
-      // (generation act_gen + 1) are observed by probes overlapped with the second part's MMA issue, so that the next
-      // step starts without a chain of ~300-cycle barrier round trips (1.4 k cycles per layer in the first timeline).
-      int next_upto = 0;
       const uint32_t act_bar0 = bar_local(&bars->act_ready[0]);
-      // non-blocking probe (no suspend hint): issued BEFORE the MMAs of the current chunk so that its ~90-cycle
-      // latency overlaps their issue; the blocking wait afterwards is only taken when the probe failed
-      auto probe = [&](uint32_t bar, uint32_t parity) -> bool { return mbar_probe(bar, parity); };
+      // short blocking probe first (wakes within tens of cycles), the sleeping wait only if that window passes
+      auto wait_bar = [&](uint32_t bar, uint32_t parity) { if (!mbar_probe(bar, parity)) mbar_wait(bar, parity); };
       auto wait_act = [&](int j) {
         if (act_gen == 0) return;
         while (ready_upto <= j) {
-          mbar_wait(act_bar0 + 8u * ready_upto, (act_gen - 1u) & 1u);
+          wait_bar(act_bar0 + 8u * ready_upto, (act_gen - 1u) & 1u);
           ++ready_upto;
         }
       };
       const uint32_t full_bar0 = bar_local(&bars->full[0]), empty_bar0 = bar_local(&bars->empty[0]);
-      const uint64_t desc_sw32 = ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61) | ((uint64_t)1 << 16);
-      const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
-      // total number of weight blocks this CTA pair will consume (to know when there is no "next stage" to probe)
-      int64_t blocks_left = 0;
-      {
-        int per_tile = 0;
-        for (int g = 0; g < plan.n_steps; ++g) per_tile += plan.steps[g].n_parts * plan.steps[g].n_k;
-        const int64_t my_tiles = (a.n_units > unit0) ? (a.n_units - unit0 + n_grid_units - 1) / n_grid_units : 0;
-        blocks_left = my_tiles * per_tile;
-      }
-      bool cur_full_ready = false;      // the full barrier of `stage` is already known complete
+      const uint32_t afree_bar0 = bar_local(&bars->a_free[0]);
+      const uint32_t hi128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+      const uint32_t hi32 = (uint32_t)(256 >> 4) | (1u << 14) | (6u << 29);     // SBO 256 B, version 1, SWIZZLE_32B
+      const uint32_t a_lo0 = ((act_base & 0x3FFFFu) >> 4) | (1u << 16);           // + LBO field (ignored for swizzled K-major)
+      const uint32_t b_lo0 = ((stage_base & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_step = (uint32_t)a.stage_bytes >> 4;
+      uint32_t b_lo = b_lo0;
       for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
-        mbar_wait(bar_local(&bars->in_ready), in_cnt & 1u); ++in_cnt;
+        wait_bar(bar_local(&bars->in_ready), in_cnt & 1u); ++in_cnt;
+        gd_seen = false;
         for (int g = 0; g < plan.n_steps; ++g) {
           const TcStep& st = plan.steps[g];
           const uint32_t idesc = make_idesc(FP16, 128 * CG, st.n_part);
-          for (int pi = 0; pi < st.n_parts; ++pi) {
-            const int pp = st.order_rev ? (st.n_parts - 1 - pi) : pi;
+          const int n_k = st.n_k, n_parts = st.n_parts;
+          const bool split = st.split_commit != 0;
+          for (int pi = 0; pi < n_parts; ++pi) {
+            const int pp = st.order_rev ? (n_parts - 1 - pi) : pi;
             const int c0 = pp * st.n_part;
-            if (pending_out && c0 < 64) { mbar_wait(bar_local(&bars->out_done), (out_cnt - 1u) & 1u); pending_out = false; }
+            if (pending_out && c0 < 64) { wait_bar(bar_local(&bars->out_done), (out_cnt - 1u) & 1u); pending_out = false; }
             {   // TMEM write-after-read: the columns of this part must have been drained
               int jl = (c0 + st.n_part - 1) / 64;
               if (jl > act_chunks - 1) jl = act_chunks - 1;
               wait_act(jl);
             }
             const uint32_t d_tmem = tmem_base + (uint32_t)c0;
-            for (int kc = 0; kc < st.n_k; ++kc) {
+            const bool commit_afree = split && pi == 1;
+            // (Issuing several slots per elect block was tried: grouping everything ran 3 % slower - MMAs issued ahead of
+            // the tensor pipe only take shared-memory bandwidth from the drain the next slots wait for - and grouping just
+            // the small bias / head slots behind a leader was slower still.  One slot per iteration it is.)
+            for (int kc = 0; kc < n_k; ++kc) {
               const uint32_t info = st.kinfo[kc];
-              const int src = info & 0xff, ks0 = (info >> 8) & 0xff, nks = (info >> 16) & 0xff;
-              if (src < act_chunks) wait_act(src);
-              if (!cur_full_ready) mbar_wait(full_bar0 + 8u * stage, phase);
+              const int src = (info >> 20) & 0xf;
+              if (src < act_chunks) { if (ready_upto <= src) wait_act(src); }
+              else if (((info >> 25) & 1u) && !gd_seen) {   // gamma(d): written several layers ago, returns at once
+                wait_bar(bar_local(&bars->gd_ready), (in_cnt - 1u) & 1u);
+                gd_seen = true;
+              }
+              wait_bar(full_bar0 + 8u * stage, phase);
               prof.stamp();
               tc_fence_after();
-              const uint32_t b_addr = stage_base + (uint32_t)stage * a.stage_bytes;
-              const uint64_t adesc = desc_hi | (uint64_t)((((act_base + (uint32_t)src * TC_CHUNK_BYTES) & 0x3FFFFu) >> 4) + 2u * ks0);
-              uint64_t bdesc = desc_hi | (uint64_t)(((b_addr & 0x3FFFFu) >> 4) + 2u * ks0);
-              if ((info >> 24) & 1u)   // bias tile: K-major SWIZZLE_32B, 8-row groups 256 bytes apart, a single K=16 slice
-                bdesc = desc_sw32 | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
-              // probes for the NEXT chunk, overlapped with the issue of this one
-              const int nstage = (stage + 1 == a.stages) ? 0 : stage + 1;
-              const uint32_t nphase = (stage + 1 == a.stages) ? (phase ^ 1u) : phase;
-              --blocks_left;
-              const bool next_full = (blocks_left > 0) ? probe(full_bar0 + 8u * nstage, nphase) : false;
-              const bool can_probe_act = act_gen > 0 && ready_upto < act_chunks;
-              const bool next_act = can_probe_act ? probe(act_bar0 + 8u * ready_upto, (act_gen - 1u) & 1u) : false;
-              // last K chunk of the second part of a split-commit step: the first output chunks (the NEXT generation) were
-              // handed over while this part ran; four non-blocking tests here save the next step a chain of barrier
-              // round trips (~340 cycles each) in front of its first MMA
-              if (st.split_commit && pi == 1 && kc == st.n_k - 1) {
-                const uint32_t npar = act_gen & 1u;
-                const uint32_t m = (mbar_test(act_bar0, npar) ? 1u : 0u) | (mbar_test(act_bar0 + 8u, npar) ? 2u : 0u) |
-                                   (mbar_test(act_bar0 + 16u, npar) ? 4u : 0u) | (mbar_test(act_bar0 + 24u, npar) ? 8u : 0u);
-                const int lead = (m == 15u) ? 4 : ((m & 7u) == 7u ? 3 : ((m & 3u) == 3u ? 2 : (int)(m & 1u)));
-                next_upto = lead < st.n_part / 64 ? lead : st.n_part / 64;
-              }
+              const uint32_t a_lo = a_lo0 + (info & 0xffffu);
               if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  if (ks < nks) umma<CG>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                const uint32_t nks = (info >> 16) & 0xfu;
+                const uint32_t acc = kc > 0 ? 1u : 0u;
+                if (nks == 4u) umma_k64<CG>(d_tmem, a_lo, b_lo, hi128, idesc, acc);
+                else if ((info >> 24) & 1u)   // bias tile: K-major SWIZZLE_32B [rows][16], a single K=16 slice
+                  umma<CG>(d_tmem, ((uint64_t)hi128 << 32) | a_lo, ((uint64_t)hi32 << 32) | b_lo, idesc, acc);
+                else
+                  for (uint32_t ks = 0; ks < nks; ++ks)
+                    umma<CG>(d_tmem, ((uint64_t)hi128 << 32) | (a_lo + 2u * ks), ((uint64_t)hi128 << 32) | (b_lo + 2u * ks), idesc,
+                             (acc || ks > 0) ? 1u : 0u);
                 umma_commit<CG>(empty_bar0 + 8u * stage);
-                if (st.split_commit && pi == 1) {
+                if (commit_afree) {
                   // input chunk x has now been read for the last time: the epilogue may overwrite it with output chunk x
-#pragma unroll
-                  for (int x = 0; x < 4; ++x)
-                    if ((int)((st.afree_pos >> (8 * x)) & 0xffu) == kc) umma_commit<CG>(bar_local(&bars->a_free[x]));
+                  uint32_t m = (info >> 26) & 0xfu;
+                  while (m) { const int x = __ffs((int)m) - 1; m &= m - 1u; umma_commit<CG>(afree_bar0 + 8u * x); }
                 }
               }
               __syncwarp();
-              if (next_act) ++ready_upto;          // that phase has been observed complete: consumed
-              cur_full_ready = next_full;
-              stage = nstage; phase = nphase;
+              if (++stage == a.stages) { stage = 0; phase ^= 1u; b_lo = b_lo0; } else b_lo += b_step;
             }
-            if (st.split_commit && pi == 0) {     // the first part's accumulator is complete: its drain starts now
+            if (split && pi == 0) {     // the first part's accumulator is complete: its drain starts now
               if (elect_one()) umma_commit<CG>(bar_local(&bars->acc_full));
               __syncwarp();
             }
           }
-          if (elect_one()) umma_commit<CG>(bar_local(st.split_commit ? &bars->acc_full2 : &bars->acc_full));
+          if (elect_one()) umma_commit<CG>(bar_local(split ? &bars->acc_full2 : &bars->acc_full));
           __syncwarp();
           prof.stamp();
-          if (st.kind == 2) { pending_out = true; ++out_cnt; } else { ++act_gen; ready_upto = next_upto; next_upto = 0; }
+          if (st.kind == 2) { pending_out = true; ++out_cnt; } else { ++act_gen; ready_upto = 0; }
         }
       }
     }
@@ -454,30 +475,36 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
       const int64_t m = (unit * CG + rank) * 128 + row;
       const bool valid = m < a.M;
       const int64_t b = valid ? (m / a.N) : 0;
-      if (hh == 0) {
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (valid) {
-          if (a.pts) { px = a.pts[m * 3 + 0]; py = a.pts[m * 3 + 1]; pz = a.pts[m * 3 + 2]; }
-          else {
-            const float* r = a.rays + b * 11; const float z = a.z_vals[m];
-            px = __fadd_rn(r[0], __fmul_rn(r[3], z)); py = __fadd_rn(r[1], __fmul_rn(r[4], z)); pz = __fadd_rn(r[2], __fmul_rn(r[5], z));
-          }
+      if (hh != 0) return;          // gamma(d) follows later (encode_gd), into the same tile
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (valid) {
+        if (a.pts) { px = a.pts[m * 3 + 0]; py = a.pts[m * 3 + 1]; pz = a.pts[m * 3 + 2]; }
+        else {
+          const float* r = a.rays + b * 11; const float z = a.z_vals[m];
+          px = __fadd_rn(r[0], __fmul_rn(r[3], z)); py = __fadd_rn(r[1], __fmul_rn(r[4], z)); pz = __fadd_rn(r[2], __fmul_rn(r[5], z));
         }
-        encode_row<FP16, false>(px, py, pz, a.L_pos, gp_base, row);
-      } else {
-        float dx = 0.f, dy = 0.f, dz = 0.f;
-        if (valid) {
-          const float* vd = a.viewdirs ? (a.viewdirs + b * 3) : (a.rays + b * 11 + 8);
-          dx = vd[0]; dy = vd[1]; dz = vd[2];
-        }
-        encode_row<FP16, true>(dx, dy, dz, a.L_dir, gd_base, row);
       }
+      encode_row<FP16, false>(px, py, pz, a.L_pos, gp_base, row);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->in_ready));
     };
-    // gamma(p) is last read by the skip layer and gamma(d) by the view layer: once the view layer's accumulator is
-    // complete both tiles are free, so the NEXT tile is encoded while the last (small) GEMM of this tile runs
+    // gamma(d) of this thread's row over columns 0..31 of the gamma tile, once the last reader of gamma(p) is done
+    auto encode_gd = [&](int64_t unit) {
+      if (hh != 1) return;
+      const int64_t m = (unit * CG + rank) * 128 + row;
+      float dx = 0.f, dy = 0.f, dz = 0.f;
+      if (m < a.M) {
+        const float* vd = a.viewdirs ? (a.viewdirs + (m / a.N) * 3) : (a.rays + (m / a.N) * 11 + 8);
+        dx = vd[0]; dy = vd[1]; dz = vd[2];
+      }
+      encode_row<FP16, true>(dx, dy, dz, a.L_dir, gp_base, row);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar_leader(&bars->gd_ready));
+    };
+    // the gamma tile is last read by the view layer (gamma(d) and the bias column): once that accumulator is complete
+    // the NEXT tile's gamma(p) is encoded while the last (small) GEMM of this tile runs
     const int enc_step = plan.n_steps - 2;
     if (unit0 < a.n_units) { load_bias(0); encode_tile(unit0); }
     for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
@@ -651,6 +678,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
           const int gn = (g + 1 < plan.n_steps) ? g + 1 : 0;
           if (gn != 0 || unit + n_grid_units < a.n_units) load_bias(gn);
         }
+        if (g == plan.gd_step) encode_gd(unit);       // this step's accumulator is complete: gamma(p) is dead
         if (g == enc_step && unit + n_grid_units < a.n_units) encode_tile(unit + n_grid_units);
         prof.stamp();
       }
@@ -684,12 +712,9 @@ __global__ void pack_stream_kernel(PackSrcTable srcs, const int* __restrict__ bl
     const int r = i >> 6, c = i & 63;
     float v = 0.f;
     if (r < rows_valid && c < cols_valid) v = S.ptr[(int64_t)(row0 + r) * S.ld + col0 + c];
-    if (bias_src >= 0 && (c == bias_col || c == bias_col + 1) && r < rows_valid) {
-      // fp32 bias as a (hi, lo) pair of 16-bit values multiplied by the two ones columns: exact to ~2^-17 relative
-      const float bv = srcs.s[bias_src].ptr[row0 + r];
-      const float hi = FP16 ? __half2float(__float2half_rn(bv)) : __bfloat162float(__float2bfloat16_rn(bv));
-      v = (c == bias_col) ? hi : (bv - hi);
-    }
+    // the bias row multiplies the ones column of the gamma tile; like every weight it is rounded to the operand type
+    // (scripts/experiments/k1_precision_sim.py: 3.9e-4 -> 4.0e-4 on the stressed fixture)
+    if (bias_src >= 0 && c == bias_col && r < rows_valid) v = srcs.s[bias_src].ptr[row0 + r];
     uint16_t o;
     if (FP16) o = __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f)));   // saturate, never inf
     else o = __bfloat16_as_ushort(__float2bfloat16_rn(v));
@@ -748,7 +773,7 @@ int tc_create(CfnHandle* h) {
   const CfnConfig& c = h->cfg;
   const int W = c.W, F = c.F, D = c.D;
   CFN_CHECK_ARG(W % 64 == 0 && W >= 128 && W <= 512, "tensor-core path: netwidth %d unsupported (multiple of 64 in 128..512)", W);
-  CFN_CHECK_ARG(h->in_pos <= 64 && h->in_dir <= 32, "tensor-core path: multires %d / multires_views %d unsupported (<=10 / <=4)", c.L_pos, c.L_dir);
+  CFN_CHECK_ARG(h->in_pos <= 63 && h->in_dir <= 32, "tensor-core path: multires %d / multires_views %d unsupported (<=10 / <=4)", c.L_pos, c.L_dir);
   CFN_CHECK_ARG(15 * F <= 256, "tensor-core path: n_flows %d unsupported", F);
   CFN_CHECK_ARG(D + 4 <= TC_MAX_STEPS, "tensor-core path: netdepth %d unsupported", D);
   CFN_CHECK_ARG(h->in_dir <= 32, "tensor-core path: multires_views %d unsupported", c.L_dir);
@@ -787,24 +812,29 @@ int tc_create(CfnHandle* h) {
     st.n_parts = (n_total + st.n_part - 1) / st.n_part;
     st.order_rev = rev ? 1 : 0;
     if (kind != 2) {
-      bool has_gd = false;
-      for (auto& k : kch) if (k.src == TC_SRC_GD) { k.kstart = 0; k.ksteps = 4; k.with_bias = 1; has_gd = true; }
-      if (!has_gd) kch.push_back({TC_SRC_GD, 3, 1, 0, 0, 2});   // with_bias == 2: stand-alone bias entry (SWIZZLE_32B tile)
+      // the bias rides in column 63 of a gamma block if the step reads the gamma tile anyway, else in a K=16 slice of its own
+      bool has_g = false;
+      for (auto& k : kch)
+        if ((k.src == TC_SRC_GD || k.src == TC_SRC_GP) && !has_g) { k.kstart = 0; k.ksteps = 4; k.with_bias = 1; has_g = true; }
+      if (!has_g) kch.push_back({TC_SRC_GP, 3, 1, 0, 0, 2});   // with_bias == 2: stand-alone bias entry (SWIZZLE_32B tile)
     }
     st.n_k = (int)kch.size();
     for (int i = 0; i < st.n_k; ++i) {
-      const int idx = kch[i].src == TC_SRC_GP ? AC : (kch[i].src == TC_SRC_GD ? AC + 1 : kch[i].src);
-      st.kinfo[i] = (unsigned)idx | ((unsigned)kch[i].kstart << 8) | ((unsigned)kch[i].ksteps << 16) |
-                    ((unsigned)(kch[i].with_bias == 2 ? 1 : 0) << 24);
+      const bool gam = kch[i].src == TC_SRC_GP || kch[i].src == TC_SRC_GD;
+      const int idx = gam ? AC : kch[i].src;
+      // bits 0..15: offset of the A operand in descriptor units (16 bytes) from the activation tile: chunk + K slice
+      st.kinfo[i] = (unsigned)((idx * TC_CHUNK_BYTES + kch[i].kstart * 32) >> 4) | ((unsigned)kch[i].ksteps << 16) |
+                    ((unsigned)idx << 20) | ((unsigned)(kch[i].with_bias == 2 ? 1 : 0) << 24) |
+                    ((unsigned)(kch[i].src == TC_SRC_GD ? 1 : 0) << 25);
+      if (kch[i].src == TC_SRC_GP && kch[i].with_bias != 2) dev.gd_step = dev.n_steps - 1;   // last reader of gamma(p)
     }
     st.split_commit = 0;
-    st.afree_pos = 0;
     if (kind != 2 && st.n_parts == 2 && !st.order_rev && (st.n_part % 128) == 0 && st.n_part / 64 <= 4 && split_drain) {
       st.split_commit = 1;
       for (int x = 0; x < st.n_part / 64; ++x) {
         int pos = 0;                                  // not read by this step: free right after the first K chunk
         for (int i = 0; i < st.n_k; ++i) if (kch[i].src == x) pos = i;
-        st.afree_pos |= (unsigned)pos << (8 * x);
+        st.kinfo[pos] |= 1u << (26 + x);
       }
     }
     st.bias_off = table_off;
@@ -824,7 +854,7 @@ int tc_create(CfnHandle* h) {
         b.rows_padded = st.n_part;
         b.stream_row = stream_row;
         b.bias_src = kch[i].with_bias ? bias_src : -1;
-        b.bias_col = kch[i].with_bias == 2 ? 14 : 62;   // stand-alone tile: K slice 48..63 -> tile columns 0..15
+        b.bias_col = kch[i].with_bias == 2 ? 15 : 63;   // stand-alone tile: K slice 48..63 -> tile columns 0..15
         p->blocks.push_back(b);
         stream_row += st.n_part;
       }
@@ -881,10 +911,11 @@ int tc_create(CfnHandle* h) {
   if (prop.major != 10) { set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor); return CFN_EINVAL; }
   p->num_sms = prop.multiProcessorCount;
   p->stage_bytes = (256 / CG) * 128;
-  const size_t fixed = (size_t)(AC + 2) * TC_CHUNK_BYTES + sizeof(TcBarriers) + 2048;   // + bias staging (512 floats)
+  const size_t fixed = (size_t)(AC + 1) * TC_CHUNK_BYTES + sizeof(TcBarriers) + 2048;   // + bias staging (512 floats)
   const size_t smem_max = (size_t)prop.sharedMemPerBlockOptin;
   int stages = (int)((smem_max - fixed) / p->stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (const char* e = getenv("CFN_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v < stages) stages = v; }   // experiments only
   if (stages < 2) return fail("not enough shared memory for two weight stages");
   p->stages = stages;
   p->smem_bytes = fixed + (size_t)stages * p->stage_bytes;

@@ -16,8 +16,8 @@ def rnd(x, mode):
     if mode == "exact": return x.double()
     raise ValueError(mode)
 
-def k1(p, cfg, pts, dirs, trunk="bf16", head_act="bf16", head_w="bf16"):
-    P = {k: v.double() for k, v in p.items()}
+def k1(p, cfg, pts, dirs, trunk="bf16", head_act="bf16", head_w="bf16", bias="exact"):
+    P = {k: (rnd(v, bias) if (k.endswith(".bias") and (k.startswith("pts_linears") or k.startswith("feature") or k.startswith("views"))) else v.double()) for k, v in p.items()}
     gp = rnd(O.positional_encoding(pts.float(), cfg.L_pos), trunk)
     gd = rnd(O.positional_encoding(dirs.float(), cfg.L_dir), trunk)
     h = gp
@@ -86,7 +86,9 @@ for name, kw in [("exact", dict(trunk="exact", head_act="exact", head_w="exact")
                  ("bf16 trunk, hilo head acts+weights", dict(head_act="hilo", head_w="hilo")),
                  ("bf16 trunk, hilo head weights only", dict(head_w="hilo")),
                  ("bf16 trunk, fp16 head acts+weights", dict(head_act="fp16", head_w="fp16")),
-                 ("all fp16", dict(trunk="fp16", head_act="fp16", head_w="fp16"))]:
+                 ("all fp16", dict(trunk="fp16", head_act="fp16", head_w="fp16")),
+                 ("all fp16, fp16-rounded trunk biases", dict(trunk="fp16", head_act="fp16", head_w="fp16", bias="fp16")),
+                 ("all bf16, bf16-rounded trunk biases", dict(bias="bf16"))]:
     a, c = k1(p, cfg, pts, dirs, **kw)
     rgb, depth = finish(p, cfg, a, c, ea, er, z, rays[:, 3:6], M)
     K = cfg.K
