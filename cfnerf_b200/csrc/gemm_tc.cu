@@ -48,6 +48,7 @@ struct TgParams {
   const float* bias; const float* aux; int64_t aux_rs;
   int64_t M; int N; int64_t K;
   int epilogue, accumulate, split_k, atomic, round_out, vec_ok;
+  int vec8_ok;         // bf16 C: rows are 16-byte addressable in groups of 8 columns (the lean bf16 epilogue)
   int bn;              // N of one tcgen05.mma (multiple of 16, <= 256)
   int b_rows_cta;      // B rows (n) staged by one CTA = bn / CG
   int b_blocks;        // N-major B: 32-column blocks staged by one CTA
@@ -89,6 +90,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
 // a one-sided error that accumulates over the layers; operands written through this are read back exactly
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
+}
+
+// two fp32 -> packed bf16 pair (lo = first column), optional fused ReLU
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 
 struct TgBarriers {
@@ -325,7 +335,48 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int64_t gm0 = tile_m0 + q * 32 + sub_r;
         // WARP-UNIFORM choice (both paths contain full-mask shuffles): the whole 32 x 32 block inside the matrix
         const bool block_inside = p.vec_ok && (tile_m0 + q * 32 + 31 < p.M) && (n_tile0 + c * 32 + 31 < p.N);
-        if (block_inside) {
+        if (CBF && (EPI == TG_PLAIN || EPI == TG_RELU || EPI == TG_MASK) && block_inside && p.vec8_ok && !p.accumulate) {
+          // ---- bf16 output, lean form (the forward / dgrad GEMMs of the bf16 training chain): 4 lanes per row, 8 rows per
+          // instruction, 8 columns = one 16-byte store per lane; bias + (ReLU fused into the conversion | mask select);
+          // row pointers advance by a constant.  The general form below spent 11 instructions per element (ncu: issue
+          // slots 61 % busy, the epilogue - not the MMAs or HBM - set the tile time); this one spends ~5.
+          const int rr = lane >> 2, l4 = lane & 3, cg8 = l4 * 8;
+          const int gn8 = n_tile0 + c * 32 + cg8;
+          float bb[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bb[i] = p.bias ? __ldg(p.bias + gn8 + i) : 0.f;
+          const int64_t row0 = tile_m0 + q * 32 + rr;
+          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + row0 * p.c_rs + gn8;
+          const int64_t cstep = 8 * p.c_rs;
+          uint32_t* mrow = (EPI == TG_RELU && p.mask_out) ? p.mask_out + row0 * p.bits_ld + ((n_tile0 + c * 32) >> 5) : nullptr;
+          const int64_t mstep = 8 * p.bits_ld;
+          const int sh = 2 * l4;   // mask word: column n of the chunk is bit 8 * (n % 4) + n / 4; this lane owns n = cg8 .. cg8 + 7
+          const float* srow = stg + rr * TG_STG_LD + cg8;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float4 a0 = *reinterpret_cast<const float4*>(srow + t * 8 * TG_STG_LD);
+            const float4 a1 = *reinterpret_cast<const float4*>(srow + t * 8 * TG_STG_LD + 4);
+            float y[8] = {a0.x + bb[0], a0.y + bb[1], a0.z + bb[2], a0.w + bb[3], a1.x + bb[4], a1.y + bb[5], a1.z + bb[6], a1.w + bb[7]};
+            if (EPI == TG_MASK && use_bits) {
+              const uint32_t kw = __shfl_sync(0xffffffffu, curb, t * 8 + rr) >> sh;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = (kw & (1u << (8 * (i & 3) + (i >> 2)))) ? y[i] : 0.f;
+            }
+            uint4 pk;
+            pk.x = pack_bf16x2<EPI == TG_RELU>(y[0], y[1]); pk.y = pack_bf16x2<EPI == TG_RELU>(y[2], y[3]);
+            pk.z = pack_bf16x2<EPI == TG_RELU>(y[4], y[5]); pk.w = pack_bf16x2<EPI == TG_RELU>(y[6], y[7]);
+            *reinterpret_cast<uint4*>(crow + t * cstep) = pk;
+            if (EPI == TG_RELU && p.mask_out) {
+              uint32_t m = 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) m |= (y[i] > 0.f ? 1u : 0u) << (8 * (i & 3) + (i >> 2));
+              m <<= sh;
+              m |= __shfl_xor_sync(0xffffffffu, m, 1);
+              m |= __shfl_xor_sync(0xffffffffu, m, 2);
+              if (l4 == 0) mrow[t * mstep] = m;
+            }
+          }
+        } else if (block_inside) {
           // ---- fast path: the whole 32 x 32 block is inside the matrix and 16-byte addressable ----
           const uint32_t sel_row = (uint32_t)sub_r | ((uint32_t)(4 + sub_r) << 4);   // byte sub_r of each vote pair
           uint32_t* mask_row = (EPI == TG_RELU && p.mask_out) ? p.mask_out + gm0 * p.bits_ld + ((n_tile0 + c * 32) >> 5) : nullptr;
@@ -560,6 +611,7 @@ static void plan_tgemm(const GemmArgs& g, TgParams& p, int& CG, bool& a_mn, bool
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.epilogue = g.epilogue; p.accumulate = g.accumulate; p.split_k = g.split_k > 1 ? g.split_k : 1;
   const int bke = g.ab_bf16 ? 64 : 32;      // elements per 128-byte K block / MN-major row
+  p.vec8_ok = g.c_bf16 && (g.c_rs % 8 == 0) && aligned16(g.C) && (g.epilogue != EPI_RELU_MASK_MUL || g.aux_bits != nullptr);
   if (g.c_bf16) p.vec_ok = (g.c_rs % 4 == 0) && (((uintptr_t)g.C & 7u) == 0);
   else p.vec_ok = (g.c_rs % 4 == 0) && aligned16(g.C) &&
                   (g.epilogue != EPI_RELU_MASK_MUL || g.aux_bits || (g.aux_rs % 4 == 0 && aligned16(g.aux)));

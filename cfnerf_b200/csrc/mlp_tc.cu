@@ -372,6 +372,15 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
       const uint32_t b_lo0 = ((stage_base & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t b_step = (uint32_t)a.stage_bytes >> 4;
       uint32_t b_lo = b_lo0;
+      bool cur_full = false;            // the full barrier of `stage` is already known complete
+      // number of weight blocks this CTA pair will consume (to know when there is no "next stage" to probe)
+      int64_t blocks_left = 0;
+      {
+        int per_tile = 0;
+        for (int g = 0; g < plan.n_steps; ++g) per_tile += plan.steps[g].n_parts * plan.steps[g].n_k;
+        const int64_t my_tiles = (a.n_units > unit0) ? (a.n_units - unit0 + n_grid_units - 1) / n_grid_units : 0;
+        blocks_left = my_tiles * per_tile;
+      }
       for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
         wait_bar(bar_local(&bars->in_ready), in_cnt & 1u); ++in_cnt;
         gd_seen = false;
@@ -402,10 +411,14 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
                 wait_bar(bar_local(&bars->gd_ready), (in_cnt - 1u) & 1u);
                 gd_seen = true;
               }
-              wait_bar(full_bar0 + 8u * stage, phase);
+              if (!cur_full) wait_bar(full_bar0 + 8u * stage, phase);
               prof.stamp();
               tc_fence_after();
               const uint32_t a_lo = a_lo0 + (info & 0xffffu);
+              // the NEXT slot's weights: probed now, so that the barrier round trip overlaps the issue of this slot
+              const int nstage = (stage + 1 == a.stages) ? 0 : stage + 1;
+              const uint32_t nphase = (stage + 1 == a.stages) ? (phase ^ 1u) : phase;
+              const bool next_full = (--blocks_left > 0) ? mbar_probe(full_bar0 + 8u * nstage, nphase) : false;
               if (elect_one()) {
                 const uint32_t nks = (info >> 16) & 0xfu;
                 const uint32_t acc = kc > 0 ? 1u : 0u;
@@ -424,7 +437,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
                 }
               }
               __syncwarp();
-              if (++stage == a.stages) { stage = 0; phase ^= 1u; b_lo = b_lo0; } else b_lo += b_step;
+              cur_full = next_full;
+              if (nstage == 0) b_lo = b_lo0; else b_lo += b_step;
+              stage = nstage; phase = nphase;
             }
             if (split && pi == 0) {     // the first part's accumulator is complete: its drain starts now
               if (elect_one()) umma_commit<CG>(bar_local(&bars->acc_full));

@@ -14,6 +14,7 @@ if [ "${1:-}" = "summarize" ]; then
   python scripts/ncu_summary.py rep $G/${R}_prof_k2.ncu-rep $P/${R}_prof_k2_summary.csv
   python scripts/ncu_summary.py rep $G/${R}_prof_k2k4_train.ncu-rep $P/${R}_prof_k2k4_train_summary.csv
   python scripts/ncu_summary.py rep $G/${R}_prof_raw2outputs.ncu-rep $P/${R}_prof_raw2outputs_summary.csv
+  python scripts/ncu_summary.py rep $G/${R}_prof_tgemm_train.ncu-rep $P/${R}_prof_tgemm_train_summary.csv
   cp $G/${R}_train4096_launches.csv $P/${R}_train_launches.csv
   python scripts/ncu_summary.py list $G/${R}_train4096_launches.csv $P/${R}_train_launch_summary.csv
   python scripts/ncu_summary.py list $G/${R}_train512_launches.csv $P/${R}_train512_launch_summary.csv
@@ -38,6 +39,9 @@ $T 400 ncu --set full --clock-control none --import-source on -k regex:raw2outpu
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-train > $G/ncu_r2o.log 2>&1
 CFN_RAYS=4096 CFN_STEPS=2 $T 300 ncu --set full --clock-control none --import-source on -k regex:flow_composite -s 2 -c 2 -f \
    -o $G/${R}_prof_k2k4_train python scripts/r2_step512.py > $G/ncu_k4.log 2>&1
+# forward / dgrad / wgrad GEMMs of one trunk layer inside the bf16 training step
+CFN_RAYS=4096 CFN_STEPS=2 $T 300 ncu --set full --clock-control none -k regex:tgemm_kernel -s 75 -c 8 -f \
+   -o $G/${R}_prof_tgemm_train python scripts/r2_step512.py > $G/ncu_tg.log 2>&1
 CFN_RAYS=4096 CFN_STEPS=3 $T 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
    --log-file $G/${R}_train4096_launches.csv python scripts/r2_step512.py > $G/ncu_t4096.log 2>&1
 CFN_RAYS=512 CFN_STEPS=3 $T 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv \

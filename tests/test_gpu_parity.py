@@ -310,6 +310,41 @@ def test_render_rays_hierarchical_fp32(cf, dev):
         assert (out[k].cpu() - ref[k]).abs().max().item() <= 5e-4, k
 
 
+def test_hierarchical_stages_meet_the_fp32_bar_one_by_one(cf, dev):
+    """The 5e-4 of the test above is the inverse CDF amplifying 1e-7 differences of the coarse weights into sample
+    positions (a discontinuous map), not error of a stage.  Stage by stage the fp32 check mode holds the 1e-5 bar of
+    north_star: (i) the coarse maps (above), (ii) sample_pdf + merge on the ORACLE's coarse weights reproduce the
+    oracle's fine grid bit for bit, (iii) the fine network + flow + compositing pass on that grid matches the
+    oracle's fine maps at 1e-5."""
+    cfg = O.CfnConfig(W=256, K=64, h_alpha=32)
+    pc, pf = O.make_params(cfg, 0, "lively"), O.make_params(cfg, 1, "lively")
+    sa, sr = O.make_latents(cfg, 0)
+    net_c, net_f = make_net(cf, cfg, pc, sa, sr, dev), make_net(cf, cfg, pf, sa, sr, dev)
+    rays = O.synthetic_rays(12, 8)
+    ea, er = O.test_latents(sa, sr)
+    with torch.no_grad():
+        ref = O.render_rays_hier(pc, pf, cfg, rays, ea, er, False, 64, 128)
+    z_ref = ref["z_vals"]
+    # (ii) resampling on the oracle's coarse weights: bit-exact grid
+    z_c = O.z_from_t(O.coarse_t_schedule(64, rays.dtype), rays[:, 6:7], rays[:, 7:8], False, None)
+    w_mean = ref["weights0"].mean(-1)
+    z_mid = .5 * (z_c[..., 1:] + z_c[..., :-1])
+    zs = cf.sample_pdf(z_mid.to(dev), w_mean[..., 1:-1].contiguous().to(dev), 128, det=True)
+    z_all = cf.merge_sorted(z_c.to(dev), zs)
+    assert torch.equal(z_all.cpu(), z_ref)
+    # (iii) the fine pass on that grid
+    eng = cf.engine_for(net_f, dev, "fp32")
+    r = rays.to(dev)
+    z = z_ref.to(dev).contiguous()
+    fp = eng.network(r.shape[0], z.shape[1], rays=r, z_vals=z)
+    out = eng.flow_composite(fp, z, r[:, 3:6], 11, ea.reshape(-1).to(dev).contiguous(), er.to(dev).contiguous(), False,
+                             want_raw=False, want_weights=False)
+    for k in ("rgb_map", "depth_map"):
+        err = (out[k].cpu() - ref[k]).abs().max().item()
+        print(f"fine pass on the oracle's grid, {k}: {err:.2e}")
+        assert err <= TOL_FP32, (k, err)
+
+
 # ------------------------------------------------------------------------------------------------
 # tensor-core modes (bf16 / fp16 operands, fp32 accumulation)
 # ------------------------------------------------------------------------------------------------
