@@ -9,6 +9,9 @@ sys.path.insert(0, ROOT)
 import torch
 
 import cfnerf_b200 as cf
+if os.environ.get("CFN_AB_LIB"):   # same-box A/B against another build of the library
+    import cfnerf_b200._lib as _L
+    _L.LIB_PATH = os.environ["CFN_AB_LIB"]
 from oracle import cfnerf_oracle as O
 
 dev = torch.device("cuda:0")
@@ -35,4 +38,4 @@ for prec in ("fp16", "bf16"):
     # correctness against the fp32 check mode on a slice
     ref = cf.engine_for(net, dev, "fp32").network(256, N, rays=rays[:256], z_vals=z[:256])
     res[prec]["max_err_vs_fp32"] = float((fp[:256 * N] - ref).abs().max())
-print(json.dumps({"split_drain": os.environ.get("CFN_TC_SPLIT_DRAIN", "1"), **res}))
+print(json.dumps({"lib": os.environ.get("CFN_AB_LIB", "tree"), "split_drain": os.environ.get("CFN_TC_SPLIT_DRAIN", "1"), **res}))
