@@ -304,6 +304,21 @@ extern "C" int cfn_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t
   return chain_network_bwd(h, g_flow_params, B, N, (float*)workspace, grads, (cudaStream_t)stream);
 }
 
+extern "C" int cfn_network_bwd_part(CfnHandle* h, const float* g_flow_params, int64_t B, int N, void* workspace,
+                                    size_t workspace_bytes, float* const* grads, int n_params, int part, int split_layer,
+                                    void* stream) {
+  CFN_CHECK_ARG(h && g_flow_params && grads && workspace, "cfn_network_bwd_part: null argument");
+  CFN_CHECK_ARG(n_params == (int)h->slots.size(), "cfn_network_bwd_part: expected %d tensors", (int)h->slots.size());
+  CFN_CHECK_ARG(part == 1 || part == 2, "cfn_network_bwd_part: part must be 1 or 2");
+  size_t need = 0;
+  cfn_workspace_bytes(h, B * N, 1, &need);
+  if (workspace_bytes < need) {
+    set_error("cfn_network_bwd_part: workspace %zu bytes < required %zu", workspace_bytes, need);
+    return CFN_ENOMEM;
+  }
+  return chain_network_bwd(h, g_flow_params, B, N, (float*)workspace, grads, (cudaStream_t)stream, part, split_layer);
+}
+
 extern "C" int cfn_flow_composite_fwd(CfnHandle* h, const float* flow_params, const float* z_vals,
                                       const float* rays_d, int rays_d_stride, const float* eps_alpha,
                                       const float* eps_rgb, int64_t eps_group_rays, int64_t B, int N, int white_bkgd,

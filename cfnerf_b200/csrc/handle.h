@@ -79,8 +79,10 @@ namespace cfn {
 size_t chain_workspace_floats(const CfnHandle* h, int64_t n_points, int save);
 int chain_network_fwd(CfnHandle* h, const float* rays, const float* z_vals, const float* pts, const float* viewdirs,
                      int64_t B, int N, float* flow_params, float* ws, int save, cudaStream_t s);
+// part 0: the whole backward.  part 1: everything down to and including the weight gradient of trunk layer `split_layer`
+// (then the gradients of every parameter from that layer on are final); part 2: the rest (trunk layers below it).
 int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, float* ws, float* const* grads,
-                     cudaStream_t s);
+                     cudaStream_t s, int part = 0, int split_layer = 0);
 int pack_fp32(CfnHandle* h, const float* const* params, cudaStream_t s);
 
 // tensor-core path (mlp_tc.cu)

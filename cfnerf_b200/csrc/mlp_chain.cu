@@ -510,8 +510,11 @@ __global__ void scatter_rows_kernel(const float* __restrict__ dAm, const float* 
 }
 
 int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N, float* ws, float* const* grads,
-                     cudaStream_t s) {
+                     cudaStream_t s, int part, int split_layer) {
   const int64_t M = B * N;
+  CFN_CHECK_ARG(part >= 0 && part <= 2 && (part == 0 || (split_layer >= 1 && split_layer < h->cfg.D)),
+                "cfn_network_bwd_part: part %d / split layer %d out of range (1..%d)", part, split_layer, h->cfg.D - 1);
+  const bool head_phase = part != 2;      // parts 0 and 1 start at the flow records; part 2 resumes inside the trunk
   const int W = h->cfg.W, D = h->cfg.D, F = h->cfg.F, PP = h->PP;
   const int ha_n = h->cfg.h_alpha, hr_n = h->cfg.h_rgb;
   ChainLayout L = make_layout(h, M, 1);
@@ -522,7 +525,7 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
   float* dAb = dAm + (int64_t)PP * (ha_n > hr_n ? ha_n : hr_n);   // (rows) gathered bias grads
 
   // 1. through the tanh on the diagonals
-  {
+  if (head_phase) {
     int64_t total = M * PP;
     tanh_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g_flow_params, ws + L.P, h->tanh_flags, ws + L.GP,
                                                                     total, PP, 3 * F, L.gpa, L.ldGP,
@@ -554,8 +557,8 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
 
   // Gradient tensors laid out back to back in slot order (cfnerf_b200.dist.FusedTrainStep's flat bucket): ONE memset
   // replaces the ~40 per-tensor ones of the split-K wgrads (each a graph node / launch of its own at 512 rays per step)
-  h->zero_lo = h->zero_hi = nullptr;
-  {
+  if (head_phase) h->zero_lo = h->zero_hi = nullptr;
+  if (head_phase) {
     bool flat = true;
     for (size_t i = 5; i < h->slots.size(); ++i)
       flat = flat && (grads[i] == grads[4] + (h->slots[i].offset - h->slots[4].offset));
@@ -567,7 +570,7 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
     }
   }
   // zero every flow-conditioning gradient: rows the path never reads keep an exact 0
-  if (!h->zero_lo)
+  if (head_phase && !h->zero_lo)
     for (int base : {h->s_frgb, h->s_falpha})
       for (int j = 0; j < 8; ++j)
         CFN_CUDA(cudaMemsetAsync(grads[base + j], 0, h->slots[base + j].numel * sizeof(float), s));
@@ -577,7 +580,7 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
   for (size_t i = 0; i < 64; ++i) table.p[i] = i < h->slots.size() ? grads[i] : nullptr;
 
   // 2. alpha conditioning branch
-  {
+  if (head_phase) {
     // gathered dAmA = GP[:, :3F]^T ha ; bias = colsum
     if ((rc = wgrad(h, GPa, ldGP, 3 * F, ws + L.ha, ha_n, ha_n, M, dAm, dAb, s))) return rc;
     scatter_rows_kernel<<<3 * F, 64, 0, s>>>(dAm, dAb, ha_n, h->gatherA_dev, 3 * F, table);
@@ -594,7 +597,7 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
     if (!fuse_heads && (rc = dgrad(h, h->s_halpha, gha, ld_gha, 0, W, G1, W, M, nullptr, 0, 0, s))) return rc;
   }
   // 3. rgb conditioning branch
-  {
+  if (head_phase) {
     if ((rc = wgrad(h, GPc, ldGP, 15 * F, ws + L.hr, hr_n, hr_n, M, dAm, dAb, s))) return rc;
     scatter_rows_kernel<<<15 * F, 64, 0, s>>>(dAm, dAb, hr_n, h->gatherC_dev, 15 * F, table);
     CFN_LAUNCH_CHECK();
@@ -631,10 +634,19 @@ int chain_network_bwd(CfnHandle* h, const float* g_flow_params, int64_t B, int N
   // 4. trunk, last layer to first
   float* gout = G1;
   float* gin = G2;
-  for (int i = D - 1; i >= 0; --i) {
+  int i_first = D - 1;
+  if (part == 2) {
+    // resume: layers D-1 .. split_layer swapped the two gradient buffers once per dgrad (D-1-split_layer of them)
+    i_first = split_layer;
+    if ((D - 1 - split_layer) & 1) { gout = G2; gin = G1; }
+  }
+  for (int i = i_first; i >= 0; --i) {
     LayerIO io = trunk_io(h, L, ws, M, i, 1);
     const int slot = h->s_pts(i, 0);
-    if ((rc = wgrad_slot(h, slot, gout, W, io.in, io.ld_in, M, grads[slot], grads[slot + 1], dWp, s))) return rc;
+    if (!(part == 2 && i == split_layer)) {     // (part 1 already took this layer's weight gradient)
+      if ((rc = wgrad_slot(h, slot, gout, W, io.in, io.ld_in, M, grads[slot], grads[slot + 1], dWp, s))) return rc;
+    }
+    if (part == 1 && i == split_layer) break;
     if (i == 0) break;
     // gradient w.r.t. the previous layer's (post-ReLU) output, masked by its ReLU
     LayerIO prev = trunk_io(h, L, ws, M, i - 1, 1);
