@@ -517,18 +517,12 @@ def main():
     keys = ("rgb_map", "disp_map", "depth_map", "kstats")
 
     def render_e2e(rays_host):
+        # the public host-in / host-out call: H2D of a chunk, render_rays, D2H of its outputs on a second stream (the
+        # copies of chunk i overlap the kernels of chunk i + 1); returns once the last byte is in pinned host memory
         nonlocal out_host
-        res = []
-        for i in range(0, rays_host.shape[0], chunk):
-            r = rays_host[i:i + chunk].to(dev, non_blocking=True)
-            res.append(cf.render_rays(r, net, None, Nc, False, False, **render_kw))
-        cat = {k: torch.cat([o[k] for o in res], 0) for k in keys}
-        if out_host is None:
-            out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in cat.items()}
-        for k, v in cat.items():
-            out_host[k].copy_(v, non_blocking=True)
+        out_host = cf.render_rays_host(rays_host, net, Nc, chunk=chunk, keys=keys, out=out_host, **render_kw)
         torch.cuda.synchronize()
-        return cat
+        return out_host
 
     for s in range(2):
         render_e2e(views_host[s % len(views_host)])

@@ -423,6 +423,46 @@ def render_image(H, W, focal, c2w, network_fn, near=0., far=1., ndc=False, chunk
     return [allr[k] for k in ex] + [{k: v for k, v in allr.items() if k not in ex}]
 
 
+_COPY_STREAMS: dict = {}
+
+
+def render_rays_host(rays_host, network_fn, N_samples=128, chunk=1024 * 32, keys=("rgb_map", "disp_map", "depth_map"),
+                     out=None, device=None, **render_kwargs):
+    """Host in, host out: what `render()` + the `.cpu()` calls of `render_path_train` do (main:129-170, 305-320), as a
+    three-stage pipeline.  `rays_host` (B,11) lives in (preferably pinned) host memory; every chunk of rays is copied to
+    the device, rendered by `render_rays` (test mode) and its outputs are copied back into pinned host tensors ON A
+    SECOND STREAM, so that the device-to-host traffic of chunk i (20 K bytes per ray: 1.6 GB per 800 x 800 image at
+    K = 128) overlaps the kernels of chunk i + 1 instead of following the last one.
+
+    Returns {key: pinned host tensor (B, ...)} for `keys` (any of the render_rays outputs, e.g. "kstats" with
+    want_kstats=True).  `out`: a dict returned by an earlier call of the same shape, to reuse its pinned buffers.
+    The call returns after the last copy has completed."""
+    dev = torch.device(device) if device is not None else next(_unwrap(network_fn).parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("cfnerf_b200.render_rays_host needs the network on a CUDA device (no CPU fallback)")
+    B = rays_host.shape[0]
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream(dev)
+        side = _COPY_STREAMS.get(dev)
+        if side is None:
+            side = _COPY_STREAMS[dev] = torch.cuda.Stream(dev)
+        out = {} if out is None else out
+        for i in range(0, B, chunk):
+            n = min(chunk, B - i)
+            r = rays_host[i:i + n].to(dev, non_blocking=True)
+            o = render_rays(r, network_fn, None, N_samples, False, False, **render_kwargs)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for k in keys:
+                    v = o[k]
+                    if k not in out or out[k].shape[0] != B or out[k].shape[1:] != v.shape[1:]:
+                        out[k] = torch.empty((B,) + tuple(v.shape[1:]), dtype=v.dtype).pin_memory()
+                    out[k][i:i + n].copy_(v, non_blocking=True)
+                    v.record_stream(side)       # the allocator may not hand this block out before the copy has run
+        side.synchronize()
+    return out
+
+
 def configure(precision: str | None = None, train_precision: str | None = None, netchunk: int | None = None):
     """Module defaults used when a call does not say otherwise: render precision ("fp16" | "bf16" | "tf32" | "fp32"),
     training precision ("tf32" | "bf16" | "fp32") and the reference's netchunk (points per network call, main:336)."""

@@ -637,6 +637,27 @@ def test_render_image_equals_render_rays_on_the_same_rays(cf, dev):
 # ------------------------------------------------------------------------------------------------
 # F1: fused K-reduction + KDE-NLL loss and its gradient
 # ------------------------------------------------------------------------------------------------
+def test_render_rays_host_pipeline_equals_render_rays(cf, dev):
+    """The host-in / host-out pipeline (H2D, render, D2H on a second stream, chunk by chunk) returns, in pinned host
+    memory, bit for bit what one render_rays call on the device returns; a ragged last chunk and buffer reuse included."""
+    cfg = O.CfnConfig()
+    p = O.make_params(cfg, 2, "lively")
+    sa, sr = O.make_latents(cfg, 2)
+    net = make_net(cf, cfg, p, sa, sr, dev)
+    rays = O.synthetic_rays(300, 5).pin_memory()
+    ref = cf.render_rays(rays.to(dev), net, None, 128, False, False, K_samples=cfg.K, want_kstats=True)
+    keys = ("rgb_map", "disp_map", "depth_map", "kstats")
+    out = cf.render_rays_host(rays, net, 128, chunk=128, keys=keys, K_samples=cfg.K, want_kstats=True)
+    for k in keys:
+        assert out[k].is_pinned() and out[k].device.type == "cpu"
+        assert torch.equal(out[k], ref[k].cpu()), k
+    ptrs = {k: out[k].data_ptr() for k in keys}
+    out2 = cf.render_rays_host(rays, net, 128, chunk=77, keys=keys, out=out, K_samples=cfg.K, want_kstats=True)
+    for k in keys:
+        assert out2[k].data_ptr() == ptrs[k]
+        assert torch.equal(out2[k], ref[k].cpu()), k
+
+
 @pytest.mark.parametrize("B,K", [(16, 32), (7, 64), (5, 128), (3, 5)])
 def test_fused_kde_nll_matches_trainer_loss_and_gradient(cf, dev, B, K):
     g = torch.Generator().manual_seed(B + K)
