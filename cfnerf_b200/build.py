@@ -35,7 +35,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + sources()
+    extra = os.environ.get("CFN_NVCC_EXTRA", "").split()     # e.g. -DCFN_TC_ISSUE_STAMPS=1 for the issuer-timeline build
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB_PATH] + sources()
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(PKG_DIR, "build.log")
     with open(log, "w") as f:

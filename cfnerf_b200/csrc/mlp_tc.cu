@@ -26,6 +26,11 @@
 
 namespace cfn {
 
+// -DCFN_TC_ISSUE_STAMPS=1 (CFN_NVCC_EXTRA of cfnerf_b200/build.py): three clock64() stamps per ring slot in the MMA issuer
+// instead of one — the diagnostic build behind scripts/r2_k1_issue.py; the stamps cost ~10 % of the kernel.
+#ifndef CFN_TC_ISSUE_STAMPS
+#define CFN_TC_ISSUE_STAMPS 0
+#endif
 constexpr int TC_MAX_STEPS = 20;
 constexpr int TC_MAX_KCH = 12;
 constexpr int TC_CHUNK_BYTES = 128 * 128;   // 128 rows x 64 columns x 2 bytes
@@ -406,6 +411,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
             for (int kc = 0; kc < n_k; ++kc) {
               const uint32_t info = st.kinfo[kc];
               const int src = (info >> 20) & 0xf;
+#if CFN_TC_ISSUE_STAMPS
+              prof.stamp();      // diagnostic build: loop top (scripts/r2_k1_issue.py)
+#endif
               if (src < act_chunks) { if (ready_upto <= src) wait_act(src); }
               else if (((info >> 25) & 1u) && !gd_seen) {   // gamma(d): written several layers ago, returns at once
                 wait_bar(bar_local(&bars->gd_ready), (in_cnt - 1u) & 1u);
@@ -437,6 +445,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
                 }
               }
               __syncwarp();
+#if CFN_TC_ISSUE_STAMPS
+              prof.stamp();      // diagnostic build: after the issue block
+#endif
               cur_full = next_full;
               if (nstage == 0) b_lo = b_lo0; else b_lo += b_step;
               stage = nstage; phase = nphase;
