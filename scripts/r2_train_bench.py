@@ -9,6 +9,9 @@ sys.path.insert(0, ROOT)
 import torch
 
 import cfnerf_b200 as cf
+if os.environ.get("CFN_AB_LIB"):   # same-box A/B against another build of the library
+    import cfnerf_b200._lib as _L
+    _L.LIB_PATH = os.environ["CFN_AB_LIB"]
 from cfnerf_b200 import dist as D
 from oracle import cfnerf_oracle as O
 
