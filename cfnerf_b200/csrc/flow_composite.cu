@@ -265,6 +265,190 @@ flow_composite_fwd_kernel(int F_rt, int K, const float* __restrict__ globals, co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Training forward for SMALL batches: one CTA of 4 warps per ray, warp s walks samples [s N/4, (s+1) N/4).
+// With one warp per ray a 512-ray batch (the reference's N_rand) occupies 512 of the 2 368 warp slots of a B200 and each
+// warp walks 128 dependent samples: the kernel is pure latency (0.114 ms for 512 rays against 0.37 ms for 4096).  The
+// flow stacks - all of the cost - are independent per sample; only the transmittance chains them.  Every warp therefore
+// starts its range at T = 1; the true transmittance is (product of the earlier ranges' final T) x local T, applied
+// afterwards to the range sums (exactly the seg_sums the backward wants), to the outputs and, in place, to `trans`.
+// Same arithmetic per sample as flow_composite_fwd_kernel<TRAIN = true>; the transmittance products associate
+// differently (relative difference ~1e-7).
+template <int MAXV, bool FAST, int FT>
+__global__ void __launch_bounds__(128, 4)
+flow_composite_fwd_seg4_kernel(int F_rt, int K, const float* __restrict__ globals, const float* __restrict__ flow_params,
+                               const float* __restrict__ z_vals, const float* __restrict__ rays_d, int rays_d_stride,
+                               const float* __restrict__ eps_alpha, const float* __restrict__ eps_rgb,
+                               int64_t eps_group_rays, int64_t B, int N, int white_bkgd, float* __restrict__ rgb_map,
+                               float* __restrict__ disp_map, float* __restrict__ depth_map, float* __restrict__ raw,
+                               float* __restrict__ logdet_sums, float* __restrict__ trans, float* __restrict__ seg_sums) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int F = FT > 0 ? FT : F_rt;
+  const int PP = 18 * F;
+  const int per_warp = (kChunk * PP + 3) & ~3;
+  float* sp = smem + warp * per_warp;                 // this warp's chunk of parameters
+  float* sz = smem + 4 * per_warp;                    // z_vals of the ray (shared by the four warps)
+  float* sd = sz + N;                                 // dists * |d|
+  float* sP = sd + N;                                 // [4][32] final local transmittance of each range
+  float* sS = sP + 4 * 32;                            // [4][5][32] scaled range sums
+  float* sL = sS + 4 * 5 * 32;                        // [4][2] log-det sums
+  const int64_t b = blockIdx.x;
+  const int64_t egrp = eps_group_rays > 0 ? b / eps_group_rays : 0;
+  eps_alpha += egrp * K;
+  eps_rgb += egrp * K * 3;
+  for (int n = threadIdx.x; n < N; n += 128) sz[n] = z_vals[b * N + n];
+  const float* d = rays_d + b * rays_d_stride;
+  const float dx = d[0], dy = d[1], dz = d[2];
+  const float norm = sqrtf(dx * dx + dy * dy + dz * dz);
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += 128) sd[n] = ((n < N - 1) ? (sz[n + 1] - sz[n]) : 10.0f) * norm;
+  __syncthreads();
+
+  const float a_mean = globals[0], a_std = globals[1];
+  const float c_mean0 = globals[2], c_mean1 = globals[3], c_mean2 = globals[4];
+  const float c_std0 = globals[5], c_std1 = globals[6], c_std2 = globals[7];
+  const int L = N / 4, n_begin = warp * L;
+  const float* prow = flow_params + (b * N + n_begin) * PP;
+  const int n_chunks = (L + kChunk - 1) / kChunk;
+  const int KG = (K + 31) / 32;
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(prow) & 15) == 0;
+  float ld_a_sum = 0.f, ld_c_sum = 0.f;
+
+  for (int kg = 0; kg < KG; ++kg) {
+    const int k = kg * 32 + lane;
+    const bool active = k < K;
+    const float ea = active ? eps_alpha[k] : 0.f;
+    const float e0 = active ? eps_rgb[k * 3 + 0] : 0.f, e1 = active ? eps_rgb[k * 3 + 1] : 0.f,
+                e2 = active ? eps_rgb[k * 3 + 2] : 0.f;
+    const float za0 = ea * a_std + a_mean;
+    const float zc00 = e0 * c_std0 + c_mean0, zc01 = e1 * c_std1 + c_mean1, zc02 = e2 * c_std2 + c_mean2;
+    float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, depth = 0.f, acc = 0.f;
+
+    float4 stage[MAXV];
+    {
+      const int npts = min(kChunk, L);
+      const int nvf = vec_ok ? ((npts * PP) & ~3) : 0;
+      chunk_load<MAXV>(prow, nvf, lane, stage);
+      __syncwarp();
+      chunk_store<MAXV>(sp, nvf, lane, stage);
+      for (int i = nvf + lane; i < npts * PP; i += 32) sp[i] = prow[i];
+      __syncwarp();
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+      const int n0 = c * kChunk;
+      const int npts = min(kChunk, L - n0);
+      const bool has_next = (c + 1) < n_chunks;
+      const int next_pts = has_next ? min(kChunk, L - n0 - kChunk) : 0;
+      const int next_vf = vec_ok ? ((next_pts * PP) & ~3) : 0;
+      if (has_next) chunk_load<MAXV>(prow + (int64_t)(n0 + kChunk) * PP, next_vf, lane, stage);
+      for (int i = 0; i < npts; ++i) {
+        const int n = n_begin + n0 + i;
+        float rec[FT > 0 ? 18 * FT : 4];
+        const float* P = sp + i * PP;
+        if (FT > 0) {
+#pragma unroll
+          for (int j = 0; j < (18 * FT) / 4; ++j) {
+            const float4 q4 = reinterpret_cast<const float4*>(sp + i * PP)[j];
+            rec[4 * j] = q4.x; rec[4 * j + 1] = q4.y; rec[4 * j + 2] = q4.z; rec[4 * j + 3] = q4.w;
+          }
+          P = rec;
+        }
+        float za = za0, lda = 0.f;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const float d1 = P[f], d2 = P[F + f], bb = P[2 * F + f];
+          const float t = tanh_<FAST>(d2 * za + bb);
+          za += d1 * t;
+          lda += log_<FAST>(fabsf((1.0f - t * t) * (d1 * d2) + 1.0f) + 1e-8f);
+        }
+        float z0 = zc00, z1 = zc01, z2 = zc02, ldc = 0.f;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const float* Q = P + 3 * F + kRgbFlowRec * f;
+          const bool odd = f & 1;
+          const float p0 = odd ? z2 : z0, p1 = z1, p2 = odd ? z0 : z2;
+          const float t0 = tanh_<FAST>(Q[6] * p0 + Q[7] * p1 + Q[8] * p2 + Q[12]);
+          const float t1 = tanh_<FAST>(Q[9] * p1 + Q[10] * p2 + Q[13]);
+          const float t2 = tanh_<FAST>(Q[11] * p2 + Q[14]);
+          const float s0 = Q[0] * t0 + Q[1] * t1 + Q[2] * t2;
+          const float s1 = Q[3] * t1 + Q[4] * t2;
+          const float s2 = Q[5] * t2;
+          z0 += odd ? s2 : s0;
+          z1 += s1;
+          z2 += odd ? s0 : s2;
+          ldc += log_<FAST>(fabsf((1.0f - t0 * t0) * (Q[0] * Q[6]) + 1.0f) + 1e-8f) +
+                 log_<FAST>(fabsf((1.0f - t1 * t1) * (Q[3] * Q[9]) + 1.0f) + 1e-8f) +
+                 log_<FAST>(fabsf((1.0f - t2 * t2) * (Q[5] * Q[11]) + 1.0f) + 1e-8f);
+        }
+        if (active) {
+          ld_a_sum += lda + (za - softplus_<FAST>(za));                                           // models.py:263
+          ld_c_sum += ldc + ((z0 + z1 + z2) - 2.0f * (softplus_<FAST>(z0) + softplus_<FAST>(z1) + softplus_<FAST>(z2)));  // :278
+        }
+        const float alpha = 1.0f - exp_<FAST>(-softplus_<FAST>(za) * sd[n]);
+        const float w = alpha * T;
+        if (active) trans[(b * N + n) * K + k] = T;          // LOCAL transmittance for now; rescaled below
+        T = T * ((1.0f - alpha) + 1e-10f);
+        cr += w * sigmoid_<FAST>(z0);
+        cg += w * sigmoid_<FAST>(z1);
+        cb += w * sigmoid_<FAST>(z2);
+        depth += w * sz[n];
+        acc += w;
+        if (active && raw) reinterpret_cast<float4*>(raw)[(b * N + n) * K + k] = make_float4(z0, z1, z2, za);
+      }
+      __syncwarp();
+      if (has_next) {
+        chunk_store<MAXV>(sp, next_vf, lane, stage);
+        const float* src = prow + (int64_t)(n0 + kChunk) * PP;
+        for (int i = next_vf + lane; i < next_pts * PP; i += 32) sp[i] = src[i];
+      }
+      __syncwarp();
+    }
+    // ---- stitch the four ranges together ----
+    sP[warp * 32 + lane] = T;
+    __syncthreads();
+    float prefix = 1.0f;
+    for (int s2 = 0; s2 < warp; ++s2) prefix *= sP[s2 * 32 + lane];
+    cr *= prefix; cg *= prefix; cb *= prefix; depth *= prefix; acc *= prefix;
+    if (active) {
+      float* o = seg_sums + ((b * 4 + warp) * 5) * K + k;
+      o[0] = cr; o[K] = cg; o[2 * K] = cb; o[3 * K] = depth; o[4 * K] = acc;
+      if (warp > 0)
+        for (int n = n_begin; n < n_begin + L; ++n) trans[(b * N + n) * K + k] *= prefix;   // own writes: L1 / L2 hits
+    }
+    float* my = sS + warp * 160;
+    my[lane] = cr; my[32 + lane] = cg; my[64 + lane] = cb; my[96 + lane] = depth; my[128 + lane] = acc;
+    __syncthreads();
+    if (warp == 0 && active) {
+      float tr = 0.f, tg = 0.f, tb = 0.f, td = 0.f, ta = 0.f;
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2) {
+        const float* q = sS + s2 * 160;
+        tr += q[lane]; tg += q[32 + lane]; tb += q[64 + lane]; td += q[96 + lane]; ta += q[128 + lane];
+      }
+      const float disp = 1.0f / fmaxf(2e-10f, td / (ta + 1e-10f) + 1e-10f);
+      if (white_bkgd) { const float bg = 1.0f - ta; tr += bg; tg += bg; tb += bg; }
+      rgb_map[(b * 3 + 0) * K + k] = tr;
+      rgb_map[(b * 3 + 1) * K + k] = tg;
+      rgb_map[(b * 3 + 2) * K + k] = tb;
+      disp_map[b * K + k] = disp;
+      depth_map[b * K + k] = td;
+    }
+    __syncthreads();     // sP / sS are reused by the next K group
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ld_a_sum += __shfl_xor_sync(0xffffffffu, ld_a_sum, o);
+    ld_c_sum += __shfl_xor_sync(0xffffffffu, ld_c_sum, o);
+  }
+  if (lane == 0) { sL[warp * 2] = ld_a_sum; sL[warp * 2 + 1] = ld_c_sum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    logdet_sums[b * 2 + 0] = (sL[0] + sL[2]) + (sL[4] + sL[6]);
+    logdet_sums[b * 2 + 1] = (sL[1] + sL[3]) + (sL[5] + sL[7]);
+  }
+}
+
 static size_t fwd_smem_bytes(int F, int N) { return (size_t)4 * ((kChunk * 18 * F + 2 * N + 3) & ~3) * sizeof(float); }
 
 int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals, const float* flow_params, const float* z_vals,
@@ -279,6 +463,24 @@ int launch_flow_composite_fwd(int fast_math, int F, int K, const float* globals,
   size_t smem = fwd_smem_bytes(F, N);
   unsigned grid = (unsigned)((B + 3) / 4);
   const bool train = logdet_sums != nullptr;
+  // small training batches: four warps per ray (see flow_composite_fwd_seg4_kernel); CFN_K2_SEG4=0 keeps one warp per ray
+  static const int seg4_env = [] { const char* e = getenv("CFN_K2_SEG4"); return e ? atoi(e) : 1; }();
+  if (train && seg4_env && trans && seg_sums && n_seg == 4 && N % 4 == 0 && !weights && !kstats && B <= 1536 && F <= 4) {
+    const size_t sm4 = ((size_t)4 * ((kChunk * 18 * F + 3) & ~3) + 2 * (size_t)N + 4 * 32 + 4 * 5 * 32 + 8) * sizeof(float);
+#define CFN_SEG4_LAUNCH(FASTM, FTT)                                                                                  \
+    do {                                                                                                             \
+      auto kern = flow_composite_fwd_seg4_kernel<9, FASTM, FTT>;                                                     \
+      if (sm4 > 48 * 1024) CFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4)); \
+      kern<<<(unsigned)B, 128, sm4, s>>>(F, K, globals, flow_params, z_vals, rays_d, rays_d_stride, eps_alpha, eps_rgb, \
+                                         eps_group_rays, B, N, white_bkgd, rgb_map, disp_map, depth_map, raw,        \
+                                         logdet_sums, trans, seg_sums);                                              \
+    } while (0)
+    if (fast_math) { if (F == 4) CFN_SEG4_LAUNCH(true, 4); else CFN_SEG4_LAUNCH(true, 0); }
+    else { if (F == 4) CFN_SEG4_LAUNCH(false, 4); else CFN_SEG4_LAUNCH(false, 0); }
+#undef CFN_SEG4_LAUNCH
+    CFN_LAUNCH_CHECK();
+    return CFN_OK;
+  }
 #define CFN_FWD_LAUNCH(MAXV, TR)                                                                                  \
   do {                                                                                                            \
     auto kern = fast_math ? (F == 4 ? flow_composite_fwd_kernel<MAXV, TR, true, 4> : flow_composite_fwd_kernel<MAXV, TR, true, 0>)\
