@@ -48,5 +48,5 @@ CFN_RAYS=512 CFN_STEPS=3 $T 300 ncu --metrics gpu__time_duration.sum --clock-con
    --log-file $G/${R}_train512_launches.csv python scripts/r2_step512.py > $G/ncu_t512.log 2>&1
 $T 400 python scripts/r2_train_bench.py > $G/r2_train_bench.log 2>&1
 CFN_TC_PROFILE=1 CFN_PRECISION=fp16 $T 200 python scripts/k1_timeline.py $G/k1_timeline.json > $G/${R}_k1_timeline.txt 2>&1
-tail -2 $G/bench.err $G/bench_fern.err $G/bench_lego.err
+for f in $G/bench.err $G/bench_fern.err $G/bench_lego.err; do tail -n 2 $f; done
 cut -c1-400 $G/${R}_bench_fern_1gpu.json; echo; cut -c1-400 $G/${R}_bench_lego_1gpu.json
