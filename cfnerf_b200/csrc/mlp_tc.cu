@@ -28,6 +28,12 @@ namespace cfn {
 
 // -DCFN_TC_ISSUE_STAMPS=1 (CFN_NVCC_EXTRA of cfnerf_b200/build.py): three clock64() stamps per ring slot in the MMA issuer
 // instead of one — the diagnostic build behind scripts/r2_k1_issue.py; the stamps cost ~10 % of the kernel.
+// -DCFN_TC_TIMELINE=1: the clock64() stamps behind scripts/k1_timeline.py / r2_k1_ring.py (CFN_TC_PROFILE=1 at run time).
+// Compiled OUT by default: predicated off they still cost 1.8 % of the kernel (same-box A/B, 17.36 -> 17.04 ms) - the
+// single-warp producer / issuer loops are that sensitive to their instruction count.
+#ifndef CFN_TC_TIMELINE
+#define CFN_TC_TIMELINE 0
+#endif
 #ifndef CFN_TC_ISSUE_STAMPS
 #define CFN_TC_ISSUE_STAMPS 0
 #endif
@@ -188,7 +194,9 @@ constexpr int TC_PROF_N = 4096;
 struct Prof {
   unsigned long long* p; int n;
   __device__ __forceinline__ void stamp() {
+#if CFN_TC_TIMELINE
     if (p && n < TC_PROF_N) p[n++] = clock64();
+#endif
   }
 };
 
@@ -378,14 +386,6 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
       const uint32_t b_step = (uint32_t)a.stage_bytes >> 4;
       uint32_t b_lo = b_lo0;
       bool cur_full = false;            // the full barrier of `stage` is already known complete
-      // number of weight blocks this CTA pair will consume (to know when there is no "next stage" to probe)
-      int64_t blocks_left = 0;
-      {
-        int per_tile = 0;
-        for (int g = 0; g < plan.n_steps; ++g) per_tile += plan.steps[g].n_parts * plan.steps[g].n_k;
-        const int64_t my_tiles = (a.n_units > unit0) ? (a.n_units - unit0 + n_grid_units - 1) / n_grid_units : 0;
-        blocks_left = my_tiles * per_tile;
-      }
       for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
         wait_bar(bar_local(&bars->in_ready), in_cnt & 1u); ++in_cnt;
         gd_seen = false;
@@ -426,7 +426,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
               // the NEXT slot's weights: probed now, so that the barrier round trip overlaps the issue of this slot
               const int nstage = (stage + 1 == a.stages) ? 0 : stage + 1;
               const uint32_t nphase = (stage + 1 == a.stages) ? (phase ^ 1u) : phase;
-              const bool next_full = (--blocks_left > 0) ? mbar_probe(full_bar0 + 8u * nstage, nphase) : false;
+              // (after the very last block this probes a phase that never completes: the short probe just returns false)
+              const bool next_full = mbar_probe(full_bar0 + 8u * nstage, nphase);
               if (elect_one()) {
                 const uint32_t nks = (info >> 16) & 0xfu;
                 const uint32_t acc = kc > 0 ? 1u : 0u;

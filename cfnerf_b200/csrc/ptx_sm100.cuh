@@ -65,11 +65,16 @@ static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) 
          (int)blockIdx.x, (int)threadIdx.x, bar, parity);
   __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait_sleep(bar, parity)) return;
+// The retry loop with its clock reads is OUT of line: inlined at every wait site it put ~20 cold instructions into the hot
+// loops of single-warp roles whose instruction stream sets the pace of the kernel.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const uint64_t t0 = globaltimer_ns();
   while (!mbar_try_wait_sleep(bar, parity))
     if (globaltimer_ns() - t0 > kMbarTimeoutNs) mbar_timeout(bar, parity);
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_sleep(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -19,7 +19,7 @@ if [ "${1:-}" = "summarize" ]; then
   python scripts/ncu_summary.py list $G/${R}_train4096_launches.csv $P/${R}_train_launch_summary.csv
   python scripts/ncu_summary.py list $G/${R}_train512_launches.csv $P/${R}_train512_launch_summary.csv
   cp $G/r2_train_bench.json $P/${R}_train_bench.json
-  cp $G/${R}_k1_timeline.txt $P/${R}_k1_timeline.txt
+  grep -q "tile total" $G/${R}_k1_timeline.txt 2>/dev/null && cp $G/${R}_k1_timeline.txt $P/${R}_k1_timeline.txt
   exit 0
 fi
 mkdir -p $G
@@ -47,6 +47,8 @@ CFN_RAYS=4096 CFN_STEPS=3 $T 300 ncu --metrics gpu__time_duration.sum --clock-co
 CFN_RAYS=512 CFN_STEPS=3 $T 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
    --log-file $G/${R}_train512_launches.csv python scripts/r2_step512.py > $G/ncu_t512.log 2>&1
 $T 400 python scripts/r2_train_bench.py > $G/r2_train_bench.log 2>&1
-CFN_TC_PROFILE=1 CFN_PRECISION=fp16 $T 200 python scripts/k1_timeline.py $G/k1_timeline.json > $G/${R}_k1_timeline.txt 2>&1
+# (needs the diagnostic build of the library, -DCFN_TC_TIMELINE=1; with the shipped one it only prints how to build it)
+CFN_TC_PROFILE=1 CFN_PRECISION=fp16 $T 200 python scripts/k1_timeline.py $G/k1_timeline.json > $G/${R}_k1_timeline_new.txt 2>&1
+grep -q "tile total" $G/${R}_k1_timeline_new.txt && mv $G/${R}_k1_timeline_new.txt $G/${R}_k1_timeline.txt
 for f in $G/bench.err $G/bench_fern.err $G/bench_lego.err; do tail -n 2 $f; done
 cut -c1-400 $G/${R}_bench_fern_1gpu.json; echo; cut -c1-400 $G/${R}_bench_lego_1gpu.json

@@ -1,5 +1,7 @@
 """Diagnostic: per-step timeline of the tensor-core network kernel (CTA 0) from its clock64() stamps.
-Run on the GPU box:  CFN_TC_PROFILE=1 python scripts/k1_timeline.py [out.json]"""
+The stamps are compiled OUT of the shipped library (even predicated off they cost 1.8 % of the kernel); build the
+diagnostic library first:   CFN_NVCC_EXTRA=-DCFN_TC_TIMELINE=1 python -m cfnerf_b200.build --force
+then on the GPU box:         CFN_TC_PROFILE=1 python scripts/k1_timeline.py [out.json]"""
 import ctypes as C
 import json
 import os
@@ -33,6 +35,8 @@ out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/k1_timeline.json"
 os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
 json.dump(roles, open(out, "w"))
 ep = roles["epilogue"]
+if not ep:
+    sys.exit("no stamps: this library was built without -DCFN_TC_TIMELINE=1 (see the docstring)")
 # epilogue stamps per tile: tile start, after encode, then per step (after acc_full wait, after epilogue) -> 2 + 2*steps
 n_steps = 12
 per_tile = 2 + 2 * n_steps

@@ -1,6 +1,6 @@
 """Diagnostic: where the MMA issuer of K1 spends its time per ring slot (three stamps per slot: loop top, after the
 waits, after the issue).  Needs the diagnostic build of the library:
-    CFN_NVCC_EXTRA=-DCFN_TC_ISSUE_STAMPS=1 python -m cfnerf_b200.build --force      (here; the .so travels with gpurun)
+    CFN_NVCC_EXTRA='-DCFN_TC_TIMELINE=1 -DCFN_TC_ISSUE_STAMPS=1' python -m cfnerf_b200.build --force      (here; the .so travels with gpurun)
 then on the GPU box:  CFN_TC_PROFILE=1 python scripts/r2_k1_issue.py"""
 import ctypes as C, json, os, sys
 os.environ.setdefault("CFN_TC_PROFILE", "1")

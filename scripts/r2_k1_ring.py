@@ -1,5 +1,6 @@
 """Diagnostic: K1's per-K-chunk MMA issue cadence (clock64 stamps of the issuer warp of CTA 0) as a function of the
-weight-ring depth.  CFN_W = netwidth, CFN_TC_STAGES caps the ring.  Run on the GPU box with CFN_TC_PROFILE=1."""
+weight-ring depth.  CFN_W = netwidth, CFN_TC_STAGES caps the ring.  Needs the diagnostic build of the library
+(CFN_NVCC_EXTRA=-DCFN_TC_TIMELINE=1 python -m cfnerf_b200.build --force); run on the GPU box with CFN_TC_PROFILE=1."""
 import ctypes as C
 import json
 import os
