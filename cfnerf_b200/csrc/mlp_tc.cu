@@ -384,6 +384,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
       const uint32_t a_lo0 = ((act_base & 0x3FFFFu) >> 4) | (1u << 16);           // + LBO field (ignored for swizzled K-major)
       const uint32_t b_lo0 = ((stage_base & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t b_step = (uint32_t)a.stage_bytes >> 4;
+      const int n_stages = a.stages;      // a register copy: the asm memory clobbers made every use a fresh constant load
       uint32_t b_lo = b_lo0;
       bool cur_full = false;            // the full barrier of `stage` is already known complete
       for (int64_t unit = unit0; unit < a.n_units; unit += n_grid_units) {
@@ -424,8 +425,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
               tc_fence_after();
               const uint32_t a_lo = a_lo0 + (info & 0xffffu);
               // the NEXT slot's weights: probed now, so that the barrier round trip overlaps the issue of this slot
-              const int nstage = (stage + 1 == a.stages) ? 0 : stage + 1;
-              const uint32_t nphase = (stage + 1 == a.stages) ? (phase ^ 1u) : phase;
+              const int nstage = (stage + 1 == n_stages) ? 0 : stage + 1;
+              const uint32_t nphase = (stage + 1 == n_stages) ? (phase ^ 1u) : phase;
               // (after the very last block this probes a phase that never completes: the short probe just returns false)
               const bool next_full = mbar_probe(full_bar0 + 8u * nstage, nphase);
               if (elect_one()) {
@@ -648,25 +649,24 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
           // software pipeline over this warp's (chunk, half) pieces: the next TMEM load is in flight while the
           // current 32 columns are biased, activated, packed and stored
           uint32_t va[32], vb[32];
+          // (the ReLU decision is taken ONCE per 32-column piece from a register: tested per 8 columns through the
+          // schedule in the parameter bank it was an indexed constant load and a branch in front of every store)
+          const bool relu = st.kind == 0;
           auto process = [&](uint32_t (&v)[32], int j, int half) {
             const uint32_t chunk = act_base + j * TC_CHUNK_BYTES;
+            uint32_t pk[16];
+            if (relu) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float x0 = __uint_as_float(v[8 * u + 0]), x1 = __uint_as_float(v[8 * u + 1]);
-              const float x2 = __uint_as_float(v[8 * u + 2]), x3 = __uint_as_float(v[8 * u + 3]);
-              const float x4 = __uint_as_float(v[8 * u + 4]), x5 = __uint_as_float(v[8 * u + 5]);
-              const float x6 = __uint_as_float(v[8 * u + 6]), x7 = __uint_as_float(v[8 * u + 7]);
-              uint32_t p0, p1, p2, p3;
-              if (st.kind == 0) {
-                p0 = pack2<FP16, true>(x0, x1); p1 = pack2<FP16, true>(x2, x3);
-                p2 = pack2<FP16, true>(x4, x5); p3 = pack2<FP16, true>(x6, x7);
-              } else {
-                p0 = pack2<FP16, false>(x0, x1); p1 = pack2<FP16, false>(x2, x3);
-                p2 = pack2<FP16, false>(x4, x5); p3 = pack2<FP16, false>(x6, x7);
-              }
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};"
-                           :: "r"(chunk + swz(row, half * 4 + u)), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+              for (int i = 0; i < 16; ++i) pk[i] = pack2<FP16, true>(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = pack2<FP16, false>(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};"
+                           :: "r"(chunk + swz(row, half * 4 + u)), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+                           : "memory");
           };
           // chunks [j0, j1) of this warp's parity; wait_free: output chunk j overwrites input chunk j, which the second
           // part's MMAs may still be reading (split-commit steps)
