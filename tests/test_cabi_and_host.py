@@ -53,6 +53,8 @@ def test_no_cpu_fallback():
         cf.raw2outputs(torch.zeros(1, 4, 2, 4), torch.zeros(1, 4), torch.zeros(1, 3))
     with pytest.raises(RuntimeError):
         net(torch.zeros(2, 90))
+    with pytest.raises(RuntimeError):
+        cf.render_rays_host(O.synthetic_rays(4), net, 128, K_samples=4)
 
 
 def test_param_container_matches_reference_state_dict_layout():
