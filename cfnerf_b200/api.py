@@ -308,6 +308,18 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=128, is_
         raise ValueError("ray_batch must be (B,11) = [o d near far viewdir] (use_viewdirs, main:504-507)")
     B = rays.shape[0]
     hier = N_importance > 0 and network_fine is not None
+    if B == 0 and not is_train:
+        # an empty ray batch (a ragged last shard): empty maps of the right shapes, no launches
+        K, f32 = eng.K, dict(dtype=torch.float32, device=dev)
+        ret = {"rgb_map": torch.empty(0, 3, K, **f32), "disp_map": torch.empty(0, K, **f32), "depth_map": torch.empty(0, K, **f32)}
+        if hier:
+            ret.update(rgb0=torch.empty(0, 3, K, **f32), disp0=torch.empty(0, K, **f32), depth0=torch.empty(0, K, **f32),
+                       z_samples=torch.empty(0, N_importance, **f32), z_vals=torch.empty(0, N_samples + N_importance, **f32))
+        if want_weights:
+            ret["weights"] = torch.empty(0, N_samples + (N_importance if hier else 0), K, **f32)
+        if want_kstats:
+            ret["kstats"] = torch.empty(0, 8, **f32)
+        return ret
     with torch.cuda.device(dev):
         t_vals = reference_t_schedule(N_samples, dev)
         if perturb > 0. and t_rand is None:
@@ -447,6 +459,9 @@ def render_rays_host(rays_host, network_fn, N_samples=128, chunk=1024 * 32, keys
         if side is None:
             side = _COPY_STREAMS[dev] = torch.cuda.Stream(dev)
         out = {} if out is None else out
+        if B == 0:
+            o = render_rays(rays_host.to(dev), network_fn, None, N_samples, False, False, **render_kwargs)
+            return {k: o[k].cpu() for k in keys}
         for i in range(0, B, chunk):
             n = min(chunk, B - i)
             r = rays_host[i:i + n].to(dev, non_blocking=True)

@@ -637,6 +637,26 @@ def test_render_image_equals_render_rays_on_the_same_rays(cf, dev):
 # ------------------------------------------------------------------------------------------------
 # F1: fused K-reduction + KDE-NLL loss and its gradient
 # ------------------------------------------------------------------------------------------------
+def test_render_rays_empty_and_tiny_batches(cf, dev):
+    """Ragged shards: an empty ray batch returns empty maps of the right shapes (no launch), a single ray and a batch that
+    straddles a 128-point tile boundary match the rows of a larger batch bit for bit."""
+    cfg = O.CfnConfig()
+    p = O.make_params(cfg, 2, "lively")
+    sa, sr = O.make_latents(cfg, 2)
+    net = make_net(cf, cfg, p, sa, sr, dev)
+    rays = O.synthetic_rays(130, 5).to(dev)
+    for prec in ("fp16", "fp32"):
+        full = cf.render_rays(rays, net, None, 128, False, False, K_samples=cfg.K, precision=prec, want_kstats=True)
+        empty = cf.render_rays(rays[:0], net, None, 128, False, False, K_samples=cfg.K, precision=prec, want_kstats=True)
+        assert empty["rgb_map"].shape == (0, 3, cfg.K) and empty["depth_map"].shape == (0, cfg.K) and empty["kstats"].shape == (0, 8)
+        for B in (1, 129):
+            part = cf.render_rays(rays[:B], net, None, 128, False, False, K_samples=cfg.K, precision=prec, want_kstats=True)
+            for k in ("rgb_map", "disp_map", "depth_map", "kstats"):
+                assert torch.equal(part[k], full[k][:B]), (prec, B, k)
+    h = cf.render_rays_host(rays[:0].cpu(), net, 128, K_samples=cfg.K)
+    assert h["rgb_map"].shape == (0, 3, cfg.K)
+
+
 def test_render_rays_host_pipeline_equals_render_rays(cf, dev):
     """The host-in / host-out pipeline (H2D, render, D2H on a second stream, chunk by chunk) returns, in pinned host
     memory, bit for bit what one render_rays call on the device returns; a ragged last chunk and buffer reuse included."""
