@@ -928,6 +928,7 @@ int tc_create(CfnHandle* h) {
   }
   // staging the last step's record rows needs 128 x (15F+1) floats in the upper half of the activation tile
   dev.stage_out = ((size_t)128 * (15 * F + 1) * sizeof(float) <= (size_t)(AC - AC / 2) * TC_CHUNK_BYTES) ? 1 : 0;
+  if (const char* e = getenv("CFN_TC_STAGE_OUT")) dev.stage_out = dev.stage_out && atoi(e) != 0;   // A/B timing
   p->stream_rows = stream_row;
   p->table_floats = table_off;
 
