@@ -609,8 +609,25 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant_
                 const float x = __uint_as_float(v[t][i]) + bb[i];
                 o[i] = (ff[i] != 0.f) ? tanh_fast(x) : x;
               }
+              // unstaged rows: 16-byte stores where the whole quad is valid (record rows are 16-byte aligned: PP = 18F floats,
+              // out_col = 3F) instead of sixteen 4-byte ones
+              const bool vec_rows = !staged && ((a.PP | st.out_col) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.flow_params) & 15) == 0;
+              if (vec_rows) {
+                if (valid) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) emit(gi * 16 + i, o[i]);
+                  for (int i = 0; i < 4; ++i) {
+                    const int c = gi * 16 + 4 * i;
+                    if (c + 3 < st.n_valid) *reinterpret_cast<float4*>(out + c) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    else {
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) if (c + j < st.n_valid) out[c + j] = o[4 * i + j];
+                    }
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) emit(gi * 16 + i, o[i]);
+              }
             }
           }
           prof2.stamp();
