@@ -14,8 +14,9 @@ Configs (BASELINE.json `configs`):
   lego    configs[4]: 800x800 views on the pose_spherical circle (200 views), K=128, white background; views go round
           robin over the GPUs, a step renders one view per GPU (weak scaling).
 
-`value` times the device-resident path (rays in HBM -> K-field maps + mean/std/depth in HBM); `e2e` times the same public
-`render_rays` call with host-pinned rays in and the K fields + statistics copied back out.  `roofline` is the dominant
+`value` times the device-resident path (rays in HBM -> K-field maps + mean/std/depth in HBM); `e2e` times the public
+host-in / host-out call `render_rays_host` (pinned host rays in, the K fields + statistics back in pinned host memory; the
+device-to-host copies of a chunk overlap the kernels of the next one).  `roofline` is the dominant
 kernel (the tcgen05 network stage K1) against the measured dense bf16 peak, timed with CUDA events inside the timed
 region; `roofline.kernels` adds the streaming kernels (raw2outputs, sample_pdf, flows+compositing forward / backward)
 measured in the same run.  `cpu_baseline` is the UNMODIFIED reference (oracle/_ref, staged by oracle/build_ref.py) on a
